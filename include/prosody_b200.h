@@ -1,0 +1,155 @@
+/*
+ * prosody_b200.h — C ABI of libprosody_b200.so (hand-written sm_100a CUDA behind plain pointers and sizes).
+ *
+ * The reference (hi-paris/Prosody-Control-French-TTS) has no FFI: its hot path is four Python closures
+ * inside AudioPipeline.measure_prosody_and_build_ssml that call parselmouth / pyloudnorm / pydub once per
+ * (wav file, t0, t1).  Each entry point below is the BATCHED form of one of those closures; the units of
+ * work are the reference's own call arguments (file, t0, t1[, meter rate]) in float64 seconds.
+ *
+ *   pb_median_pitch_batch   <- get_median_pitch(wav, t0, t1)      Code/audioPipeline.py:326-335
+ *   pb_lufs_batch           <- get_lufs(wav, meter, t0, t1)       Code/audioPipeline.py:338-358
+ *   pb_part_duration_batch  <- get_part_duration(wav, t0, t1)     Code/audioPipeline.py:314-323
+ *                              get_duration(wav)                  Code/audioPipeline.py:360-361
+ *   pb_extract_batch        <- the four above for one list of units, host PCM in, host records out
+ *                              (what one pass of the step's loops :375-400 / :495-521 needs per unit)
+ *   pb_intensity_batch      <- Sound.to_intensity()               Code/visualisation/Compare_speech_noenhanced.py:19-26
+ *
+ * Conventions
+ *   - All functions return PB_OK (0) or a PB_E* code; pb_last_error(h) gives the message.
+ *   - A "file" is mono 16-bit PCM (what the reference pipeline writes); all files of a call live in one
+ *     concatenated int16 buffer, file f occupying [file_off[f], file_off[f]+file_nx[f]).
+ *   - `pcm_on_device` selects whether `pcm` is a device pointer (HBM-resident input) or a host pointer
+ *     (the library stages it through its own stream; pin it for full PCIe speed).
+ *   - Unit descriptors and per-unit results are HOST arrays owned by the caller.  Optional per-frame outputs
+ *     are host arrays sized with pb_pitch_plan().
+ *   - The library owns only the handle: tables per analysis geometry and a scratch arena that grows on demand.
+ *     A handle is bound to one device and one stream and is not thread-safe; use one per GPU.
+ *   - There is no CPU fallback: without a CUDA device pb_create fails with PB_ENODEVICE.
+ */
+#ifndef PROSODY_B200_H
+#define PROSODY_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+
+enum {
+    PB_OK = 0,
+    PB_EINVAL = 1,      /* bad argument */
+    PB_ENODEVICE = 2,   /* no usable CUDA device */
+    PB_ECUDA = 3,       /* CUDA runtime error (message in pb_last_error) */
+    PB_ENOMEM = 4,
+    PB_EUNSUPPORTED = 5 /* geometry outside the kernels' compiled range */
+};
+
+/* per-unit status (what the reference's third-party call would have done) */
+enum {
+    PB_UNIT_OK = 0,
+    PB_UNIT_TOO_SHORT = 1,     /* Praat throws: slice shorter than periods_per_window / pitch_floor */
+    PB_UNIT_NO_SAMPLES = 2,    /* Praat throws: extracted Sound would contain no samples */
+    PB_UNIT_WINDOW = 3,        /* Praat throws: analysis window too short */
+    PB_UNIT_LUFS_FALLBACK = 16,/* flag: slice empty or < 0.4 s -> whole-file loudness (audioPipeline.py:345-358) */
+    PB_UNIT_LUFS_ERROR = 32,   /* even the whole file is < 0.4 s: pyloudnorm ValueError escapes */
+    PB_UNIT_SLICE_ERROR = 64   /* pydub TooManyMissingFrames */
+};
+
+typedef struct PbHandle PbHandle;
+
+/* parselmouth Sound.to_pitch(time_step, pitch_floor, pitch_ceiling) == Praat Sound_to_Pitch_ac with the
+ * remaining arguments at Praat's defaults; all of them are exposed so the legacy callers
+ * (Code/Pipeline/compute_pitch_adjustments.py:191-199) can be served too. */
+typedef struct PbPitchParams {
+    double time_step;            /* 0 -> auto = periods_per_window / pitch_floor / 4 */
+    double pitch_floor;          /* reference: 150 */
+    double pitch_ceiling;        /* reference: 600 */
+    double periods_per_window;   /* 3.0 */
+    double silence_threshold;    /* 0.03 */
+    double voicing_threshold;    /* 0.45 */
+    double octave_cost;          /* 0.01 */
+    double octave_jump_cost;     /* 0.35 */
+    double voiced_unvoiced_cost; /* 0.14 */
+    int32_t max_candidates;      /* 15 */
+    int32_t reserved;
+} PbPitchParams;
+
+/* One unit of work = one call of a reference closure. SoA, host memory, n_units entries each. */
+typedef struct PbUnits {
+    int64_t n_units;
+    const int64_t* file_off;   /* sample offset of the unit's file inside pcm */
+    const int64_t* file_nx;    /* samples in that file */
+    const double* rate;        /* file sample rate (Hz) */
+    const int32_t* has_t1;     /* 0: whole file (t1 is None); 1: slice [t0, t1] */
+    const double* t0;          /* seconds (the reference passes start_ms/1000) */
+    const double* t1;
+    const double* meter_rate;  /* pyln.Meter(rate) the reference built for this call; may be NULL for pitch-only */
+} PbUnits;
+
+/* kernel timings of the last batch call, measured with CUDA events on the handle's stream */
+typedef struct PbTimings {
+    float total_ms;        /* first enqueue .. last result on host */
+    float h2d_ms;          /* PCM + descriptor upload */
+    float unit_stats_ms;   /* K0: per-unit mean / global peak */
+    float frames_ms;       /* K1+K2: framing, FFT autocorrelation, candidates (dominant kernel) */
+    float path_ms;         /* K3: Viterbi path finder + median of voiced */
+    float lufs_ms;         /* K4: K-weighting + gated loudness */
+    float intensity_ms;    /* K4b */
+    float d2h_ms;
+    int64_t n_frames;      /* pitch frames analysed */
+    int64_t n_lufs_samples;/* samples filtered */
+    int32_t n_launches;    /* kernels launched */
+    int32_t reserved;
+} PbTimings;
+
+int pb_abi_version(void);
+int pb_create(int device, PbHandle** out);
+void pb_destroy(PbHandle* h);
+const char* pb_last_error(const PbHandle* h);
+/* stream: a cudaStream_t to enqueue on (0 -> the handle's own non-blocking stream) */
+int pb_set_stream(PbHandle* h, void* stream);
+int pb_get_timings(const PbHandle* h, PbTimings* out);
+int pb_device_info(const PbHandle* h, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* total_mem);
+
+void pb_pitch_params_default(PbPitchParams* p);
+
+/* Host-only planning: what Praat would do with each unit (status) and how many frames it yields.
+ * frame_off (n_units+1 entries, may be NULL) receives the exclusive prefix sum of n_frames over OK units. */
+int pb_pitch_plan(const PbPitchParams* p, const PbUnits* u, int32_t* status, int32_t* n_frames, int64_t* frame_off);
+
+/* get_median_pitch, batched.  Outputs (host): median_f0 (0.0 when no voiced frame), n_voiced, n_frames, status.
+ * Optional per-frame outputs (host, frame_off[n_units] entries, layout given by pb_pitch_plan): f0 / strength
+ * of the selected candidate (parselmouth selected_array), intensity = Praat's relative frame intensity. */
+int pb_median_pitch_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
+                          const PbUnits* u, const PbPitchParams* p,
+                          double* median_f0, int32_t* n_voiced, int32_t* n_frames, int32_t* status,
+                          float* frame_f0, float* frame_strength, float* frame_intensity);
+
+/* get_lufs, batched (pydub ms slicing, peak normalisation, pyloudnorm K-weighted gated loudness, and the
+ * reference's two whole-file fallbacks).  lufs may be -inf exactly where pyloudnorm returns -inf. */
+int pb_lufs_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
+                  const PbUnits* u, double* lufs, int32_t* status);
+
+/* get_part_duration / get_duration, batched (host arithmetic only; h may be NULL). */
+int pb_part_duration_batch(const PbUnits* u, double* duration_s, int32_t* status);
+
+/* Everything one pass of the step needs for its units. want_* select the work; outputs may be NULL when
+ * not wanted.  This is the call the end-to-end benchmark times with host PCM. */
+int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
+                     const PbUnits* u, const PbPitchParams* p,
+                     const uint8_t* want_pitch, const uint8_t* want_lufs,
+                     double* median_f0, int32_t* n_voiced, int32_t* n_frames,
+                     double* lufs, double* duration_s, int32_t* status);
+
+/* Praat Sound_to_Intensity (parselmouth Sound.to_intensity(minimum_pitch=100, time_step=0, subtract_mean=True)),
+ * whole files only.  n_frames[f] / frame_off from pb_intensity_plan; intensity_db has frame_off[n] entries. */
+int pb_intensity_plan(const PbUnits* u, double minimum_pitch, double time_step, int32_t* status,
+                      int32_t* n_frames, int64_t* frame_off, double* t_first, double* dt);
+int pb_intensity_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
+                       const PbUnits* u, double minimum_pitch, double time_step, int subtract_mean,
+                       float* intensity_db, int32_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROSODY_B200_H */

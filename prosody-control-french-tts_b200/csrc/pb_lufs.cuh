@@ -1,0 +1,218 @@
+// pb_lufs.cuh — device code of the loudness path (K4) and Praat frame intensity (K4b).
+//
+// get_lufs (/root/reference/Code/audioPipeline.py:338-358): samples / max|samples| -> pyloudnorm
+// Meter(rate).integrated_loudness: K-weighting (RBJ high-shelf then high-pass biquad, scipy.lfilter, float64),
+// 400 ms blocks every 100 ms, absolute (-70 LUFS) and relative (-10 LU) gates.
+//
+// The IIR cascade is a 4-state linear recurrence.  Instead of one sequential pass per unit it is evaluated as a
+// chunk-parallel scan: the 100 ms hops of pyloudnorm's block grid are the chunks; (1) every chunk is filtered
+// from a zero state to get its state contribution, (2) a tiny per-unit pass chains the chunk states with the
+// precomputed transition matrix A^L, (3) every chunk is filtered again from its true initial state while
+// accumulating the energy of the weighted signal.  Block j is exactly chunks j..j+3 because pyloudnorm's upper
+// bound int(T_g*(j*step+1)*rate) is the lower bound of block j+4 evaluated on the same float64 operands.
+// All filter state is float64 (the 38 Hz high-pass has a double pole at radius ~0.99).
+#pragma once
+#include "pb_rt.h"
+#include <math.h>
+
+#define PB_LUFS_NM 6          // transition matrices A^(L0) .. A^(L0+NM-1) kept per meter rate
+
+struct PbMeterDev {           // one per distinct pyln.Meter(rate)
+    double b1[3], a1[3];      // high shelf  (a[0] == 1)
+    double b2[3], a2[3];      // high pass
+    double rate;
+    int32_t L0;               // smallest chunk length with a precomputed transition matrix
+    int32_t pad;
+    double M[PB_LUFS_NM][16]; // row-major 4x4, M[k] = A^(L0+k) on the state (p0,p1,q0,q1)
+};
+
+struct PbLufsUnitDev {
+    int64_t pcm_off;          // file start in the pcm buffer
+    int64_t a, b;             // real samples [a, b) of the file ...
+    int64_t npad;             // ... followed by npad zeros (pydub's missing-frame padding)
+    int64_t chunk_off;        // first chunk of this unit in the chunk arrays
+    int32_t n_chunks;         // numBlocks + 3
+    int32_t n_blocks;
+    int32_t meter;            // index into the meter table
+    int32_t out_index;
+    double inv_peak;          // filled by the peak kernel: 1 / (max|x| or 1.0)
+};
+
+// chunk boundary c of a unit: int(T_g * (c * step) * rate) clipped to n (numpy slice clipping)
+__device__ __forceinline__ long long pb_lufs_bound(int c, double rate, long long n) {
+    const double v = __dmul_rn(__dmul_rn(0.4, __dmul_rn((double)c, 0.25)), rate);
+    long long l = (long long)v;
+    return l > n ? n : l;
+}
+
+__global__ void __launch_bounds__(256) pb_lufs_peak_kernel(const int16_t* __restrict__ pcm, PbLufsUnitDev* __restrict__ units, int n_units) {
+    __shared__ int s_max[8];
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const PbLufsUnitDev ud = units[u];
+        const int16_t* p = pcm + ud.pcm_off;
+        int mx = 0;
+        for (long long i = ud.a + threadIdx.x; i < ud.b; i += blockDim.x) { int v = p[i]; v = v < 0 ? -v : v; mx = max(mx, v); }
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(PB_FULL_MASK, mx, o));
+        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nwarp = (blockDim.x + 31) >> 5;
+            for (int k = 1; k < nwarp; k++) mx = max(mx, s_max[k]);
+            units[u].inv_peak = mx > 0 ? 1.0 / (double)mx : 1.0;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int pb_lufs_find_unit(const PbLufsUnitDev* __restrict__ units, int n, long long chunk) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (units[mid].chunk_off <= chunk) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// Filters one chunk. ENERGY=false: from a zero state, returns the final state. ENERGY=true: from state_io, returns sum y^2.
+template <bool ENERGY>
+__global__ void __launch_bounds__(128)
+pb_lufs_chunk_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
+                     const PbMeterDev* __restrict__ meters, long long n_chunks_total,
+                     double* __restrict__ state /* [n_chunks][4] */, double* __restrict__ energy /* [n_chunks] */) {
+    for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < n_chunks_total; ch += (long long)gridDim.x * blockDim.x) {
+        const int u = pb_lufs_find_unit(units, n_units, ch);
+        const PbLufsUnitDev ud = units[u];
+        const PbMeterDev* __restrict__ mt = meters + ud.meter;
+        const int c = (int)(ch - ud.chunk_off);
+        const long long nreal = ud.b - ud.a, n = nreal + ud.npad;
+        const long long lo = pb_lufs_bound(c, mt->rate, n), hi = pb_lufs_bound(c + 1, mt->rate, n);
+        const double b10 = mt->b1[0], b11 = mt->b1[1], b12 = mt->b1[2], a11 = mt->a1[1], a12 = mt->a1[2];
+        const double b20 = mt->b2[0], b21 = mt->b2[1], b22 = mt->b2[2], a21 = mt->a2[1], a22 = mt->a2[2];
+        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0, e = 0.0;
+        if (ENERGY) { p0 = state[ch * 4 + 0]; p1 = state[ch * 4 + 1]; q0 = state[ch * 4 + 2]; q1 = state[ch * 4 + 3]; }
+        const int16_t* __restrict__ p = pcm + ud.pcm_off + ud.a;
+        const double ip = ud.inv_peak;
+        for (long long i = lo; i < hi; i++) {
+            const double x = i < nreal ? (double)p[i] * ip : 0.0;
+            // scipy.signal.lfilter, direct form II transposed
+            const double y1 = b10 * x + p0;
+            p0 = b11 * x - a11 * y1 + p1;
+            p1 = b12 * x - a12 * y1;
+            const double y2 = b20 * y1 + q0;
+            q0 = b21 * y1 - a21 * y2 + q1;
+            q1 = b22 * y1 - a22 * y2;
+            if (ENERGY) e += y2 * y2;
+        }
+        if (ENERGY) energy[ch] = e;
+        else { state[ch * 4 + 0] = p0; state[ch * 4 + 1] = p1; state[ch * 4 + 2] = q0; state[ch * 4 + 3] = q1; }
+    }
+}
+
+// Per unit: turn the zero-state chunk contributions into true initial states: s_in[c+1] = A^len(c) s_in[c] + s_zs[c].
+__global__ void __launch_bounds__(128)
+pb_lufs_scan_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const PbMeterDev* __restrict__ meters, double* __restrict__ state) {
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        const PbLufsUnitDev ud = units[u];
+        const PbMeterDev* __restrict__ mt = meters + ud.meter;
+        const long long n = (ud.b - ud.a) + ud.npad;
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int c = 0; c < ud.n_chunks; c++) {
+            double* st = state + (ud.chunk_off + c) * 4;
+            const double z0 = st[0], z1 = st[1], z2 = st[2], z3 = st[3];     // zero-state contribution of chunk c
+            st[0] = s[0]; st[1] = s[1]; st[2] = s[2]; st[3] = s[3];          // becomes its initial state
+            const long long lo = pb_lufs_bound(c, mt->rate, n), hi = pb_lufs_bound(c + 1, mt->rate, n);
+            int len = (int)(hi - lo);
+            // s <- A^len s
+            int k = len - mt->L0;
+            if (k >= 0) {
+                int extra = 0;
+                if (k >= PB_LUFS_NM) { extra = k - (PB_LUFS_NM - 1); k = PB_LUFS_NM - 1; }
+                const double* M = mt->M[k];
+                double t[4];
+                for (int r = 0; r < 4; r++) t[r] = M[r * 4 + 0] * s[0] + M[r * 4 + 1] * s[1] + M[r * 4 + 2] * s[2] + M[r * 4 + 3] * s[3];
+                for (int r = 0; r < 4; r++) s[r] = t[r];
+                len = extra;
+            }
+            for (int i = 0; i < len; i++) {       // short (clipped) chunks: step the homogeneous recurrence
+                const double y1 = s[0];
+                const double np0 = -mt->a1[1] * y1 + s[1], np1 = -mt->a1[2] * y1;
+                const double y2 = mt->b2[0] * y1 + s[2];
+                const double nq0 = mt->b2[1] * y1 - mt->a2[1] * y2 + s[3], nq1 = mt->b2[2] * y1 - mt->a2[2] * y2;
+                s[0] = np0; s[1] = np1; s[2] = nq0; s[3] = nq1;
+            }
+            s[0] += z0; s[1] += z1; s[2] += z2; s[3] += z3;
+        }
+    }
+}
+
+// Per unit: block energies from 4 consecutive chunks, the two gates, LUFS (pyloudnorm meter.py).
+__global__ void __launch_bounds__(128)
+pb_lufs_gate_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const PbMeterDev* __restrict__ meters,
+                    const double* __restrict__ energy, double* __restrict__ lufs_out) {
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        const PbLufsUnitDev ud = units[u];
+        const double rate = meters[ud.meter].rate;
+        const double inv = 1.0 / (0.4 * rate);
+        const double* e = energy + ud.chunk_off;
+        const double NEG_INF = -(double)INFINITY;
+        // absolute gate
+        double sum = 0.0; int cnt = 0;
+        for (int j = 0; j < ud.n_blocks; j++) {
+            const double z = inv * (e[j] + e[j + 1] + e[j + 2] + e[j + 3]);
+            const double l = z > 0.0 ? -0.691 + 10.0 * log10(z) : NEG_INF;
+            if (l >= -70.0) { sum += z; cnt++; }
+        }
+        double out = NEG_INF;
+        if (cnt > 0) {
+            const double gamma_r = -0.691 + 10.0 * log10(sum / (double)cnt) - 10.0;
+            sum = 0.0; cnt = 0;
+            for (int j = 0; j < ud.n_blocks; j++) {
+                const double z = inv * (e[j] + e[j + 1] + e[j + 2] + e[j + 3]);
+                const double l = z > 0.0 ? -0.691 + 10.0 * log10(z) : NEG_INF;
+                if (l > gamma_r && l > -70.0) { sum += z; cnt++; }
+            }
+            if (cnt > 0) { const double za = sum / (double)cnt; out = za > 0.0 ? -0.691 + 10.0 * log10(za) : NEG_INF; }
+        }
+        lufs_out[ud.out_index] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4b: Praat Sound_to_Intensity
+// One warp per frame: Kaiser-Bessel-like window (Praat's bessel_i0 window), mean-subtracted energy, dB re 4e-10.
+struct PbIntensityUnitDev {
+    int64_t pcm_off; int64_t frame_off; double x1; double t1; int32_t nx; int32_t n_frames; int32_t out_index; int32_t pad;
+};
+__global__ void __launch_bounds__(128)
+pb_intensity_kernel(const int16_t* __restrict__ pcm, const PbIntensityUnitDev* __restrict__ units, const int64_t* __restrict__ frame_off,
+                    int n_units, long long n_frames_total, const float* __restrict__ window /* [2*half+1] */, int half,
+                    double dx, double dt, int subtract_mean, float* __restrict__ out_db) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long fr = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); fr < n_frames_total; fr += (long long)gridDim.x * wpb) {
+        int lo = 0, hi = n_units;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frame_off[mid] <= fr) lo = mid; else hi = mid; }
+        const PbIntensityUnitDev ud = units[lo];
+        const int f = (int)(fr - ud.frame_off);
+        const double t = __dadd_rn(ud.t1, __dmul_rn((double)f, dt));
+        // Sampled_xToNearestIndex: round((t - x1)/dx + 1)
+        const long long mid = (long long)floor(__dadd_rn(__ddiv_rn(__dsub_rn(t, ud.x1), dx), 1.0) + 0.5);
+        long long l = mid - half, r = mid + half;
+        if (l < 1) l = 1; if (r > ud.nx) r = ud.nx;
+        const int16_t* p = pcm + ud.pcm_off;
+        // mean over the clipped span (exact in integers)
+        long long s = 0;
+        for (long long i = l + lane; i <= r; i += 32) s += p[i - 1];
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(PB_FULL_MASK, s, o);
+        const double mean = subtract_mean && r >= l ? ((double)s / 32768.0) / (double)(r - l + 1) : 0.0;
+        double sumxw = 0.0, sumw = 0.0;
+        for (long long i = l + lane; i <= r; i += 32) {
+            const double w = (double)window[(int)(i - mid + half)];
+            const double x = (double)p[i - 1] / 32768.0 - mean;
+            sumxw += x * x * w; sumw += w;
+        }
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
+            sumxw += __shfl_xor_sync(PB_FULL_MASK, sumxw, o); sumw += __shfl_xor_sync(PB_FULL_MASK, sumw, o);
+        }
+        if (lane == 0) {
+            double I = sumw > 0.0 ? sumxw / sumw : 0.0;
+            I /= 4.0e-10;
+            out_db[fr] = I < 1.0e-30 ? -300.0f : (float)(10.0 * log10(I));
+        }
+    }
+}
