@@ -1,0 +1,46 @@
+"""CPU-side check of the kernel sources themselves: the SIMT-emulated build (tests/simt_emu, test infrastructure, never
+loaded by the product) against the oracle, on inputs small enough for one-thread-per-CUDA-thread emulation."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import compare_tracks, speechlike
+
+
+@pytest.fixture(scope="module")
+def emu(emu_lib):
+    import prosody_b200 as pb
+    ex = pb.Extractor(0, lib=emu_lib)
+    yield ex
+    ex.close()
+
+
+@pytest.mark.parametrize("sr,floor,dur", [(16000, 75.0, 0.6), (16000, 150.0, 0.4), (44100, 150.0, 0.25), (44100, 75.0, 0.25), (8000, 150.0, 0.5)])
+def test_emulated_pitch_kernels_match_oracle(emu, oracle, sr, floor, dur):
+    import prosody_b200 as pb
+    x = speechlike(2, dur, sr, seed=3)
+    n = x.shape[1]
+    units = pb.Units.from_list([(0, n, sr, 0.0, None), (n, n, sr, 0.05, dur - 0.03)])
+    r = emu.median_pitch(x.reshape(-1), units, pb.pitch_params(floor, 600.0), frames=True)
+    for i, (t0, t1) in enumerate(((0.0, None), (0.05, dur - 0.03))):
+        o = oracle.pitch_track(x[i], sr, t0, t1, params=oracle.pitch_params(floor, 600.0))
+        a, b = r["frame_off"][i], r["frame_off"][i + 1]
+        assert b - a == o["n_frames"]
+        agree, rel = compare_tracks(r["frame_f0"][a:b], o["frequency"])
+        assert agree >= 1.0 - 1.0 / (b - a) and rel < 5e-3
+        assert np.max(np.abs(r["frame_intensity"][a:b] - o["intensity"])) < 1e-5
+        if o["median"] > 0:
+            assert abs(r["median_f0"][i] - o["median"]) / o["median"] < 5e-3
+
+
+def test_emulated_lufs_kernels_match_oracle(emu, oracle):
+    import prosody_b200 as pb
+    x = speechlike(1, 1.2, 16000, seed=4)[0]
+    items = [(0, len(x), 16000, 0.0, None, 16000.0), (0, len(x), 16000, 0.1, 0.9, 44100.0), (0, len(x), 16000, 0.2, 0.4, 16000.0),
+             (0, len(x), 16000, 0.7, 1.2015, 16000.0)]
+    out, st = emu.lufs(x, pb.Units.from_list(items))
+    for k, it in enumerate(items):
+        ref = oracle.lufs(x, it[2], it[5], it[3], it[4])
+        assert abs(out[k] - ref) < 1e-9
+    assert st[2] & 16

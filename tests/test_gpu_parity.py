@@ -1,0 +1,203 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: F0 within 0.5 % on frames voiced in both, voicing decisions agree on >= 99.5 % of
+frames, loudness within 0.05 dB, indices (frame counts, statuses, durations) identical."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import compare_tracks, speechlike
+
+pytestmark = pytest.mark.gpu
+
+F0_TOL = 5e-3
+VOICING_AGREE = 0.995
+LUFS_TOL_DB = 0.05
+
+
+def _units_whole(pb, x, sr):
+    n_utt, n = x.shape
+    return pb.Units.from_list([(i * n, n, sr, 0.0, None) for i in range(n_utt)])
+
+
+@pytest.mark.parametrize("sr,floor,dur", [(16000, 75.0, 2.0), (16000, 150.0, 1.5), (24000, 75.0, 1.5), (22050, 150.0, 1.0),
+                                          (44100, 150.0, 1.0), (44100, 75.0, 1.0), (8000, 150.0, 1.5)])
+def test_pitch_tracks_match_oracle(gpu_extractor, oracle, sr, floor, dur):
+    import prosody_b200 as pb
+    x = speechlike(6, dur, sr, seed=100 + sr // 1000)
+    units = _units_whole(pb, x, sr)
+    r = gpu_extractor.median_pitch(x.reshape(-1), units, pb.pitch_params(floor, 600.0), frames=True)
+    tot = agree_n = 0
+    worst = 0.0
+    for i in range(x.shape[0]):
+        o = oracle.pitch_track(x[i], sr, params=oracle.pitch_params(floor, 600.0))
+        a, b = r["frame_off"][i], r["frame_off"][i + 1]
+        assert b - a == o["n_frames"] == r["n_frames"][i]
+        agree, rel = compare_tracks(r["frame_f0"][a:b], o["frequency"])
+        agree_n += agree * (b - a); tot += b - a
+        worst = max(worst, rel)
+        assert np.max(np.abs(r["frame_intensity"][a:b] - o["intensity"])) < 1e-5
+        if o["median"] > 0:
+            assert abs(r["median_f0"][i] - o["median"]) / o["median"] < F0_TOL
+        assert abs(int(r["n_voiced"][i]) - o["n_voiced"]) <= max(1, int(0.005 * o["n_frames"]))
+    assert agree_n / tot >= VOICING_AGREE
+    assert worst < F0_TOL
+
+
+def test_pitch_slices_and_praat_errors(gpu_extractor, oracle):
+    """Slices like the reference's syntagme calls (t = ms/1000), incl. ones running past the file end (zero-filled)
+    and ones Praat refuses (shorter than 3 / floor)."""
+    import prosody_b200 as pb
+    sr = 16000
+    x = speechlike(3, 3.0, sr, seed=7)
+    n = x.shape[1]
+    rng = np.random.default_rng(3)
+    items, spec = [], []
+    for i in range(3):
+        for _ in range(8):
+            a = int(rng.integers(0, 2600)); d = int(rng.integers(15, 900))
+            items.append((i * n, n, sr, a / 1000, (a + d) / 1000)); spec.append((i, a / 1000, (a + d) / 1000))
+        items.append((i * n, n, sr, 2.9, 3.4)); spec.append((i, 2.9, 3.4))          # past the end
+        items.append((i * n, n, sr, 1.0, 1.010)); spec.append((i, 1.0, 1.010))      # too short for floor 150
+        items.append((i * n, n, sr, 5.0, 5.5)); spec.append((i, 5.0, 5.5))          # entirely outside: zeros
+    units = pb.Units.from_list(items)
+    r = gpu_extractor.median_pitch(x.reshape(-1), units, pb.pitch_params(150.0, 600.0), frames=True)
+    for k, (i, t0, t1) in enumerate(spec):
+        try:
+            o = oracle.pitch_track(x[i], sr, t0, t1, params=oracle.pitch_params(150.0, 600.0))
+        except oracle.PraatError:
+            assert r["status"][k] != 0 and r["n_frames"][k] == 0 and r["median_f0"][k] == 0.0
+            continue
+        assert r["status"][k] == 0
+        a, b = r["frame_off"][k], r["frame_off"][k + 1]
+        assert b - a == o["n_frames"]
+        agree, rel = compare_tracks(r["frame_f0"][a:b], o["frequency"])
+        assert agree >= 1.0 - max(0.005, 1.0 / max(b - a, 1)) and rel < F0_TOL
+        if o["median"] > 0 and r["median_f0"][k] > 0:
+            assert abs(r["median_f0"][k] - o["median"]) / o["median"] < F0_TOL
+
+
+def test_pitch_degenerate_inputs(gpu_extractor, oracle):
+    """Digital silence (Praat: all frames voiceless), a constant offset, a full-scale square wave, a pure tone."""
+    import prosody_b200 as pb
+    sr = 16000
+    n = sr
+    t = np.arange(n) / sr
+    sigs = [np.zeros(n, np.int16), np.full(n, 1234, np.int16),
+            (np.sign(np.sin(2 * np.pi * 200 * t)) * 32767).astype(np.int16),
+            (0.5 * 32767 * np.sin(2 * np.pi * 311.0 * t)).astype(np.int16),
+            (0.8 * 32767 * np.sin(2 * np.pi * 3000.0 * t)).astype(np.int16)]     # many maxima: candidate overflow path
+    x = np.stack(sigs)
+    units = _units_whole(pb, x, sr)
+    for floor in (75.0, 150.0):
+        r = gpu_extractor.median_pitch(x.reshape(-1), units, pb.pitch_params(floor, 600.0), frames=True)
+        for i in range(len(sigs)):
+            o = oracle.pitch_track(x[i], sr, params=oracle.pitch_params(floor, 600.0))
+            a, b = r["frame_off"][i], r["frame_off"][i + 1]
+            agree, rel = compare_tracks(r["frame_f0"][a:b], o["frequency"])
+            assert agree >= VOICING_AGREE and rel < F0_TOL, (floor, i, agree, rel)
+            assert abs(int(r["n_voiced"][i]) - o["n_voiced"]) <= 1
+    assert r["median_f0"][0] == 0.0 and r["median_f0"][1] == 0.0
+    assert abs(r["median_f0"][3] - 311.0) < 0.05
+
+
+def test_lufs_matches_oracle(gpu_extractor, oracle):
+    """get_lufs incl. ms slicing, the wrong-rate meter the reference builds, both whole-file fallbacks and the error."""
+    import prosody_b200 as pb
+    xa = speechlike(2, 3.0, 16000, seed=11); xb = speechlike(2, 2.5, 44100, seed=12); xc = speechlike(1, 0.3, 24000, seed=13)
+    bufs = [xa[0], xa[1], xb[0], xb[1], xc[0]]; rates = [16000, 16000, 44100, 44100, 24000]
+    offs = np.concatenate([[0], np.cumsum([len(b) for b in bufs])])
+    cat = np.concatenate(bufs)
+    items = []
+    for f, (b, sr) in enumerate(zip(bufs, rates)):
+        for mr in (sr, 44100.0 if sr != 44100 else 16000.0):
+            items.append((offs[f], len(b), sr, 0.0, None, mr))
+            for (t0, t1) in ((0.25, 1.75), (0.5, 0.95), (1.001, 1.3), (2.2, 9.0), (7.0, 8.0), (0.0, 0.4)):
+                items.append((offs[f], len(b), sr, t0, t1, mr))
+    units = pb.Units.from_list(items)
+    out, st = gpu_extractor.lufs(cat, units)
+    n_fallback = n_err = 0
+    for k, it in enumerate(items):
+        arr = cat[it[0]:it[0] + it[1]]
+        try:
+            ref = oracle.lufs(arr, it[2], it[5], it[3], it[4])
+        except ValueError:
+            assert st[k] & 32 and math.isnan(out[k]); n_err += 1
+            continue
+        a, b, npad, fb = oracle.lufs_resolve(len(arr), it[2], it[5], it[3], it[4])
+        assert bool(st[k] & 16) == fb
+        n_fallback += fb
+        if math.isinf(ref):
+            assert out[k] == ref
+        else:
+            assert abs(out[k] - ref) < LUFS_TOL_DB, (it, out[k], ref)
+            assert abs(out[k] - ref) < 1e-9          # float64 path: far inside the tolerance
+    assert n_fallback > 0 and n_err > 0
+
+
+def test_lufs_silence_is_minus_inf(gpu_extractor, oracle):
+    import prosody_b200 as pb
+    x = np.zeros(16000, np.int16)
+    out, st = gpu_extractor.lufs(x, pb.Units.from_list([(0, len(x), 16000, 0.0, None, 16000.0)]))
+    assert out[0] == -math.inf == oracle.lufs(x, 16000, 16000.0)
+
+
+def test_extract_batch_device_and_host_pcm_agree(gpu_extractor, oracle):
+    """pb_extract_batch with HBM-resident PCM (torch CUDA tensor) and with host PCM give the same records."""
+    import torch
+    import prosody_b200 as pb
+    sr = 16000
+    x = speechlike(8, 2.0, sr, seed=21)
+    n = x.shape[1]
+    items = []
+    for i in range(8):
+        items.append((i * n, n, sr, 0.0, None, float(sr)))
+        items.append((i * n, n, sr, 0.2, 1.4, float(sr)))
+    units = pb.Units.from_list(items)
+    flat = x.reshape(-1)
+    p = pb.pitch_params(75.0, 600.0)
+    r_host = gpu_extractor.extract(flat, units, p)
+    r_pin = gpu_extractor.extract(torch.from_numpy(flat).pin_memory(), units, p)
+    r_dev = gpu_extractor.extract(torch.from_numpy(flat).cuda(), units, p)
+    for k in ("median_f0", "n_voiced", "n_frames", "lufs", "duration_s", "status"):
+        assert np.array_equal(r_host[k], r_dev[k], equal_nan=True) and np.array_equal(r_host[k], r_pin[k], equal_nan=True)
+    for k, it in enumerate(items):
+        arr = flat[it[0]:it[0] + it[1]]
+        ref = oracle.median_pitch(arr, sr, it[3], it[4], 75.0, 600.0)
+        assert abs(r_dev["median_f0"][k] - ref) <= F0_TOL * max(ref, 1.0)
+        assert abs(r_dev["lufs"][k] - oracle.lufs(arr, sr, it[5], it[3], it[4])) < 1e-9
+        assert r_dev["duration_s"][k] == oracle.part_duration(len(arr), sr, it[3], it[4])
+    t = gpu_extractor.timings()
+    assert t["n_launches"] >= 8 and t["n_frames"] > 0 and t["frames_ms"] > 0
+
+
+def test_full_size_properties(gpu_extractor):
+    """BASELINE config-2 shaped batch (scaled to 2000 x 5 s @ 16 kHz): size-independent properties —
+    a permutation of the units permutes the results; gain invariance of F0 and of the peak-normalised loudness;
+    re-running is bit-identical."""
+    import torch
+    import prosody_b200 as pb
+    from prosody_b200 import synth
+    sr, n_utt = 16000, 2000
+    pcm = synth.make_corpus(n_utt, 5.0, sr, seed=1234, device="cuda")
+    n = pcm.shape[1]
+    units = pb.Units.from_list([(i * n, n, sr, 0.0, None, float(sr)) for i in range(n_utt)])
+    p = pb.pitch_params(75.0, 600.0)
+    r1 = gpu_extractor.extract(pcm.reshape(-1), units, p)
+    r2 = gpu_extractor.extract(pcm.reshape(-1), units, p)
+    assert np.array_equal(r1["median_f0"], r2["median_f0"]) and np.array_equal(r1["lufs"], r2["lufs"])
+    assert (r1["n_frames"] == 497).all() and (r1["status"] == 0).all()
+    perm = np.random.default_rng(0).permutation(n_utt)
+    r3 = gpu_extractor.extract(pcm.reshape(-1), units.select(perm), p)
+    assert np.array_equal(r3["median_f0"], r1["median_f0"][perm]) and np.array_equal(r3["lufs"], r1["lufs"][perm])
+    half = (pcm.to(torch.int32) // 2 * 2 // 2).to(torch.int16)       # exact halving of even-ised samples
+    pcm_even = (half.to(torch.int32) * 2).to(torch.int16)
+    ra = gpu_extractor.extract(pcm_even.reshape(-1), units, p)
+    rb = gpu_extractor.extract(half.reshape(-1), units, p)
+    v = (ra["median_f0"] > 0) & (rb["median_f0"] > 0)
+    assert v.mean() > 0.9
+    assert np.max(np.abs(ra["median_f0"][v] - rb["median_f0"][v]) / ra["median_f0"][v]) < 1e-3
+    assert np.max(np.abs(ra["lufs"] - rb["lufs"])) < 1e-9
+    voiced_frac = r1["n_voiced"].sum() / r1["n_frames"].sum()
+    assert 0.2 < voiced_frac < 0.95
