@@ -149,6 +149,28 @@ int pb_intensity_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm
                        const PbUnits* u, double minimum_pitch, double time_step, int subtract_mean,
                        float* intensity_db, int32_t* status);
 
+/* ---- host-side arithmetic of the step (float64, same libm calls and operation order as the reference's Python) */
+
+/* prosody settings read by the step (Code/audioPipeline.py:127-139, config.yaml prosody_settings) */
+typedef struct PbDeltaParams {
+    double pitch_semitones;            /* P_ST */
+    double pitch_lower_clip_factor;
+    double volume_pct;
+    double rate_percent;               /* R_PCT */
+    double threshold_duration_before_slowing_down;
+    double slow_floor_per_sec;
+} PbDeltaParams;
+
+/* Per-syntagme raw deltas (Code/audioPipeline.py:515-577): pitch % from 12*log2(p_nat/base_f0) clipped in semitones,
+ * volume % from the loudness gap to the baseline, rate % from words per second nat vs synth with the asymmetric
+ * length scaling, extra slow-down and clamps. All arrays have n entries. */
+int pb_syntagme_deltas(int64_t n, const double* p_nat, const double* base_f0, const double* base_loud, const double* l_syn,
+                       const int32_t* word_count, const double* nat_total_s, const double* syn_total_s, const int32_t* pause_ms,
+                       const PbDeltaParams* prm, double* raw_pitch, double* raw_volume, double* raw_rate);
+
+/* EMA over all rows then the forward jump clamp (Code/audioPipeline.py:593-602). out may alias x. */
+int pb_ema_clamp(const double* x, int64_t n, double alpha, double max_jump, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,7 +41,13 @@ class PbTimings(C.Structure):
                 ("n_frames", C.c_int64), ("n_lufs_samples", C.c_int64), ("n_launches", C.c_int32), ("reserved", C.c_int32)]
 
 
-EXPORTS = ["pb_abi_version", "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_get_timings",
+class PbDeltaParams(C.Structure):
+    _fields_ = [("pitch_semitones", C.c_double), ("pitch_lower_clip_factor", C.c_double), ("volume_pct", C.c_double),
+                ("rate_percent", C.c_double), ("threshold_duration_before_slowing_down", C.c_double),
+                ("slow_floor_per_sec", C.c_double)]
+
+
+EXPORTS = ["pb_syntagme_deltas", "pb_ema_clamp", "pb_abi_version", "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_get_timings",
            "pb_device_info", "pb_pitch_params_default", "pb_pitch_plan", "pb_median_pitch_batch", "pb_lufs_batch",
            "pb_part_duration_batch", "pb_extract_batch", "pb_intensity_plan", "pb_intensity_batch"]
 
@@ -64,6 +70,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.pb_extract_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, P, u8p, u8p, dp, i32p, i32p, dp, dp, i32p]
     lib.pb_intensity_plan.argtypes = [U, C.c_double, C.c_double, i32p, i32p, i64p, dp, dp]
     lib.pb_intensity_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, C.c_double, C.c_double, C.c_int, fp, i32p]
+    lib.pb_syntagme_deltas.argtypes = [C.c_int64, dp, dp, dp, dp, i32p, dp, dp, i32p, C.POINTER(PbDeltaParams), dp, dp, dp]
+    lib.pb_ema_clamp.argtypes = [dp, C.c_int64, C.c_double, C.c_double, dp]
     for name in EXPORTS:
         if name not in ("pb_destroy", "pb_last_error", "pb_pitch_params_default"):
             getattr(lib, name).restype = C.c_int

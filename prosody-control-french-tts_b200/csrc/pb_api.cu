@@ -5,6 +5,8 @@
 #include "pb_rt.h"
 #include "pb_plan.h"
 #include "pb_pitch.cuh"
+#include "pb_pitch_frames.cuh"
+#include "pb_pitch_path.cuh"
 #include "pb_lufs.cuh"
 
 #include <algorithm>
@@ -176,6 +178,7 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
     if (oc == h->occ_cache.end()) {
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail(h, PB_ECUDA, "cudaFuncSetAttribute: %s", pbrt_error());
+        cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         h->occ_cache[LOG2N] = per_sm;
     } else per_sm = oc->second;
@@ -289,6 +292,8 @@ int enqueue_pitch(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const PbP
         gm.brent_ixmax = (int)pc.g.brent_ixmax;
         gm.scan_lim = (int)std::min(pc.g.max_lag, pc.g.brent_ixmax);
         gm.max_cand = pc.g.max_cand; gm.n_units = (int)m; gm.n_pairs = (int)pairs;
+        // a maximum at lag i refines to a lag <= i+1: below this lag its frequency stays above the ceiling (never voiced)
+        gm.min_refine_lag = (int)std::floor(1.0 / pc.g.dx / pc.g.ceiling) - 1;
         gm.sr = (float)(1.0 / pc.g.dx); gm.half_voicing = (float)(0.5 * p->voicing_threshold);
         gm.octave_cost = (float)p->octave_cost; gm.min_pitch = (float)p->pitch_floor;
         gm.dx = pc.g.dx; gm.dt = pc.g.dt; gm.ceiling = pc.g.ceiling; gm.silence_threshold = p->silence_threshold;
@@ -617,6 +622,59 @@ int pb_intensity_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm
                        double time_step, int subtract_mean, float* intensity_db, int32_t* status) {
     (void)pcm; (void)pcm_len; (void)pcm_on_device; (void)u; (void)minimum_pitch; (void)time_step; (void)subtract_mean; (void)intensity_db; (void)status;
     return fail(h, PB_EUNSUPPORTED, "%s", "pb_intensity_batch is not wired yet");
+}
+
+int pb_syntagme_deltas(int64_t n, const double* p_nat, const double* base_f0, const double* base_loud, const double* l_syn,
+                       const int32_t* word_count, const double* nat_total_s, const double* syn_total_s, const int32_t* pause_ms,
+                       const PbDeltaParams* prm, double* raw_pitch, double* raw_volume, double* raw_rate) {
+    if (n < 0 || !prm || (n && (!p_nat || !base_f0 || !base_loud || !l_syn || !word_count || !nat_total_s || !syn_total_s ||
+                                !pause_ms || !raw_pitch || !raw_volume || !raw_rate))) return PB_EINVAL;
+    // np.clip(x, lo, hi) == minimum(maximum(x, lo), hi), NaN-propagating
+    auto clip = [](double x, double lo, double hi) { if (x != x) return x; x = x < lo ? lo : x; return x > hi ? hi : x; };
+    for (int64_t i = 0; i < n; i++) {
+        const double pause_s = (double)pause_ms[i] / 1000.0;
+        double d_nat = nat_total_s[i] - pause_s; if (!(d_nat > 1e-4)) d_nat = 1e-4;      // max(x, 1e-4)
+        double d_syn = syn_total_s[i] - pause_s; if (!(d_syn > 1e-4)) d_syn = 1e-4;
+        double p_pct = 0.0;
+        if (p_nat[i] > 0.0) {
+            double st = 12.0 * log2(p_nat[i] / base_f0[i]);
+            st = clip(st, -prm->pitch_semitones * prm->pitch_lower_clip_factor, prm->pitch_semitones);
+            p_pct = (pow(2.0, st / 12.0) - 1.0) * 100.0;
+        }
+        const double db_diff = base_loud[i] - l_syn[i];
+        double v_pct = (pow(10.0, db_diff / 20.0) - 1.0) * 100.0;
+        v_pct = clip(v_pct, -prm->volume_pct, prm->volume_pct);
+        double rp = 0.0;
+        if (word_count[i] > 0) {
+            const double nat_r = (double)word_count[i] / d_nat, syn_r = (double)word_count[i] / d_syn;
+            rp = (nat_r - syn_r) / syn_r * 100.0;
+        }
+        const double length_s = d_nat;
+        double slow = 1.0, fast = 1.0;
+        if (!(length_s <= 1.0)) { slow = pow(length_s, 1.5); fast = sqrt(length_s); }
+        rp = rp < 0.0 ? rp * slow : rp / fast;
+        double over = length_s - prm->threshold_duration_before_slowing_down; if (!(over > 0.0)) over = 0.0;
+        rp = rp - over * prm->slow_floor_per_sec;
+        const double lo = length_s > 5.0 ? prm->rate_percent * 1.5 : prm->rate_percent;
+        const double hi = length_s > 5.0 ? prm->rate_percent * 0.5 : prm->rate_percent;
+        rp = clip(rp, -lo, hi);
+        raw_pitch[i] = p_pct; raw_volume[i] = v_pct; raw_rate[i] = rp;
+    }
+    return PB_OK;
+}
+
+int pb_ema_clamp(const double* x, int64_t n, double alpha, double max_jump, double* out) {
+    if (n < 0 || (n && (!x || !out))) return PB_EINVAL;
+    if (n == 0) return PB_OK;
+    const double beta = 1.0 - alpha;
+    double s = x[0];
+    out[0] = s;
+    for (int64_t i = 1; i < n; i++) { s = alpha * x[i] + beta * s; out[i] = s; }
+    for (int64_t i = 1; i < n; i++) {
+        const double d = out[i] - out[i - 1];
+        if (fabs(d) > max_jump) out[i] = out[i - 1] + (d > 0.0 ? 1.0 : -1.0) * max_jump;
+    }
+    return PB_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,392 @@
+// pb_pitch_frames.cuh — K1 + K2: frames -> normalised autocorrelation -> pitch candidates, one kernel.
+//
+// Follows Sound_into_PitchFrame (Praat fon/Sound_to_Pitch.cpp, AC_HANNING) per frame; see pb_pitch.cuh for the layout.
+// Code-size discipline matters here: the fully unrolled radix-32 butterfly network is ~600 instructions, so the kernel
+// keeps exactly ONE copy of it and runs it from a 4-step loop (2 FFTs x 2 passes); likewise one copy of the candidate
+// search serves both frames of a pair.  (The first version inlined four copies: ~210 KB of SASS, 55 % of the stall
+// samples were instruction-fetch misses — profiles/r01_frames_v1_*.)
+#pragma once
+#include "pb_pitch.cuh"
+
+// ------------------------------------------------------------------------------------------------ sinc interpolation
+// Praat NUM_interpolate_sinc (melder/NUMinterpol.cpp) on y[1..2B+1] = r[-B..B] at lag x, by 8 cooperating lanes
+// (sl = lane within the group; every lane of the group passes the same x).  With phi = frac(x), il = floor(x),
+// D = min(depth, B - il) the usable depth:
+//   y(x) = sin(pi phi)/(2 pi) * sum_{m<D} (-1)^m [ r[il-m]   (1 + cos(pi (phi+m)   / (phi+D)))   / (phi+m)
+//                                                + r[il+1+m] (1 + cos(pi (1-phi+m) / (1-phi+D))) / (1-phi+m) ]
+// Lane sl takes one side (sl & 1) and every 4th m starting at sl >> 1, so side, sign and the window scale are
+// loop-invariant; the loop body is one shared load, two MUFU (cos, rcp) and a handful of FP32 ops.
+__device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, float x, int depth, int sl) {
+    const float fl = floorf(x);
+    const float phi = x - fl;
+    const int il = (int)fl;
+    int D = B - il; if (depth < D) D = depth;
+    float acc = 0.0f;
+    if (phi == 0.0f) {                                        // on a sample: Praat returns y[x] (no early return:
+        if (sl == 0 && depth > 0) acc = r[abs(il)];           // the other groups of the warp still shuffle below)
+    } else if (D > 0) {
+        const int side = sl & 1, j0 = sl >> 1;
+        const float e = side ? 1.0f - phi : phi;
+        const float k = __fdividef(PB_PI_F, e + (float)D);
+        float d = e + (float)j0;
+        int idx = side ? il + 1 + j0 : il - j0;
+        const int step = side ? 4 : -4;
+#ifndef PB_SIMT_EMU
+#pragma unroll 2
+#endif
+        for (int m = j0; m < D; m += 4) {
+            const float yv = r[abs(idx)];
+            acc += __fdividef(yv * (1.0f + __cosf(d * k)), d);
+            d += 4.0f; idx += step;
+        }
+        if (j0 & 1) acc = -acc;
+        acc *= sinpif(phi) * (0.5f / PB_PI_F);
+    }
+    acc += __shfl_xor_sync(PB_FULL_MASK, acc, 1);
+    acc += __shfl_xor_sync(PB_FULL_MASK, acc, 2);
+    acc += __shfl_xor_sync(PB_FULL_MASK, acc, 4);
+    return acc;
+}
+// vertex of the parabola through (xa,fa),(xb,fb),(xc,fc), xa < xb < xc; xb if not concave
+__device__ __forceinline__ float pb_parabola(float xa, float fa, float xb, float fb, float xc, float fc) {
+    const float a = xb - xa, b = xb - xc;
+    const float num = a * a * (fb - fc) - b * b * (fb - fa);
+    const float den = a * (fb - fc) - b * (fb - fa);
+    return den > 0.0f ? xb - 0.5f * __fdividef(num, den) : xb;
+}
+
+// ------------------------------------------------------------------------------------------------ candidates of one frame
+// One warp. r: normalised autocorrelation for lags 0..B (shared memory). scratch: 3*PB_MAXC words of shared memory.
+// Maxima of r above voicingThreshold/2 between lag 2 and scan_lim-1 become candidates (the weakest is replaced when
+// there are more than max_cand-1), each is then refined on the sinc-interpolated curve (depth 70, or 700 above 0.3/dx).
+// Praat refines with Brent (tol 1e-10, <= 60 iterations); here the maximiser is found with FOUR evaluations:
+// the two half-sample points next to the maximum, the vertex of the parabola through the best three of the
+// five-point grid, and the vertex of the parabola through that point and its grid neighbours.  On speech this
+// reproduces Brent's optimum to ~1e-4 relative in lag and ~1e-6 in strength (DESIGN.md "candidate refinement").
+// Maxima below min_refine_lag stay above the pitch ceiling wherever in [i-1, i+1] their refinement lands: the path
+// finder treats them as voiceless whatever their strength, so they keep their first-pass values.
+__device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r, float* scratch, const PbPitchGeomDev& gm,
+                                                    int lane, float* __restrict__ out_f, float* __restrict__ out_s,
+                                                    uint8_t* __restrict__ out_n) {
+    float* cf = scratch;                       // first-pass frequency
+    float* cs = scratch + PB_MAXC;             // first-pass strength
+    int* imax = (int*)(scratch + 2 * PB_MAXC); // lag of the maximum
+    const int B = gm.brent_ixmax, lim = gm.scan_lim, maxc = gm.max_cand;
+    const int sub = lane >> 3, sl = lane & 7;
+    // ---- count the maxima
+    int total = 0;
+    for (int base = 2; base < lim; base += 32) {
+        const int i = base + lane;
+        const bool pk = i < lim && r[i] > gm.half_voicing && r[i] > r[i - 1] && r[i] >= r[i + 1];
+        total += __popc(__ballot_sync(PB_FULL_MASK, pk));
+    }
+    int ncf = 1;
+    const bool overflow = total > maxc - 1;
+    if (total > 0) {
+        for (int base = 2; base < lim; base += 32) {
+            const int i = base + lane;
+            const bool pk = i < lim && r[i] > gm.half_voicing && r[i] > r[i - 1] && r[i] >= r[i + 1];
+            unsigned mask = __ballot_sync(PB_FULL_MASK, pk);
+            if (!overflow) {
+                // common case: every maximum gets its own slot, in lag order
+                if (pk) imax[ncf + __popc(mask & ((1u << lane) - 1u))] = i;
+                ncf += __popc(mask);
+            } else {
+                // rare (tonal high-frequency content): Praat's sequential insert / replace-the-weakest
+                while (mask) {
+                    unsigned m = mask;
+                    for (int q = 0; q < sub; q++) m &= m - 1;
+                    const bool have = m != 0;
+                    const int ip = have ? base + __ffs((int)m) - 1 : 2;
+                    const float dr = 0.5f * (r[ip + 1] - r[ip - 1]), d2r = 2.0f * r[ip] - r[ip - 1] - r[ip + 1];
+                    const float x0 = (float)ip + ((have && d2r > 0.0f) ? dr / d2r : 0.0f);
+                    float st = pb_sinc8(r, B, x0, 30, sl);
+                    if (st > 1.0f) st = 1.0f / st;
+                    const float fq0 = gm.sr / x0;
+                    for (int q = 0; q < 4; q++) {
+                        const int hv = __shfl_sync(PB_FULL_MASK, (int)have, q * 8);
+                        if (!hv) break;
+                        const float fq = __shfl_sync(PB_FULL_MASK, fq0, q * 8), sq = __shfl_sync(PB_FULL_MASK, st, q * 8);
+                        const int iq = __shfl_sync(PB_FULL_MASK, ip, q * 8);
+                        int place = 0;
+                        if (ncf < maxc) place = ncf++;
+                        else {
+                            // weakest of slots 1..maxc-1 by strength - octaveCost*log2(minPitch/f); first minimum wins
+                            float ls = 3.0e38f; int li = lane;
+                            if (lane >= 1 && lane < maxc) ls = cs[lane] - gm.octave_cost * log2f(gm.min_pitch / cf[lane]);
+                            PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
+                                const float os = __shfl_xor_sync(PB_FULL_MASK, ls, o);
+                                const int oi = __shfl_xor_sync(PB_FULL_MASK, li, o);
+                                if (os < ls || (os == ls && oi < li)) { ls = os; li = oi; }
+                            }
+                            if (sq - gm.octave_cost * log2f(gm.min_pitch / fq) > ls) place = li;
+                        }
+                        if (place && lane == 0) { cf[place] = fq; cs[place] = sq; imax[place] = iq; }
+                        __syncwarp();
+                    }
+                    for (int q = 0; q < 4 && mask; q++) mask &= mask - 1;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) { out_f[0] = 0.0f; out_s[0] = 0.0f; *out_n = (uint8_t)ncf; }
+    // ---- candidates that can never be voiced keep first-pass values (sorted by lag unless the overflow path ran)
+    int c_first = 1;
+    if (!overflow) {
+        int nskip = 0;
+        for (int c = 1 + lane; c < ncf; c += 32) {
+            const int i = imax[c];
+            const bool skip = i < gm.min_refine_lag;
+            if (skip) {
+                const float r0 = r[i], rm = r[i - 1], rp = r[i + 1];
+                out_f[c] = __fdividef(gm.sr, (float)i + 0.5f * __fdividef(rp - rm, 2.0f * r0 - rm - rp));
+                out_s[c] = r0;
+            }
+            nskip += skip;
+        }
+        c_first = 1 + pb_warp_sum_i(nskip);
+    }
+    // ---- refine the others on the sinc curve: 4 candidates at a time, 8 lanes each
+    for (int c0 = c_first; c0 < ncf; c0 += 4) {
+        const int c = c0 + sub;
+        const bool have = c < ncf;
+        const int i = have ? imax[c] : 2;
+        const float fi = (float)i;
+        const float r0 = r[i], rm = r[i - 1], rp = r[i + 1];
+        const float den0 = 2.0f * r0 - rm - rp;
+        const float x_first = fi + ((have && den0 > 0.0f) ? 0.5f * __fdividef(rp - rm, den0) : 0.0f);   // Praat's first guess
+        const int depth = !have ? 0 : (x_first < (1.0f / 0.3f)) ? 700 : 70;                    // f > 0.3/dx; idle groups do no work
+        // four evaluations through ONE call site (code size): y(i-.5), y(i+.5), y(x1), y(x2)
+        float xe = fi - 0.5f, ya = 0.0f, xc = fi, yc = r0, yl = 0.0f, yr = 0.0f, x1 = fi, y1 = 0.0f, y2 = 0.0f;
+#ifndef PB_SIMT_EMU
+#pragma unroll 1
+#endif
+        for (int e = 0; e < 4; e++) {
+            const float y = pb_sinc8(r, B, xe, depth, sl);
+            if (e == 0) { ya = y; xe = fi + 0.5f; }
+            else if (e == 1) {
+                // half-sample grid r[i-1], y(i-.5), r[i], y(i+.5), r[i+1]: best of the middle three and its neighbours
+                const float yb = y;
+                yl = ya; yr = yb;
+                if (ya > yc && ya >= yb) { xc = fi - 0.5f; yc = ya; yl = rm; yr = r0; }
+                else if (yb > yc) { xc = fi + 0.5f; yc = yb; yl = r0; yr = rp; }
+                x1 = pb_parabola(xc - 0.5f, yl, xc, yc, xc + 0.5f, yr);
+                x1 = fminf(fmaxf(x1, xc - 0.5f), xc + 0.5f);
+                xe = x1;
+            } else if (e == 2) {
+                // second parabola: x1 with the grid points that bracket it
+                y1 = y;
+                float x2 = x1;
+                if (x1 > xc) x2 = pb_parabola(xc, yc, x1, y1, xc + 0.5f, yr);
+                else if (x1 < xc) x2 = pb_parabola(xc - 0.5f, yl, x1, y1, xc, yc);
+                x2 = fminf(fmaxf(x2, fminf(x1, xc) - 0.25f), fmaxf(x1, xc) + 0.25f);
+                x2 = fminf(fmaxf(x2, fi - 1.0f), fi + 1.0f);
+                xe = x2;
+            } else y2 = y;
+        }
+        float bx = xe, by = y2;
+        if (y1 > by) { bx = x1; by = y1; }
+        if (yc > by) { bx = xc; by = yc; }
+        if (by > 1.0f) by = __fdividef(1.0f, by);
+        if (have && sl == 0) { out_f[c] = __fdividef(gm.sr, bx); out_s[c] = by; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1 + K2
+template <int LOG2N>
+__global__ void __launch_bounds__(PbFftCfg<LOG2N>::WARPS_PER_CTA * 32, PbFftCfg<LOG2N>::MIN_CTAS)
+pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off,
+                       PbPitchGeomDev gm, float* __restrict__ cand_f, float* __restrict__ cand_s,
+                       uint8_t* __restrict__ ncand, float* __restrict__ intensity) {
+    typedef PbFftCfg<LOG2N> C;
+    constexpr int R = C::R, LR = C::LR, N = C::N, G = C::G, GT = C::GT;
+    PB_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = warp / G, wg = warp % G;          // group in CTA, warp in group
+    const int g = wg * 32 + lane;                       // thread in group = butterfly index
+    const int bar_id = 1 + group;
+    // per-group shared memory: FFT buffer, then a small reduction scratch
+    float2* buf = (float2*)smem_raw + (size_t)group * (C::BUF + 8 * G);
+    float* red = (float*)(buf + C::BUF);                // [G][4] floats
+    const int B = gm.brent_ixmax;
+    const int rstride = (B + 4) & ~1;
+    float* rbase = (float*)buf;                         // r of frame A, r of frame B, then candidate scratch
+    const int pk_lo = max(0, gm.half_nw - gm.half_period), pk_hi = min(gm.nw, gm.half_nw + gm.half_period);   // [lo, hi)
+    const int mean_n0 = gm.half_nw - gm.nsamp_period;   // local mean spans frame samples [mean_n0, mean_n0 + 2 P)
+
+    for (int item = blockIdx.x * C::GROUPS_PER_CTA + group; item < gm.n_pairs; item += gridDim.x * C::GROUPS_PER_CTA) {
+        const int u = pb_upper_unit(pair_off, gm.n_units, item);
+        const PbUnitDev ud = units[u];
+        const int fA = 2 * (item - ud.pair_off);
+        const bool hasB = fA + 1 < ud.n_frames;
+        const bool global_silent = ud.global_peak == 0.0;
+        float2 v[R];
+        float pkA = 0.0f, pkB = 0.0f, sA = 1.0f, sB = 1.0f;
+        bool active = false;
+
+#ifndef PB_SIMT_EMU
+#pragma unroll 1
+#endif
+        for (int step = 0; step < 4; step++) {          // FFT (step >> 1), pass (step & 1): one copy of the butterfly code
+            const int pass = step & 1;
+            if (step == 0) {
+                // ---- frame positions (float64: Praat's Sampled_indexToX / Sampled_xToLowIndex), sample windows
+                const int16_t* fp[2]; int nlo[2], nhi[2]; float lmean[2];
+                PB_UNROLL for (int f = 0; f < 2; f++) {
+                    const double t = __dadd_rn(ud.t1, __dmul_rn((double)(fA + f), gm.dt));
+                    const long long left = (long long)floor(__ddiv_rn(__dsub_rn(t, ud.x1), gm.dx)) + 1;
+                    const long long start = left + 1 - gm.half_nw;     // part index (1-based) of frame sample n = 0
+                    // frame sample n is part sample start+n = file sample ix1+start+n-2; zero outside the part or the file
+                    long long lo = 1 - start, hi = ud.nx - start + 1;
+                    const long long lo2 = 2 - ud.ix1 - start, hi2 = (long long)ud.file_nx - ud.ix1 - start + 2;
+                    if (lo2 > lo) lo = lo2; if (hi2 < hi) hi = hi2;
+                    const long long BIG = 1 << 30;
+                    nlo[f] = (int)(lo < -BIG ? -BIG : (lo > BIG ? BIG : lo));
+                    nhi[f] = (int)(hi < -BIG ? -BIG : (hi > BIG ? BIG : hi));
+                    fp[f] = pcm + ud.pcm_off + (ud.ix1 + start - 2);
+                    // local mean: one longest period to both sides of the frame centre (exact in integers)
+                    int s = 0;
+                    for (int q = lane; q < 2 * gm.nsamp_period; q += 32) {
+                        const int n = mean_n0 + q;
+                        s += (n >= nlo[f] && n < nhi[f]) ? (int)fp[f][n] : 0;
+                    }
+                    s = pb_warp_sum_i(s);
+                    lmean[f] = (float)(((double)s / 32768.0) / (double)(2 * gm.nsamp_period));
+                }
+                if (!hasB) { nlo[1] = 0; nhi[1] = 0; }
+                // ---- window both frames into the FFT buffer, z = a + i b (natural order, zero padded); a compact
+                //      rolled loop: the range checks live here once instead of in 32 unrolled copies
+                float mxA = 0.0f, mxB = 0.0f;
+                for (int n = g; n < N; n += GT) {
+                    float a = 0.0f, b = 0.0f;
+                    if (n < gm.nw) {
+                        const float w = __ldg(&gm.window[n]);
+                        const int sa = (n >= nlo[0] && n < nhi[0]) ? (int)fp[0][n] : 0;
+                        const int sb = (n >= nlo[1] && n < nhi[1]) ? (int)fp[1][n] : 0;
+                        a = ((float)sa * (1.0f / 32768.0f) - lmean[0]) * w;
+                        b = hasB ? ((float)sb * (1.0f / 32768.0f) - lmean[1]) * w : 0.0f;
+                        const float aa = fabsf(a), ab = fabsf(b);
+                        mxA = fmaxf(mxA, aa); mxB = fmaxf(mxB, ab);
+                        if (n >= pk_lo && n < pk_hi) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, ab); }
+                    }
+                    buf[pb_pad5(n)] = make_float2(a, b);
+                }
+                mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB); pkA = pb_warp_max(pkA); pkB = pb_warp_max(pkB);
+                if (G > 1) {
+                    if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; red[wg * 4 + 2] = pkA; red[wg * 4 + 3] = pkB; }
+                    pb_group_sync<G>(bar_id);
+                    for (int k = 0; k < G; k++) {
+                        mxA = fmaxf(mxA, red[k * 4 + 0]); mxB = fmaxf(mxB, red[k * 4 + 1]);
+                        pkA = fmaxf(pkA, red[k * 4 + 2]); pkB = fmaxf(pkB, red[k * 4 + 3]);
+                    }
+                    pb_group_sync<G>(bar_id);
+                }
+                active = !global_silent && (pkA > 0.0f || pkB > 0.0f);
+                if (!active) break;
+                // bring both frames to comparable magnitude (power-of-two scales are exact and cancel in r = ac/ac[0]):
+                // keeps the weaker frame of a pair out of the stronger one's rounding noise
+                // (exponent arithmetic on the float bits: scale = 2^-(exponent of the maximum))
+                sA = mxA > 0.0f ? __int_as_float((254 - ((__float_as_int(mxA) >> 23) & 0xff)) << 23) : 1.0f;
+                sB = mxB > 0.0f ? __int_as_float((254 - ((__float_as_int(mxB) >> 23) & 0xff)) << 23) : 1.0f;
+                pb_group_sync<G>(bar_id);               // the windowed frames are in the buffer
+            } else if (step == 2) {
+                // ---- power spectra of both frames: P_a = |Z_k + conj Z_-k|^2 / 4, P_b = |Z_k - conj Z_-k|^2 / 4
+                for (int k = g; k <= N / 2; k += GT) {
+                    const int k2 = (N - k) & (N - 1);
+                    const float2 za = buf[pb_pad5(k)], zb = buf[pb_pad5(k2)];
+                    const float S = za.x * za.x + za.y * za.y + zb.x * zb.x + zb.y * zb.y;
+                    const float Cc = 2.0f * (za.x * zb.x - za.y * zb.y);
+                    const float2 w = make_float2(S + Cc, S - Cc);
+                    buf[pb_pad5(k)] = w; buf[pb_pad5(k2)] = w;
+                }
+                pb_group_sync<G>(bar_id);
+            }
+            {
+                // pass 1 reads natural order (pad5): the windowed frames (step 0) or the spectra (step 2);
+                // pass 2 reads the pass-1 layout and applies the inter-pass twiddles
+                const int sh = pass ? LR : 5;
+                PB_UNROLL for (int t = 0; t < R; t++) { const int i = g + t * (N / R); v[t] = buf[i + (i >> sh)]; }
+                if (step == 0) { PB_UNROLL for (int t = 0; t < R; t++) { v[t].x *= sA; v[t].y *= sB; } }
+                if (pass) {
+                    const int k = g & (R - 1);
+                    PB_UNROLL for (int t = 1; t < R; t++) {
+                        const float2 w = __ldg(&gm.tw_a[t * R + k]);
+                        const float2 x = v[t];
+                        v[t] = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+                    }
+                }
+                pb_group_sync<G>(bar_id);               // every load of this step is done before any store
+            }
+            pb_dft<R>(v);
+            {
+                // pass 1 (Ns = 1): out[g*R + t], skew (index >> LR);  pass 2 (Ns = R): out[(g/R) R^2 + g%R + t R], skew 5
+                const int ob = pass ? ((g >> LR) * (R * R) + (g & (R - 1))) : g * R;
+                const int os = pass ? R : 1;
+                const int osh = pass ? 5 : LR;
+                PB_UNROLL for (int t = 0; t < R; t++) { const int o = ob + t * os; buf[o + (o >> osh)] = v[pb_bitrev(t, LR)]; }
+            }
+            pb_group_sync<G>(bar_id);
+            if (pass && C::F > 1) {
+                // ---- final pass (radix F, Ns = R*R): butterflies are in place
+                constexpr int F = C::F > 1 ? C::F : 2, LF = pb_ilog2(F);
+                PB_UNROLL for (int b = 0; b < C::FB; b++) {
+                    const int j = g + b * GT;             // 0 .. N/F-1 = R*R-1
+                    float2 a[F];
+                    PB_UNROLL for (int t = 0; t < F; t++) a[t] = buf[pb_pad5(j + t * (R * R))];
+                    PB_UNROLL for (int t = 1; t < F; t++) {
+                        const float2 w = __ldg(&gm.tw_b[t * (R * R) + j]);
+                        const float2 x = a[t];
+                        a[t] = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+                    }
+                    pb_dft<F>(a);
+                    PB_UNROLL for (int t = 0; t < F; t++) buf[pb_pad5(j + t * (R * R))] = a[pb_bitrev(t, LF)];
+                }
+                pb_group_sync<G>(bar_id);
+            }
+        }
+
+        if (active) {
+            // ---- r[lag] = ac[lag] / (ac[0] * windowR[lag]) for lags 0..B+1, into shared memory
+            float ra[C::RPL], rb[C::RPL];
+            const float2 ac0 = buf[0];
+            const float iA = ac0.x > 0.0f ? 1.0f / ac0.x : 0.0f, iB = ac0.y > 0.0f ? 1.0f / ac0.y : 0.0f;
+            PB_UNROLL for (int q = 0; q < C::RPL; q++) {
+                const int lag = g + q * GT;
+                ra[q] = 0.0f; rb[q] = 0.0f;
+                if (lag <= B + 1) {
+                    const float2 a = buf[pb_pad5(lag)];
+                    const float iw = lag <= B ? __ldg(&gm.inv_wr[lag]) : 0.0f;
+                    ra[q] = a.x * iA * iw; rb[q] = a.y * iB * iw;
+                }
+            }
+            pb_group_sync<G>(bar_id);
+            PB_UNROLL for (int q = 0; q < C::RPL; q++) {
+                const int lag = g + q * GT;
+                if (lag <= B + 1) { rbase[lag] = lag == 0 ? 1.0f : ra[q]; rbase[rstride + lag] = lag == 0 ? 1.0f : rb[q]; }
+            }
+            pb_group_sync<G>(bar_id);
+        }
+        // ---- candidates: warp 0 of the group takes frame A, warp 1 (or warp 0 again) frame B
+        {
+            const float gpk = (float)ud.global_peak;
+#ifndef PB_SIMT_EMU
+#pragma unroll 1
+#endif
+            for (int f = 0; f < 2; f++) {
+                const int owner = (G > 1) ? f : 0;
+                if (wg != owner || (f == 1 && !hasB)) continue;
+                const int64_t fr = ud.frame_off + fA + f;
+                const float pk = f ? pkB : pkA;
+                float* of = cand_f + fr * gm.max_cand; float* os = cand_s + fr * gm.max_cand;
+                if (!active || pk == 0.0f) {
+                    if (lane == 0) { of[0] = 0.0f; os[0] = 0.0f; ncand[fr] = 1; intensity[fr] = 0.0f; }
+                } else {
+                    if (lane == 0) { const float it = pk / gpk; intensity[fr] = it > 1.0f ? 1.0f : it; }
+                    pb_frame_candidates(rbase + f * rstride, rbase + 2 * rstride + f * (3 * PB_MAXC), gm, lane, of, os, ncand + fr);
+                }
+            }
+        }
+        pb_group_sync<G>(bar_id);     // buf is reused by the next item
+    }
+}

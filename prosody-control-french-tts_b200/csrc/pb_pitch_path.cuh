@@ -1,0 +1,118 @@
+// pb_pitch_path.cuh — K3: Viterbi path finder + median of the voiced frames (see pb_pitch.cuh for the overview).
+#pragma once
+#include "pb_pitch.cuh"
+
+// ------------------------------------------------------------------------------------------------ K3: path finder + median
+// One warp per unit; lane c2 owns candidate c2 of the current frame.  Praat Pitch_pathFinder (fon/Pitch.cpp):
+// Viterbi over the candidate lattice in float64, strict '>' so the lowest-index predecessor wins ties.
+// Back-pointers go to global memory (one byte per candidate); the backtrack then writes selected_array
+// (frequency, strength of the chosen candidate per frame).  Finally np.median of the frequencies > 0
+// (mean of the two middle values) by bisection on the float bit patterns.
+__device__ __forceinline__ double pb_shfl_d(double v, int src) { return __shfl_sync(PB_FULL_MASK, v, src); }
+
+__global__ void __launch_bounds__(128)
+pb_pitch_path_kernel(const PbUnitDev* __restrict__ units, PbPitchGeomDev gm, const float* __restrict__ cand_f,
+                     const float* __restrict__ cand_s, const uint8_t* __restrict__ ncand, const float* __restrict__ intensity,
+                     uint8_t* __restrict__ psi, float* __restrict__ sel_f, float* __restrict__ sel_s,
+                     double* __restrict__ median_out, int32_t* __restrict__ nvoiced_out) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int maxc = gm.max_cand;
+    const double tcorr = 0.01 / gm.dt;
+    const double ojc = gm.octave_jump_cost * tcorr, vuc = gm.voiced_unvoiced_cost * tcorr;
+    for (int u = blockIdx.x * wpb + (threadIdx.x >> 5); u < gm.n_units; u += gridDim.x * wpb) {
+        const PbUnitDev ud = units[u];
+        const int nF = ud.n_frames;
+        const int64_t f0 = ud.frame_off;
+        if (ud.global_peak == 0.0) {
+            // Praat returns before the path finder: every frame voiceless
+            for (int f = lane; f < nF; f += 32) { sel_f[f0 + f] = 0.0f; sel_s[f0 + f] = 0.0f; }
+            if (lane == 0) { median_out[ud.out_index] = 0.0; nvoiced_out[ud.out_index] = 0; }
+            continue;
+        }
+        double delta_prev = 0.0, l2_prev = 0.0;     // of candidate `lane` in the previous frame
+        int voiced_prev = 0, nc_prev = 0;
+        // prefetch frame 0
+        int nc_n = ncand[f0];
+        float cf_n = lane < nc_n ? cand_f[f0 * maxc + lane] : 0.0f, cs_n = lane < nc_n ? cand_s[f0 * maxc + lane] : 0.0f;
+        float in_n = intensity[f0];
+        for (int f = 0; f < nF; f++) {
+            const int nc = nc_n; const float cf = cf_n, cs = cs_n, inten = in_n;
+            if (f + 1 < nF) {
+                const int64_t fr = f0 + f + 1;
+                nc_n = ncand[fr];
+                cf_n = lane < nc_n ? cand_f[fr * maxc + lane] : 0.0f; cs_n = lane < nc_n ? cand_s[fr * maxc + lane] : 0.0f;
+                in_n = intensity[fr];
+            }
+            const double fr_d = (double)cf;
+            const int voiced = fr_d > 0.0 && fr_d < gm.ceiling;
+            double us = gm.silence_threshold <= 0.0 ? 0.0 : 2.0 - (double)inten / (gm.silence_threshold / (1.0 + gm.voicing_threshold));
+            us = gm.voicing_threshold + (us > 0.0 ? us : 0.0);
+            const double l2 = voiced ? log2(fr_d) : 0.0;
+            const double local = voiced ? (double)cs - gm.octave_cost_d * (log2(gm.ceiling) - l2) : us;
+            double best = local; int place = 0;
+            if (f > 0) {
+                best = -1.0e30; place = -1;
+                for (int c1 = 0; c1 < nc_prev; c1++) {
+                    const double dp = pb_shfl_d(delta_prev, c1), lp = pb_shfl_d(l2_prev, c1);
+                    const int vp = __shfl_sync(PB_FULL_MASK, voiced_prev, c1);
+                    double cost;
+                    if (!voiced) cost = vp ? vuc : 0.0;
+                    else cost = vp ? ojc * fabs(lp - l2) : vuc;
+                    const double value = __dadd_rn(__dsub_rn(dp, cost), local);
+                    if (value > best) { best = value; place = c1; }
+                }
+                if (lane < nc) psi[(f0 + f) * maxc + lane] = (uint8_t)place;
+            }
+            delta_prev = best; l2_prev = l2; voiced_prev = voiced; nc_prev = nc;
+        }
+        // terminal candidate: first maximum
+        double bv = lane < nc_prev ? delta_prev : -1.0e300; int bi = lane;
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
+            const double ov = pb_shfl_d(bv, lane ^ o); const int oi = __shfl_xor_sync(PB_FULL_MASK, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        __syncwarp();
+        // backtrack (lane 0), writing selected_array
+        if (lane == 0) {
+            int place = bi;
+            for (int f = nF - 1; f >= 0; f--) {
+                const int64_t fr = f0 + f;
+                sel_f[fr] = cand_f[fr * maxc + place]; sel_s[fr] = cand_s[fr * maxc + place];
+                if (f > 0) place = psi[fr * maxc + place];
+            }
+        }
+        __syncwarp();
+        // ---- np.median(freqs[freqs > 0]) : positive floats order like their bit patterns
+        int nv = 0;
+        for (int f = lane; f < nF; f += 32) nv += sel_f[f0 + f] > 0.0f;
+        nv = pb_warp_sum_i(nv);
+        double med = 0.0;
+        if (nv > 0) {
+            const int k = (nv - 1) >> 1;                       // 0-based rank of the lower middle
+            unsigned lo = 0u, hi = 0x7f800000u;                // smallest pattern with count(<= pattern) >= k+1
+            while (lo < hi) {
+                const unsigned mid = lo + ((hi - lo) >> 1);
+                int c = 0;
+                for (int f = lane; f < nF; f += 32) { const float v = sel_f[f0 + f]; c += (v > 0.0f && __float_as_uint(v) <= mid); }
+                c = pb_warp_sum_i(c);
+                if (c >= k + 1) hi = mid; else lo = mid + 1;
+            }
+            const float lower = __uint_as_float(lo);
+            float upper = lower;
+            if ((nv & 1) == 0) {
+                // the next order statistic: lower again if enough duplicates, else the smallest value above it
+                int c = 0; float nxt = 3.0e38f;
+                for (int f = lane; f < nF; f += 32) {
+                    const float v = sel_f[f0 + f];
+                    if (v > 0.0f) { if (v <= lower) c++; else nxt = fminf(nxt, v); }
+                }
+                c = pb_warp_sum_i(c);
+                PB_UNROLL for (int o = 16; o > 0; o >>= 1) nxt = fminf(nxt, __shfl_xor_sync(PB_FULL_MASK, nxt, o));
+                upper = (c >= k + 2) ? lower : nxt;
+            }
+            med = ((double)lower + (double)upper) / 2.0;
+        }
+        if (lane == 0) { median_out[ud.out_index] = med; nvoiced_out[ud.out_index] = nv; }
+    }
+}
