@@ -59,26 +59,31 @@ def words_and_pauses(intervals) -> list:
     return seq
 
 
-_TOK = re.compile(r"\w+(?:['’\-]\w+)*['’]?|[^\w\s]", re.UNICODE)
+_TOK = re.compile(r"\[\*\]|\w+(?:['’\-]\w+)*['’]?|[^\w\s]", re.UNICODE)
 
 
 def strip_spurious_commas(text: str, pos_of: Callable[[str], str]) -> str:
     """audioPipeline.py:64-81 with the spaCy tagger replaced by an injected ``pos_of(word) -> POS``.
-    Tokenisation stand-in: words vs single punctuation characters, original spacing preserved."""
-    out, last_pos, prev_end = [], None, 0
-    pieces = []
+    Tokenisation stand-in: words vs single punctuation characters.  As in spaCy, whitespace TRAILS its token
+    (``text_with_ws``), so a dropped comma takes the space after it along ("de, la" -> "dela")."""
+    toks, prev_end = [], 0
     for m in _TOK.finditer(text):
-        pieces.append((text[prev_end:m.start()], m.group(0)))
+        if toks:
+            toks[-1][1] += text[prev_end:m.start()]
+        lead = text[prev_end:m.start()] if not toks else ""
+        toks.append([m.group(0), "", lead])
         prev_end = m.end()
-    tail = text[prev_end:]
-    kept = []
-    for lead, tok in pieces:
+    if not toks:
+        return text
+    toks[-1][1] += text[prev_end:]
+    kept, last_pos = [], None
+    for tok, ws, lead in toks:
         is_word = bool(re.match(r"\w", tok))
-        if tok == "," and kept and last_pos in FORBIDDEN_POS:
+        if (tok == "," or tok == "[*]") and kept and last_pos in FORBIDDEN_POS:
             continue
-        kept.append(lead + tok)
+        kept.append(lead + tok + ws)
         last_pos = pos_of(tok) if is_word else "PUNCT"
-    return "".join(kept) + tail
+    return "".join(kept)
 
 
 def build_syntagmes(seq) -> list:

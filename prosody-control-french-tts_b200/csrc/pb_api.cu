@@ -14,6 +14,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -49,6 +50,21 @@ struct PitchTables {        // per (nw, log2n): lives for the life of the handle
 
 struct EvPair { pbEvent_t a, b; int kind; };   // kind: index into the PbTimings float fields
 
+struct LufsKey {
+    int64_t first, len, npad; double meter;
+    bool operator==(const LufsKey& o) const { return first == o.first && len == o.len && npad == o.npad && meter == o.meter; }
+};
+struct LufsKeyHash {
+    size_t operator()(const LufsKey& k) const {
+        uint64_t hsh = (uint64_t)k.first * 0x9E3779B97F4A7C15ull;
+        hsh ^= ((uint64_t)k.len + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+        hsh ^= (uint64_t)k.npad * 0x165667B19E3779F9ull;
+        uint64_t mb; memcpy(&mb, &k.meter, 8);
+        hsh ^= mb * 0x27D4EB2F165667C5ull;
+        return (size_t)(hsh ^ (hsh >> 29));
+    }
+};
+
 }  // namespace
 
 struct PbHandle {
@@ -67,6 +83,7 @@ struct PbHandle {
     size_t ev_used = 0;
     PbTimings last;
     std::map<int, int> occ_cache;
+    std::vector<std::pair<int64_t, int64_t>> lufs_dups;   // (unit, unit it duplicates): filled per call by enqueue_lufs
 };
 
 namespace {
@@ -345,6 +362,11 @@ int enqueue_lufs(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const uint
     PB_CKMEM(h->stage_lunits.ensure((size_t)n * sizeof(PbLufsUnitDev) + 64), "lufs descriptors");
     PbLufsUnitDev* su = (PbLufsUnitDev*)h->stage_lunits.p;
     size_t m = 0; int64_t chunks = 0, samples = 0;
+    // Units that resolve to the same samples and meter have the same loudness (the reference's < 0.4 s / empty-slice
+    // fallbacks send every short syntagme of a file to that file's whole-file value): measure once, copy on the host.
+    h->lufs_dups.clear();
+    std::unordered_map<LufsKey, int64_t, LufsKeyHash> seen;
+    seen.reserve((size_t)n);
     for (int64_t i = 0; i < n; i++) {
         status_flags[i] = 0;
         if (want && !want[i]) continue;
@@ -353,6 +375,11 @@ int enqueue_lufs(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const uint
         const int st = pb_lufs_resolve(u->file_nx[i], u->rate[i], mr, u->has_t1[i], u->t0[i], u->t1[i], &a, &b, &npad);
         status_flags[i] = st;
         if (st & (PB_UNIT_LUFS_ERROR | PB_UNIT_SLICE_ERROR)) continue;
+        {
+            const LufsKey key{u->file_off[i] + a, b - a, npad, mr};
+            auto ins = seen.emplace(key, i);
+            if (!ins.second) { h->lufs_dups.push_back(std::make_pair(i, ins.first->second)); continue; }
+        }
         auto it = meter_ix.find(mr);
         if (it == meter_ix.end()) {
             PbMeterDev md; memset(&md, 0, sizeof md);
@@ -571,6 +598,7 @@ int pb_lufs_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_d
     PB_CK(pbrt_stream_sync(h->stream), "stream sync");
     end_call(h);
     memcpy(lufs, h->stage_out.p, (size_t)n * 8);
+    for (auto& d : h->lufs_dups) lufs[d.first] = lufs[d.second];
     return PB_OK;
 }
 
@@ -608,7 +636,10 @@ int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_o
     end_call(h);
     const char* so = (const char*)h->stage_out.p;
     if (do_pitch) { memcpy(median_f0, so, (size_t)n * 8); memcpy(n_voiced, so + (size_t)n * 8, (size_t)n * 4); }
-    if (do_lufs) memcpy(lufs, so + (size_t)n * 12, (size_t)n * 8);
+    if (do_lufs) {
+        memcpy(lufs, so + (size_t)n * 12, (size_t)n * 8);
+        for (auto& d : h->lufs_dups) lufs[d.first] = lufs[d.second];
+    }
     for (int64_t i = 0; i < n; i++) status[i] = pstat[(size_t)i] | lflags[(size_t)i];
     return PB_OK;
 }

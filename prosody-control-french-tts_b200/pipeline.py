@@ -1,0 +1,134 @@
+"""File-level drop-ins with the reference's own names and signatures.
+
+    get_part_duration(wav_path, t0=0.0, t1=None)   Code/audioPipeline.py:314-323
+    get_median_pitch(wav_path, t0=0.0, t1=None)    Code/audioPipeline.py:326-335
+    get_lufs(wav_path, meter, t0=0.0, t1=None)     Code/audioPipeline.py:338-358
+    get_duration(wav_path)                         Code/audioPipeline.py:360-361
+    measure_prosody_and_build_ssml(self)           Code/audioPipeline.py:261-711  (bind it onto AudioPipeline)
+
+The scalar closures exist for API parity and tests; each call is one GPU unit, so real work should go through
+measure_prosody_and_build_ssml (one GPU call for the whole voice) or prosody_b200.step directly.
+"""
+from __future__ import annotations
+
+import logging
+import re
+import wave
+from pathlib import Path
+
+import numpy as np
+
+from . import intervals as IV
+from . import ssml as SSML
+from . import step as S
+from . import textgrid as TG
+from .batch import Extractor, Units, part_durations, pitch_params
+
+
+class CouldntDecodeError(Exception):
+    """Stands in for pydub.exceptions.CouldntDecodeError (the reference falls back to natural audio on it)."""
+
+
+class Meter:
+    """Shim for ``pyln.Meter(rate)``: the hot path only needs the rate the meter was built with."""
+
+    def __init__(self, rate):
+        self.rate = float(rate)
+
+
+def read_wav(path):
+    """Mono 16-bit PCM WAV -> (int16 samples, rate). Anything else is outside what the pipeline writes."""
+    try:
+        with wave.open(str(path), "rb") as w:
+            if w.getsampwidth() != 2 or w.getnchannels() != 1 or w.getcomptype() != "NONE":
+                raise CouldntDecodeError(f"{path}: only mono 16-bit PCM WAV is supported")
+            return np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.int16), w.getframerate()
+    except (wave.Error, EOFError, FileNotFoundError) as e:
+        raise CouldntDecodeError(str(e)) from e
+
+
+_default_ex: Extractor | None = None
+
+
+def default_extractor() -> Extractor:
+    global _default_ex
+    if _default_ex is None:
+        _default_ex = Extractor(0)
+    return _default_ex
+
+
+def _unit(pcm, sr, t0, t1, meter_rate=None):
+    return Units.from_list([(0, len(pcm), sr, float(t0), None if t1 is None else float(t1), float(meter_rate or sr))])
+
+
+def get_median_pitch(wav_path, t0=0.0, t1=None, extractor: Extractor | None = None) -> float:
+    pcm, sr = read_wav(wav_path)
+    r = (extractor or default_extractor()).median_pitch(pcm, _unit(pcm, sr, t0, t1), pitch_params(**S.REFERENCE_PITCH))
+    if r["status"][0] != 0:
+        raise S.PraatError(f"Praat refuses this sound (status {int(r['status'][0])}): shorter than 3 / pitch_floor s or empty")
+    return float(r["median_f0"][0])
+
+
+def get_lufs(wav_path, meter, t0=0.0, t1=None, extractor: Extractor | None = None) -> float:
+    pcm, sr = read_wav(wav_path)
+    out, st = (extractor or default_extractor()).lufs(pcm, _unit(pcm, sr, t0, t1, meter.rate))
+    if st[0] & 96:
+        raise ValueError("Audio must have length greater than the block size.")
+    return float(out[0])
+
+
+def get_part_duration(wav_path, t0=0.0, t1=None) -> float:
+    pcm, sr = read_wav(wav_path)
+    d, _ = part_durations(_unit(pcm, sr, t0, t1))
+    return float(d[0])
+
+
+def get_duration(wav_path) -> float:
+    return get_part_duration(wav_path)
+
+
+def load_voice(audio_dir, raw_audio_dir, textgrid_dir):
+    """Reads segment_ph*.wav (sorted by number, :364-367), the raw-synth twins and the TextGrids into one PCM buffer."""
+    seg_files = sorted(Path(audio_dir).glob("*.wav"), key=lambda p: int(re.search(r"segment_ph(\d+)", p.stem).group(1)))
+    bufs, segs, off = [], [], 0
+    for wav in seg_files:
+        pcm, sr = read_wav(wav)
+        seg = S.Segment(wav.stem, off, len(pcm), sr, TG.word_intervals(Path(textgrid_dir) / f"{wav.stem}.TextGrid"))
+        bufs.append(pcm); off += len(pcm)
+        try:
+            spcm, ssr = read_wav(Path(raw_audio_dir) / f"{wav.stem}.wav")
+            seg.syn_off, seg.syn_nx, seg.syn_sr = off, len(spcm), ssr
+            bufs.append(spcm); off += len(spcm)
+        except CouldntDecodeError:
+            logging.warning(f"Couldn’t decode raw audio {wav.stem}.wav; falling back to natural metrics")
+        segs.append(seg)
+    return (np.concatenate(bufs) if bufs else np.zeros(0, np.int16)), segs
+
+
+def measure_prosody_and_build_ssml(self, extractor: Extractor | None = None, pos_of: IV.PosFn | None = None):
+    """Drop-in for AudioPipeline.measure_prosody_and_build_ssml: same inputs on disk, same three CSVs out."""
+    logging.info(">>> Measure Prosody & Build SSML")
+    pcm, segs = load_voice(self.voice_dir / "audio", self.raw_audio_dir, self.textgrid_dir)
+    if not segs:
+        logging.error("No audio segments found!")
+        return
+    prosody = dict(pitch_semitones=self.p_st, pitch_lower_clip_factor=self.pitch_lower_clip_factor, volume_pct=self.v_pct,
+                   rate_percent=self.r_pct_clamp, smoothing_alpha=self.alpha, max_jump_percent=self.max_jump,
+                   end_punctuation_pause_ms=self.end_pause_ms, baseline_window=self.baseline_window,
+                   inter_syntagme_pause_factor=self.inter_syntagme_pause_factor,
+                   threshold_duration_before_slowing_down=self.threshold_duration_before_slowing_down,
+                   slow_floor_per_sec=self.slow_floor_per_sec)
+    if pos_of is None:
+        try:
+            pos_of = IV.spacy_pos()
+        except Exception:                     # spaCy / fr_core_news_sm not installed: nothing is filtered
+            logging.warning("spaCy fr_core_news_sm unavailable: comma / pause POS filter disabled")
+            pos_of = IV.NO_POS
+    ex = extractor or default_extractor()
+    pl = S.plan(segs, prosody, pos_of)
+    out = S.measure(ex, pcm, pl, prosody)
+    names = [segs[i].name for i in pl.syn_seg]
+    final, syn_rows, synth_rows = SSML.build(names, pl.syn_words, pl.syn_pause_ms, out["sm_pitch"], out["sm_rate"],
+                                             out["raw_volume"], self.azure_voice, self.inter_syntagme_pause_factor)
+    SSML.write_csvs(final, syn_rows, synth_rows, self.bdd_ssml_csv, self.bdd_syntagme_ssml_csv, self.bdd_syntagme_synth_csv)
+    return out

@@ -98,7 +98,12 @@ def make_word_grid(n_utt: int, dur_s: float, seed: int = 0):
                 e = min(round(t + p, 3), round(dur_s, 3))
                 out.append((t, e, ""))
                 t = e
-        if t < round(dur_s, 3):
-            out.append((t, round(dur_s, 3), ""))
+        end = round(dur_s, 3)
+        if end - t >= 0.06:
+            out.append((t, end, ""))
+        elif t < end and out:
+            # a shorter tail would be a slice Praat refuses (< 3 / pitch_floor s aborts the reference step): extend instead
+            a, _, mark = out[-1]
+            out[-1] = (a, end, mark)
         grids.append(out)
     return grids

@@ -1,0 +1,102 @@
+"""Host logic of the step (intervals, unit planning, baselines, deltas, smoothing) against the loop-by-loop oracle
+restatement of Code/audioPipeline.py:261-711, with the kernels running in the SIMT emulator (CPU, tiny inputs)."""
+import numpy as np
+import pytest
+
+from conftest import speechlike
+
+POS = {"le": "DET", "la": "DET", "de": "ADP", "et": "CCONJ", "que": "SCONJ", "il": "PRON"}
+pos_of = lambda w: POS.get(w.lower().strip(",.?!"), "NOUN")
+
+GRID_A = [(0.0, 0.08, ""), (0.08, 0.41, "Bonjour,"), (0.41, 0.62, "le"), (0.62, 0.70, ""), (0.70, 1.02, "chat"), (1.02, 1.31, "dort."),
+          (1.31, 1.50, ""), (1.50, 1.83, "de,"), (1.83, 2.20, "jour")]
+GRID_B = [(0.0, 0.21, ""), (0.21, 0.55, "Il"), (0.55, 0.95, "mange."), (0.95, 1.25, "Et"), (1.25, 1.32, ""), (1.32, 1.78, "puis?"), (1.78, 2.0, "")]
+
+
+def test_interval_logic_matches_oracle_flow():
+    from oracle import flow as F
+    from prosody_b200 import intervals as IV
+    for grid in (GRID_A, GRID_B):
+        assert IV.words_and_pauses(grid) == F.words_and_pauses(grid)
+        for ep in (150, 400):
+            seq = IV.segment_sequence(grid, pos_of, ep)
+            assert seq == F.segment_sequence(grid, pos_of, ep)
+            mine = IV.syntagmes(seq)
+            ref = F.build_syntagmes(seq)
+            assert [(d["words"], d["start_ms"], d["end_ms"], d["pause_ms"]) for d in ref] == mine
+    assert IV.strip_spurious_commas("de, la, maison", pos_of) == F.strip_spurious_commas("de, la, maison", pos_of) == "delamaison"
+
+
+def test_textgrid_roundtrip(tmp_path):
+    from prosody_b200 import textgrid as TG
+    p = tmp_path / "a.TextGrid"
+    TG.write(p, {"words": [(0.0, 0.5, 'dit "oui"'), (0.5, 0.5, "x"), (0.5, 1.25, "")]}, xmax=1.25)
+    ivs = TG.word_intervals(p)
+    assert ivs == [(0.0, 0.5, 'dit "oui"'), (0.5, 1.25, "")]          # the empty-length interval is dropped
+    short = 'File type = "ooTextFile"\nObject class = "TextGrid"\n\n0\n1.25\n<exists>\n1\n"IntervalTier"\n"words"\n0\n1.25\n2\n0\n0.5\n"a"\n0.5\n1.25\n""\n'
+    assert TG.parse(short).tiers[0].intervals == [(0.0, 0.5, "a"), (0.5, 1.25, "")]
+
+
+@pytest.mark.parametrize("window", [None, 2])
+def test_step_matches_oracle_flow_on_emulator(emu_lib, oracle, window):
+    import prosody_b200 as pb
+    from prosody_b200 import step as S
+    from oracle import flow as F
+    nat = speechlike(3, 2.2, 16000, seed=31)
+    syn = speechlike(3, 2.0, 24000, seed=32)
+    bufs, segs, fsegs, off = [], [], [], 0
+    grids = [GRID_A, GRID_B, GRID_A]
+    for i in range(3):
+        has_syn = i != 1                                   # segment 1: undecodable synth -> natural fallback
+        n_off = off; bufs.append(nat[i]); off += len(nat[i])
+        s_off = None
+        if has_syn:
+            s_off = off; bufs.append(syn[i]); off += len(syn[i])
+        segs.append(S.Segment(f"segment_ph{i+1}", n_off, len(nat[i]), 16000, grids[i], s_off, len(syn[i]) if has_syn else None, 24000 if has_syn else None))
+        fsegs.append(F.Segment(f"segment_ph{i+1}", nat[i], 16000, syn[i] if has_syn else None, 24000 if has_syn else None, grids[i]))
+    pcm = np.concatenate(bufs)
+    prm = dict(baseline_window=window, pitch_semitones=1.3, smoothing_alpha=0.2, end_punctuation_pause_ms=400)
+    ref = F.measure_and_build(fsegs, prm, pos_of)
+    with pb.Extractor(0, lib=emu_lib) as ex:
+        pl = S.plan(segs, prm, pos_of)
+        out = S.measure(ex, pcm, pl, prm)
+    assert pl.n_syn == len(ref["raw_rows"])
+    assert pl.syn_words == [r["syntagme"] for r in ref["raw_rows"]]
+    assert list(pl.syn_pause_ms) == [r["pause"] for r in ref["raw_rows"]]
+    # loudness / durations are float64 on both sides; pitch carries the FP32 kernel tolerance (0.5 %)
+    np.testing.assert_allclose(out["seg_stats"]["l_nat"], [s["l_nat"] for s in ref["seg_stats"]], atol=1e-9)
+    np.testing.assert_allclose(out["seg_stats"]["l_syn"], [s["l_syn"] for s in ref["seg_stats"]], atol=1e-9)
+    assert list(out["seg_stats"]["d_syn"]) == [s["d_syn"] for s in ref["seg_stats"]]
+    np.testing.assert_allclose(out["seg_stats"]["p_nat"], [s["p_nat"] for s in ref["seg_stats"]], rtol=5e-3)
+    np.testing.assert_allclose(out["syn"]["l_syn"], [u["l_syn"] for u in ref["units"]], atol=1e-9)
+    assert list(out["syn"]["nat_total"]) == [u["nat_total"] for u in ref["units"]]
+    assert list(out["syn"]["syn_total"]) == [u["syn_total"] for u in ref["units"]]
+    np.testing.assert_allclose(out["raw_volume"], [r["raw_volume"] for r in ref["raw_rows"]], atol=1e-9)
+    np.testing.assert_allclose(out["raw_rate"], [r["raw_rate"] for r in ref["raw_rows"]], atol=1e-12)
+    np.testing.assert_allclose(out["raw_pitch"], [r["raw_pitch"] for r in ref["raw_rows"]], atol=0.6)   # 0.5 % of F0 ~ 0.5 pct-points
+    np.testing.assert_allclose(out["sm_rate"], ref["sm_r"], atol=1e-12)
+
+
+def test_delta_and_smoothing_helpers_match_python_arithmetic(native_lib):
+    """pb_syntagme_deltas / pb_ema_clamp (host C, no GPU) vs the reference's scalar Python expressions, bit for bit."""
+    import ctypes as C
+    from oracle import flow as F
+    from prosody_b200 import _native as N
+    rng = np.random.default_rng(9)
+    n = 4000
+    p_nat = np.where(rng.random(n) < 0.2, 0.0, rng.uniform(80, 400, n)); f0 = rng.uniform(100, 300, n)
+    loud = rng.uniform(-30, -10, n); l_syn = np.where(rng.random(n) < 0.02, -np.inf, rng.uniform(-35, -8, n))
+    wc = rng.integers(0, 9, n).astype(np.int32); nat = rng.uniform(0.0, 7.0, n); syn = rng.uniform(0.0, 7.0, n)
+    pause = np.where(rng.random(n) < 0.3, rng.integers(0, 900, n), 0).astype(np.int32)
+    prm = dict(F.DEFAULT_PARAMS)
+    dp = N.PbDeltaParams(prm["pitch_semitones"], prm["pitch_lower_clip_factor"], prm["volume_pct"], prm["rate_percent"],
+                         prm["threshold_duration_before_slowing_down"], prm["slow_floor_per_sec"])
+    rp, rv, rr = np.empty(n), np.empty(n), np.empty(n)
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)); ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    assert native_lib.pb_syntagme_deltas(n, d(p_nat), d(f0), d(loud), d(l_syn), ip(wc), d(nat), d(syn), ip(pause), C.byref(dp), d(rp), d(rv), d(rr)) == 0
+    for i in range(n):
+        e = F.syntagme_deltas(p_nat[i], dict(f0=f0[i], loud=loud[i]), l_syn[i], int(wc[i]), nat[i], syn[i], int(pause[i]), prm)
+        assert (rp[i], rv[i], rr[i]) == e, (i, (rp[i], rv[i], rr[i]), e)
+    x = rng.normal(0, 6, 3000); out = np.empty(3000)
+    assert native_lib.pb_ema_clamp(d(x), 3000, 0.4, 5.0, d(out)) == 0
+    assert list(out) == F.smooth(list(x), 0.4, 5.0)
