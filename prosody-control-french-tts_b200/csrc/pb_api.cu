@@ -1,6 +1,11 @@
 // pb_api.cu — the C ABI of libprosody_b200.so (see include/prosody_b200.h): handle, device buffers, per-geometry
 // tables, host-side planning and kernel orchestration.  Built by nvcc for sm_100a; the same source is compiled by
 // g++ against the SIMT emulator for CPU-side tests only (tests/simt_emu).
+//
+// One batch call = plan every unit on the host (float64 index arithmetic, pb_plan.h), then for each PCM SEGMENT:
+// upload that slice of the PCM on the copy stream, and on the compute stream (after an event) upload the descriptors of
+// the units whose samples are now resident and launch K0 / K1+K2 / K3 / K4 for them.  With device-resident PCM there
+// is a single segment; with host PCM the upload of segment s+1 overlaps the kernels of segment s.
 #include "../../include/prosody_b200.h"
 #include "pb_rt.h"
 #include "pb_plan.h"
@@ -65,25 +70,44 @@ struct LufsKeyHash {
     }
 };
 
+struct PitchClass { PbGeomHost g; int gstatus = 0; double rate = 0.0; };
+
+// everything the host decides about a batch before any GPU work
+struct BatchPlan {
+    // pitch
+    std::vector<PbUnitPlan> pplan;            // per caller unit
+    std::vector<int32_t> pclass;              // class index per caller unit, -1 = no pitch work
+    std::vector<PitchClass> classes;
+    int max_cand = 0;
+    int64_t total_frames = 0;
+    // loudness: compact list of the units actually measured (duplicates removed)
+    std::vector<PbLufsUnitDev> lunits;
+    std::vector<int64_t> lneed;               // pcm offset one past the last sample each compact unit reads
+    std::vector<PbMeterDev> meters;
+    std::vector<std::pair<int64_t, int64_t>> dups;     // (caller unit, caller unit it duplicates)
+    int64_t lufs_samples = 0;
+};
+
 }  // namespace
 
 struct PbHandle {
     int device = 0;
     int sm_count = 1, cc_major = 0, cc_minor = 0;
     long long total_mem = 0;
-    pbStream_t own_stream = 0, stream = 0;
+    pbStream_t own_stream = 0, stream = 0, copy_stream = 0;
     std::string err;
     // device buffers (grow on demand)
     DevBuf pcm, units, pair_off, cand_f, cand_s, ncand, inten, psi, sel_f, sel_s, med, nvoiced;
     DevBuf lunits, meters, lstate, lenergy, lufs;
     HostBuf stage_units, stage_pairs, stage_lunits, stage_meters, stage_out;
+    size_t su_off = 0, sp_off = 0, sl_off = 0;           // running offsets (elements) into the pinned staging buffers
     std::map<std::pair<int64_t, int>, PitchTables*> tables;
+    std::map<double, DevBuf*> lufs_tables;                // per meter rate: impulse-state table H
     std::vector<EvPair> evs;
     std::vector<pbEvent_t> ev_pool;
     size_t ev_used = 0;
     PbTimings last;
     std::map<int, int> occ_cache;
-    std::vector<std::pair<int64_t, int64_t>> lufs_dups;   // (unit, unit it duplicates): filled per call by enqueue_lufs
 };
 
 namespace {
@@ -101,22 +125,23 @@ pbEvent_t* next_event(PbHandle* h) {
     if (h->ev_used == h->ev_pool.size()) { pbEvent_t e; pbrt_event_create(&e); h->ev_pool.push_back(e); }
     return &h->ev_pool[h->ev_used++];
 }
-struct ScopedEv {     // records an event pair around a section of the stream
-    PbHandle* h; size_t idx;
-    ScopedEv(PbHandle* h_, int kind) : h(h_) {
+struct ScopedEv {     // records an event pair around a section of a stream
+    PbHandle* h; size_t idx; pbStream_t s;
+    ScopedEv(PbHandle* h_, int kind, pbStream_t s_ = 0) : h(h_), s(s_ ? s_ : h_->stream) {
         EvPair p; p.kind = kind; p.a = *next_event(h); p.b = *next_event(h);
-        pbrt_event_record(&p.a, h->stream);
+        pbrt_event_record(&p.a, s);
         h->evs.push_back(p); idx = h->evs.size() - 1;
     }
-    ~ScopedEv() { pbrt_event_record(&h->evs[idx].b, h->stream); }
+    ~ScopedEv() { pbrt_event_record(&h->evs[idx].b, s); }
 };
 enum { EV_TOTAL = 0, EV_H2D, EV_STATS, EV_FRAMES, EV_PATH, EV_LUFS, EV_INTENSITY, EV_D2H };
 
 void begin_call(PbHandle* h) {
     h->evs.clear(); h->ev_used = 0;
+    h->su_off = h->sp_off = h->sl_off = 0;
     memset(&h->last, 0, sizeof h->last);
 }
-void end_call(PbHandle* h) {   // after the stream has been synchronised
+void end_call(PbHandle* h) {   // after the streams have been synchronised
     float* f = &h->last.total_ms;
     for (auto& p : h->evs) f[p.kind] += pbrt_event_ms(p.a, p.b);
 }
@@ -181,6 +206,128 @@ int get_tables(PbHandle* h, const PbGeomHost& g, PitchTables** out) {
     return PB_OK;
 }
 
+int get_lufs_table(PbHandle* h, PbMeterDev& md) {
+    // H[j] = A^j B: the state j samples after a unit impulse into a filter at rest (device table, cached per rate)
+    const double mr = md.rate;
+    md.Lmax = (int)std::floor(0.1 * mr) + 3;
+    auto ht = h->lufs_tables.find(mr);
+    if (ht == h->lufs_tables.end()) {
+        std::vector<double> H((size_t)md.Lmax * 4);
+        double s[4] = {0, 0, 0, 0};
+        for (int j = 0; j < md.Lmax; j++) {
+            const double x = j == 0 ? 1.0 : 0.0;
+            const double y1 = md.b1[0] * x + s[0];
+            const double np0 = md.b1[1] * x - md.a1[1] * y1 + s[1], np1 = md.b1[2] * x - md.a1[2] * y1;
+            const double y2 = md.b2[0] * y1 + s[2];
+            const double nq0 = md.b2[1] * y1 - md.a2[1] * y2 + s[3], nq1 = md.b2[2] * y1 - md.a2[2] * y2;
+            s[0] = np0; s[1] = np1; s[2] = nq0; s[3] = nq1;
+            for (int r = 0; r < 4; r++) H[(size_t)j * 4 + r] = s[r];
+        }
+        DevBuf* db = new DevBuf();
+        if (db->ensure(H.size() * 8)) { delete db; return fail(h, PB_ENOMEM, "out of memory: %s", "loudness tables"); }
+        pbrt_h2d(db->p, H.data(), H.size() * 8, h->stream);
+        pbrt_stream_sync(h->stream);
+        ht = h->lufs_tables.insert(std::make_pair(mr, db)).first;
+    }
+    md.H = (const double*)ht->second->p;
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ planning (host only)
+int validate_units(PbHandle* h, const PbUnits* u, int64_t pcm_len) {
+    if (!u || u->n_units < 0) return fail(h, PB_EINVAL, "%s", "units is null or n_units < 0");
+    if (u->n_units && (!u->file_off || !u->file_nx || !u->rate || !u->has_t1 || !u->t0 || !u->t1))
+        return fail(h, PB_EINVAL, "%s", "unit arrays must not be null");
+    for (int64_t i = 0; i < u->n_units; i++) {
+        if (u->file_off[i] < 0 || u->file_nx[i] < 0 || (pcm_len >= 0 && u->file_off[i] + u->file_nx[i] > pcm_len))
+            return fail(h, PB_EINVAL, "unit %s: file range outside the pcm buffer", std::to_string(i).c_str());
+        if (!(u->rate[i] > 0.0)) return fail(h, PB_EINVAL, "unit %s: rate must be positive", std::to_string(i).c_str());
+        if (u->file_nx[i] > 0x7fffffffLL) return fail(h, PB_EUNSUPPORTED, "unit %s: file longer than 2^31 samples", std::to_string(i).c_str());
+    }
+    return PB_OK;
+}
+
+// status / n_frames must be zero-initialised by the caller; only wanted units are touched
+int plan_pitch(PbHandle* h, const PbUnits* u, const PbPitchParams* p, const uint8_t* want, int32_t* status, int32_t* n_frames, BatchPlan& bp) {
+    const int64_t n = u->n_units;
+    bp.pplan.resize((size_t)n); bp.pclass.assign((size_t)n, -1);
+    double last_rate = -1.0; int last_cls = -1;
+    for (int64_t i = 0; i < n; i++) {
+        if (want && !want[i]) continue;
+        int ci = last_cls;
+        if (u->rate[i] != last_rate) {
+            ci = -1;
+            for (size_t k = 0; k < bp.classes.size(); k++) if (bp.classes[k].rate == u->rate[i]) { ci = (int)k; break; }
+            if (ci < 0) {
+                PitchClass pc; pc.rate = u->rate[i]; pc.gstatus = pb_geom_for_rate(u->rate[i], *p, pc.g);
+                bp.classes.push_back(pc); ci = (int)bp.classes.size() - 1;
+            }
+            last_rate = u->rate[i]; last_cls = ci;
+        }
+        PitchClass& pc = bp.classes[(size_t)ci];
+        PbUnitPlan& pl = bp.pplan[(size_t)i];
+        pb_plan_pitch_unit(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], *p, pc.g, pc.gstatus, pl);
+        status[i] = pl.status; n_frames[i] = pl.n_frames;
+        if (pl.status == PB_UNIT_OK) { bp.pclass[(size_t)i] = ci; bp.total_frames += pl.n_frames; bp.max_cand = pc.g.max_cand; }
+    }
+    if (bp.max_cand > PB_MAXC) return fail(h, PB_EUNSUPPORTED, "%s", "pitch_ceiling / pitch_floor exceeds 32 candidates per frame");
+    return PB_OK;
+}
+
+// flags must be zero-initialised by the caller; only wanted units are touched
+int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags, BatchPlan& bp) {
+    const int64_t n = u->n_units;
+    std::map<double, int> meter_ix;
+    // Units that resolve to the same samples and meter have the same loudness (the reference's < 0.4 s / empty-slice
+    // fallbacks send every short syntagme of a file to that file's whole-file value): measure once, copy on the host.
+    std::unordered_map<LufsKey, int64_t, LufsKeyHash> seen;
+    seen.reserve((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        if (want && !want[i]) continue;
+        const double mr = u->meter_rate ? u->meter_rate[i] : u->rate[i];
+        int64_t a, b, npad;
+        const int st = pb_lufs_resolve(u->file_nx[i], u->rate[i], mr, u->has_t1[i], u->t0[i], u->t1[i], &a, &b, &npad);
+        flags[i] = st;
+        if (st & (PB_UNIT_LUFS_ERROR | PB_UNIT_SLICE_ERROR)) continue;
+        const LufsKey key{u->file_off[i] + a, b - a, npad, mr};
+        auto ins = seen.emplace(key, i);
+        if (!ins.second) { bp.dups.push_back(std::make_pair(i, ins.first->second)); continue; }
+        auto it = meter_ix.find(mr);
+        if (it == meter_ix.end()) {
+            PbMeterDev md; memset(&md, 0, sizeof md);
+            pb_kweight_coeffs(mr, md.b1, md.a1, md.b2, md.a2);
+            md.rate = mr;
+            int L0 = (int)std::floor(0.1 * mr) - 2; if (L0 < 1) L0 = 1;
+            md.L0 = L0;
+            // columns of A^L: run the homogeneous recurrence from each basis state
+            for (int c = 0; c < 4; c++) {
+                double s[4] = {0, 0, 0, 0}; s[c] = 1.0;
+                for (int step = 1; step < L0 + PB_LUFS_NM; step++) {
+                    const double y1 = s[0];
+                    const double np0 = -md.a1[1] * y1 + s[1], np1 = -md.a1[2] * y1;
+                    const double y2 = md.b2[0] * y1 + s[2];
+                    const double nq0 = md.b2[1] * y1 - md.a2[1] * y2 + s[3], nq1 = md.b2[2] * y1 - md.a2[2] * y2;
+                    s[0] = np0; s[1] = np1; s[2] = nq0; s[3] = nq1;
+                    if (step >= L0) for (int r = 0; r < 4; r++) md.M[step - L0][r * 4 + c] = s[r];
+                }
+            }
+            int rc = get_lufs_table(h, md);
+            if (rc != PB_OK) return rc;
+            bp.meters.push_back(md);
+            it = meter_ix.insert(std::make_pair(mr, (int)bp.meters.size() - 1)).first;
+        }
+        PbLufsUnitDev d;
+        d.pcm_off = u->file_off[i]; d.a = a; d.b = b; d.npad = npad; d.chunk_off = 0;
+        const int64_t len = b - a + npad;
+        d.n_blocks = (int32_t)pb_lufs_num_blocks(len, mr); d.n_chunks = d.n_blocks + 3;
+        d.meter = it->second; d.out_index = (int)i; d.inv_peak = 1.0;
+        bp.lunits.push_back(d);
+        bp.lneed.push_back(u->file_off[i] + b);
+        bp.lufs_samples += len;
+    }
+    return PB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ launches
 template <int LOG2N>
 int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, const int32_t* d_pair_off, const PbPitchGeomDev& gm,
@@ -197,6 +344,11 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
             return fail(h, PB_ECUDA, "cudaFuncSetAttribute: %s", pbrt_error());
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        // ask for just the shared memory the resident CTAs use: the rest of the 228 KB stays L1 for the lookup tables
+        // (window, 1/windowR, twiddles) and the samples consecutive frame pairs share
+        int pct = (int)((100 * ((size_t)per_sm * (smem + 1024)) + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         h->occ_cache[LOG2N] = per_sm;
     } else per_sm = oc->second;
 #endif
@@ -208,97 +360,44 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
     return PB_OK;
 }
 
-struct PitchClass {
-    PbGeomHost g; int gstatus = 0;
-    std::vector<int> ids;       // caller indices of the OK units
-};
-
-// Stage host PCM on the device if needed. Returns the device pointer in *d_pcm.
-int stage_pcm(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, const int16_t** d_pcm) {
-    if (on_device) { *d_pcm = pcm; return PB_OK; }
-    PB_CKMEM(h->pcm.ensure((size_t)pcm_len * 2 + 64), "pcm staging");
-    ScopedEv ev(h, EV_H2D);
-    PB_CK(pbrt_h2d(h->pcm.p, pcm, (size_t)pcm_len * 2, h->stream), "pcm upload");
-    *d_pcm = (const int16_t*)h->pcm.p;
-    return PB_OK;
-}
-
-int validate_units(PbHandle* h, const PbUnits* u, int64_t pcm_len) {
-    if (!u || u->n_units < 0) return fail(h, PB_EINVAL, "%s", "units is null or n_units < 0");
-    if (u->n_units && (!u->file_off || !u->file_nx || !u->rate || !u->has_t1 || !u->t0 || !u->t1))
-        return fail(h, PB_EINVAL, "%s", "unit arrays must not be null");
-    for (int64_t i = 0; i < u->n_units; i++) {
-        if (u->file_off[i] < 0 || u->file_nx[i] < 0 || (pcm_len >= 0 && u->file_off[i] + u->file_nx[i] > pcm_len))
-            return fail(h, PB_EINVAL, "unit %s: file range outside the pcm buffer", std::to_string(i).c_str());
-        if (!(u->rate[i] > 0.0)) return fail(h, PB_EINVAL, "unit %s: rate must be positive", std::to_string(i).c_str());
-        if (u->file_nx[i] > 0x7fffffffLL) return fail(h, PB_EUNSUPPORTED, "unit %s: file longer than 2^31 samples", std::to_string(i).c_str());
-    }
-    return PB_OK;
-}
-
-// Enqueue the whole F0 path for the wanted units. Results land in h->med / h->nvoiced (device, caller-indexed)
-// and per-frame selected values in h->sel_f / h->sel_s / h->inten.
-int enqueue_pitch(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const PbPitchParams* p, const uint8_t* want,
-                  int32_t* status, int32_t* n_frames, std::vector<int64_t>& frame_off, int64_t* total_frames_out) {
-    const int64_t n = u->n_units;
-    std::map<double, PitchClass> classes;
-    std::vector<PbUnitPlan> plans((size_t)n);
-    frame_off.assign((size_t)n + 1, 0);
-    int64_t total = 0; int max_cand = 0;
-    for (int64_t i = 0; i < n; i++) {
-        frame_off[(size_t)i] = total;
-        PbUnitPlan& pl = plans[(size_t)i];
-        pl.status = PB_UNIT_OK; pl.n_frames = 0;
-        if (want && !want[i]) { status[i] = PB_UNIT_OK; n_frames[i] = 0; continue; }
-        auto it = classes.find(u->rate[i]);
-        if (it == classes.end()) {
-            PitchClass pc; pc.gstatus = pb_geom_for_rate(u->rate[i], *p, pc.g);
-            it = classes.insert(std::make_pair(u->rate[i], pc)).first;
-        }
-        PitchClass& pc = it->second;
-        pb_plan_pitch_unit(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], *p, pc.g, pc.gstatus, pl);
-        status[i] = pl.status; n_frames[i] = pl.n_frames;
-        if (pl.status == PB_UNIT_OK) { pc.ids.push_back((int)i); total += pl.n_frames; max_cand = pc.g.max_cand; }
-    }
-    frame_off[(size_t)n] = total;
-    *total_frames_out = total;
-    h->last.n_frames += total;
-    PB_CKMEM(h->med.ensure((size_t)n * 8 + 8) || h->nvoiced.ensure((size_t)n * 4 + 4), "unit results");
-    PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
-    if (total == 0) return PB_OK;
-    if (max_cand > PB_MAXC) return fail(h, PB_EUNSUPPORTED, "%s", "pitch_ceiling / pitch_floor exceeds 32 candidates per frame");
-    const size_t T = (size_t)total;
-    PB_CKMEM(h->cand_f.ensure(T * max_cand * 4) || h->cand_s.ensure(T * max_cand * 4) || h->ncand.ensure(T) ||
-             h->inten.ensure(T * 4) || h->psi.ensure(T * max_cand) || h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4), "frame arrays");
-    // stage all classes' descriptors in one pinned buffer each
-    size_t n_ok = 0; for (auto& kv : classes) n_ok += kv.second.ids.size();
-    PB_CKMEM(h->stage_units.ensure(n_ok * sizeof(PbUnitDev)) || h->stage_pairs.ensure((n_ok + classes.size()) * 4) ||
-             h->units.ensure(n_ok * sizeof(PbUnitDev)) || h->pair_off.ensure((n_ok + classes.size()) * 4), "unit descriptors");
-    size_t uoff = 0, poff = 0;
-    for (auto& kv : classes) {
-        PitchClass& pc = kv.second;
-        const size_t m = pc.ids.size();
+// Enqueue the F0 path for the caller units `ids` (all planned OK). Frame arrays are reused by every launch group:
+// launches are stream-ordered, and per-frame values are only read back when there is a single segment.
+// Results land in h->med / h->nvoiced (device, caller-indexed).
+int launch_pitch(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const PbPitchParams* p, const BatchPlan& bp,
+                 const std::vector<int64_t>& ids, const std::vector<int64_t>* frame_off_by_unit) {
+    if (ids.empty()) return PB_OK;
+    const size_t ncls = bp.classes.size();
+    std::vector<std::vector<int64_t>> by_class(ncls);
+    for (int64_t i : ids) by_class[(size_t)bp.pclass[(size_t)i]].push_back(i);
+    int64_t frame_base = 0;
+    for (size_t ci = 0; ci < ncls; ci++) {
+        const std::vector<int64_t>& cid = by_class[ci];
+        const size_t m = cid.size();
         if (!m) continue;
+        const PitchClass& pc = bp.classes[ci];
         PitchTables* tb = nullptr;
         int rc = get_tables(h, pc.g, &tb);
         if (rc != PB_OK) return rc;
-        PbUnitDev* su = (PbUnitDev*)h->stage_units.p + uoff;
-        int32_t* sp = (int32_t*)h->stage_pairs.p + poff;
+        PbUnitDev* su = (PbUnitDev*)h->stage_units.p + h->su_off;
+        int32_t* sp = (int32_t*)h->stage_pairs.p + h->sp_off;
+        PbUnitDev* du = (PbUnitDev*)h->units.p + h->su_off;
+        int32_t* dp = (int32_t*)h->pair_off.p + h->sp_off;
         int64_t pairs = 0;
         for (size_t k = 0; k < m; k++) {
-            const int i = pc.ids[k];
-            const PbUnitPlan& pl = plans[(size_t)i];
+            const int64_t i = cid[k];
+            const PbUnitPlan& pl = bp.pplan[(size_t)i];
             PbUnitDev& d = su[k];
-            d.pcm_off = u->file_off[i]; d.ix1 = pl.ix1; d.nx = pl.nx; d.frame_off = frame_off[(size_t)i];
+            d.pcm_off = u->file_off[i]; d.ix1 = pl.ix1; d.nx = pl.nx;
+            d.frame_off = frame_off_by_unit ? (*frame_off_by_unit)[(size_t)i] : frame_base;
             d.x1 = pl.x1; d.t1 = pl.t1; d.mean = 0.0; d.global_peak = 0.0;
-            d.file_nx = (int32_t)u->file_nx[i]; d.n_frames = pl.n_frames; d.pair_off = (int32_t)pairs; d.out_index = i;
+            d.file_nx = (int32_t)u->file_nx[i]; d.n_frames = pl.n_frames; d.pair_off = (int32_t)pairs; d.out_index = (int32_t)i;
             sp[k] = (int32_t)pairs;
             pairs += (pl.n_frames + 1) / 2;
-            if (pairs > 0x7ffffff0LL) return fail(h, PB_EUNSUPPORTED, "%s", "more than 2^31 frame pairs in one call; split the batch");
+            frame_base += pl.n_frames;
+            if (pairs > 0x7ffffff0LL) return fail(h, PB_EUNSUPPORTED, "%s", "more than 2^31 frame pairs in one launch; split the batch");
         }
         sp[m] = (int32_t)pairs;
-        PbUnitDev* du = (PbUnitDev*)h->units.p + uoff;
-        int32_t* dp = (int32_t*)h->pair_off.p + poff;
+        h->su_off += m; h->sp_off += m + 1;
         {
             ScopedEv ev(h, EV_H2D);
             PB_CK(pbrt_h2d(du, su, m * sizeof(PbUnitDev), h->stream) || pbrt_h2d(dp, sp, (m + 1) * 4, h->stream), "descriptor upload");
@@ -343,102 +442,169 @@ int enqueue_pitch(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const PbP
             ScopedEv ev(h, EV_PATH);
             const int wpb = 4;
             int grid = (int)std::min<size_t>((m + wpb - 1) / wpb, (size_t)h->sm_count * 16);
-            PB_LAUNCH(pb_pitch_path_kernel, dim3(grid), dim3(wpb * 32), 0, h->stream, du, gm, (const float*)h->cand_f.p,
+            PB_LAUNCH(pb_pitch_path_kernel, dim3(grid), dim3(wpb * 32), 0, h->stream, (const PbUnitDev*)du, gm, (const float*)h->cand_f.p,
                       (const float*)h->cand_s.p, (const uint8_t*)h->ncand.p, (const float*)h->inten.p, (uint8_t*)h->psi.p,
                       (float*)h->sel_f.p, (float*)h->sel_s.p, (double*)h->med.p, (int32_t*)h->nvoiced.p);
             h->last.n_launches++;
         }
         PB_CK(pbrt_last_error(), "pitch kernels");
-        uoff += m; poff += m + 1;
     }
     return PB_OK;
 }
 
-// Enqueue the loudness path. Results land in h->lufs (device, caller-indexed; NaN where the reference would raise).
-int enqueue_lufs(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const uint8_t* want, int32_t* status_flags) {
-    const int64_t n = u->n_units;
-    std::map<double, int> meter_ix;
-    std::vector<PbMeterDev> meters;
-    PB_CKMEM(h->stage_lunits.ensure((size_t)n * sizeof(PbLufsUnitDev) + 64), "lufs descriptors");
-    PbLufsUnitDev* su = (PbLufsUnitDev*)h->stage_lunits.p;
-    size_t m = 0; int64_t chunks = 0, samples = 0;
-    // Units that resolve to the same samples and meter have the same loudness (the reference's < 0.4 s / empty-slice
-    // fallbacks send every short syntagme of a file to that file's whole-file value): measure once, copy on the host.
-    h->lufs_dups.clear();
-    std::unordered_map<LufsKey, int64_t, LufsKeyHash> seen;
-    seen.reserve((size_t)n);
-    for (int64_t i = 0; i < n; i++) {
-        status_flags[i] = 0;
-        if (want && !want[i]) continue;
-        const double mr = u->meter_rate ? u->meter_rate[i] : u->rate[i];
-        int64_t a, b, npad;
-        const int st = pb_lufs_resolve(u->file_nx[i], u->rate[i], mr, u->has_t1[i], u->t0[i], u->t1[i], &a, &b, &npad);
-        status_flags[i] = st;
-        if (st & (PB_UNIT_LUFS_ERROR | PB_UNIT_SLICE_ERROR)) continue;
-        {
-            const LufsKey key{u->file_off[i] + a, b - a, npad, mr};
-            auto ins = seen.emplace(key, i);
-            if (!ins.second) { h->lufs_dups.push_back(std::make_pair(i, ins.first->second)); continue; }
-        }
-        auto it = meter_ix.find(mr);
-        if (it == meter_ix.end()) {
-            PbMeterDev md; memset(&md, 0, sizeof md);
-            pb_kweight_coeffs(mr, md.b1, md.a1, md.b2, md.a2);
-            md.rate = mr;
-            int L0 = (int)std::floor(0.1 * mr) - 2; if (L0 < 1) L0 = 1;
-            md.L0 = L0;
-            // columns of A^L: run the homogeneous recurrence from each basis state
-            for (int c = 0; c < 4; c++) {
-                double s[4] = {0, 0, 0, 0}; s[c] = 1.0;
-                for (int step = 1; step < L0 + PB_LUFS_NM; step++) {
-                    const double y1 = s[0];
-                    const double np0 = -md.a1[1] * y1 + s[1], np1 = -md.a1[2] * y1;
-                    const double y2 = md.b2[0] * y1 + s[2];
-                    const double nq0 = md.b2[1] * y1 - md.a2[1] * y2 + s[3], nq1 = md.b2[2] * y1 - md.a2[2] * y2;
-                    s[0] = np0; s[1] = np1; s[2] = nq0; s[3] = nq1;
-                    if (step >= L0) for (int r = 0; r < 4; r++) md.M[step - L0][r * 4 + c] = s[r];
-                }
-            }
-            meters.push_back(md);
-            it = meter_ix.insert(std::make_pair(mr, (int)meters.size() - 1)).first;
-        }
-        PbLufsUnitDev& d = su[m++];
-        d.pcm_off = u->file_off[i]; d.a = a; d.b = b; d.npad = npad; d.chunk_off = chunks;
-        const int64_t len = b - a + npad;
-        d.n_blocks = (int32_t)pb_lufs_num_blocks(len, mr); d.n_chunks = d.n_blocks + 3;
-        d.meter = it->second; d.out_index = (int)i; d.inv_peak = 1.0;
-        chunks += d.n_chunks; samples += len;
-    }
-    h->last.n_lufs_samples += samples;
-    PB_CKMEM(h->lufs.ensure((size_t)n * 8 + 8), "lufs results");
-    PB_CK(pbrt_memset(h->lufs.p, 0xff, (size_t)n * 8, h->stream), "memset");      // all-ones = NaN
+// Enqueue the loudness path for the compact units `ids` (indices into bp.lunits). Results land in h->lufs.
+int launch_lufs(PbHandle* h, const int16_t* d_pcm, const BatchPlan& bp, const std::vector<int64_t>& ids) {
+    const size_t m = ids.size();
     if (!m) return PB_OK;
-    PB_CKMEM(h->lunits.ensure(m * sizeof(PbLufsUnitDev)) || h->meters.ensure(meters.size() * sizeof(PbMeterDev)) ||
-             h->stage_meters.ensure(meters.size() * sizeof(PbMeterDev)) || h->lstate.ensure((size_t)chunks * 32) ||
-             h->lenergy.ensure((size_t)chunks * 8), "lufs buffers");
-    memcpy(h->stage_meters.p, meters.data(), meters.size() * sizeof(PbMeterDev));
+    PbLufsUnitDev* su = (PbLufsUnitDev*)h->stage_lunits.p + h->sl_off;
+    PbLufsUnitDev* du = (PbLufsUnitDev*)h->lunits.p + h->sl_off;
+    int64_t chunks = 0;
+    for (size_t k = 0; k < m; k++) { su[k] = bp.lunits[(size_t)ids[k]]; su[k].chunk_off = chunks; chunks += su[k].n_chunks; }
+    h->sl_off += m;
     {
         ScopedEv ev(h, EV_H2D);
-        PB_CK(pbrt_h2d(h->lunits.p, su, m * sizeof(PbLufsUnitDev), h->stream) ||
-              pbrt_h2d(h->meters.p, h->stage_meters.p, meters.size() * sizeof(PbMeterDev), h->stream), "lufs descriptor upload");
+        PB_CK(pbrt_h2d(du, su, m * sizeof(PbLufsUnitDev), h->stream), "lufs descriptor upload");
     }
     {
         ScopedEv ev(h, EV_LUFS);
-        PbLufsUnitDev* du = (PbLufsUnitDev*)h->lunits.p;
         const PbMeterDev* dm = (const PbMeterDev*)h->meters.p;
         double* st = (double*)h->lstate.p; double* en = (double*)h->lenergy.p;
         int g1 = (int)std::min<size_t>(m, (size_t)h->sm_count * 8);
         PB_LAUNCH(pb_lufs_peak_kernel, dim3(g1), dim3(256), 0, h->stream, d_pcm, du, (int)m);
         int gc = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 127) / 128, (int64_t)h->sm_count * 16));
-        auto k0 = pb_lufs_chunk_kernel<false>; auto k1 = pb_lufs_chunk_kernel<true>;
-        PB_LAUNCH(k0, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
+        int gw = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 3) / 4, (int64_t)h->sm_count * 16));
+        PB_LAUNCH(pb_lufs_state_kernel, dim3(gw), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st);
         int gu = (int)std::max<size_t>(1, std::min<size_t>((m + 127) / 128, (size_t)h->sm_count * 16));
         PB_LAUNCH(pb_lufs_scan_kernel, dim3(gu), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, st);
-        PB_LAUNCH(k1, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
+        PB_LAUNCH(pb_lufs_energy_kernel, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks,
+                  (const double*)st, en);
         PB_LAUNCH(pb_lufs_gate_kernel, dim3(gu), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, (const double*)en, (double*)h->lufs.p);
         h->last.n_launches += 5;
     }
     PB_CK(pbrt_last_error(), "lufs kernels");
+    return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ one batch call
+struct BatchOut {
+    double* median_f0 = nullptr; int32_t* n_voiced = nullptr; int32_t* n_frames = nullptr;   // pitch (all or none)
+    double* lufs = nullptr; double* duration_s = nullptr; int32_t* status = nullptr;
+    float* frame_f0 = nullptr; float* frame_strength = nullptr; float* frame_intensity = nullptr;   // force a single segment
+};
+
+int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, const PbUnits* u, const PbPitchParams* p,
+              const uint8_t* want_pitch, const uint8_t* want_lufs, const BatchOut& o) {
+    int rc = validate_units(h, u, pcm_len);
+    if (rc != PB_OK) return rc;
+    pbrt_set_device(h->device);
+    begin_call(h);
+    const int64_t n = u->n_units;
+    const bool do_pitch = o.median_f0 && o.n_voiced && o.n_frames, do_lufs = o.lufs != nullptr;
+    const bool want_frames = o.frame_f0 || o.frame_strength || o.frame_intensity;
+    std::vector<int32_t> pstat((size_t)n, 0), lflags((size_t)n, 0);
+    BatchPlan bp;
+    if (do_pitch) {
+        memset(o.n_frames, 0, (size_t)n * 4);
+        rc = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp);
+        if (rc != PB_OK) return rc;
+    }
+    if (do_lufs) { rc = plan_lufs(h, u, want_lufs, lflags.data(), bp); if (rc != PB_OK) return rc; }
+    h->last.n_frames = bp.total_frames; h->last.n_lufs_samples = bp.lufs_samples;
+
+    // ---- segments of the PCM buffer: one when it is already resident, several when it is uploaded here
+    const size_t pcm_bytes = (size_t)pcm_len * 2;
+    int n_seg = 1;
+    if (!on_device && !want_frames && pcm_bytes >= ((size_t)64 << 20)) n_seg = 8;
+    const int64_t seg_samples = n_seg > 1 ? (((pcm_len + n_seg - 1) / n_seg + 127) & ~(int64_t)127) : (pcm_len > 0 ? pcm_len : 1);
+    auto seg_of = [&](int64_t need_end) { int64_t s = need_end > 0 ? (need_end - 1) / seg_samples : 0; return (int)(s >= n_seg ? n_seg - 1 : s); };
+    std::vector<std::vector<int64_t>> pids((size_t)n_seg), lids((size_t)n_seg);
+    std::vector<int64_t> seg_frames((size_t)n_seg, 0), seg_chunks((size_t)n_seg, 0);
+    size_t n_pok = 0;
+    if (do_pitch) for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0) {
+        const int s = seg_of(u->file_off[i] + u->file_nx[i]);
+        pids[(size_t)s].push_back(i); seg_frames[(size_t)s] += bp.pplan[(size_t)i].n_frames; n_pok++;
+    }
+    for (size_t k = 0; k < bp.lunits.size(); k++) {
+        const int s = seg_of(bp.lneed[k]);
+        lids[(size_t)s].push_back((int64_t)k); seg_chunks[(size_t)s] += bp.lunits[k].n_chunks;
+    }
+    // per-frame outputs follow the caller's unit order (the layout pb_pitch_plan reports)
+    std::vector<int64_t> frame_off;
+    if (want_frames) {
+        frame_off.assign((size_t)n + 1, 0);
+        int64_t acc = 0;
+        for (int64_t i = 0; i < n; i++) { frame_off[(size_t)i] = acc; if (bp.pclass[(size_t)i] >= 0) acc += bp.pplan[(size_t)i].n_frames; }
+        frame_off[(size_t)n] = acc;
+    }
+    // ---- size every buffer once, before anything is in flight
+    const size_t T = (size_t)*std::max_element(seg_frames.begin(), seg_frames.end());
+    const size_t CH = (size_t)*std::max_element(seg_chunks.begin(), seg_chunks.end());
+    const size_t mc = (size_t)(bp.max_cand > 0 ? bp.max_cand : 1);
+    PB_CKMEM(h->med.ensure((size_t)n * 8 + 8) || h->nvoiced.ensure((size_t)n * 4 + 4) || h->lufs.ensure((size_t)n * 8 + 8) ||
+             h->stage_out.ensure((size_t)n * 20 + 64), "unit results");
+    if (n_pok) PB_CKMEM(h->cand_f.ensure(T * mc * 4) || h->cand_s.ensure(T * mc * 4) || h->ncand.ensure(T) || h->inten.ensure(T * 4) ||
+                        h->psi.ensure(T * mc) || h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4) ||
+                        h->stage_units.ensure(n_pok * sizeof(PbUnitDev)) || h->units.ensure(n_pok * sizeof(PbUnitDev)) ||
+                        h->stage_pairs.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4) ||
+                        h->pair_off.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4), "pitch buffers");
+    if (!bp.lunits.empty()) {
+        PB_CKMEM(h->stage_lunits.ensure(bp.lunits.size() * sizeof(PbLufsUnitDev)) || h->lunits.ensure(bp.lunits.size() * sizeof(PbLufsUnitDev)) ||
+                 h->meters.ensure(bp.meters.size() * sizeof(PbMeterDev)) || h->stage_meters.ensure(bp.meters.size() * sizeof(PbMeterDev)) ||
+                 h->lstate.ensure(CH * 32) || h->lenergy.ensure(CH * 8), "loudness buffers");
+        memcpy(h->stage_meters.p, bp.meters.data(), bp.meters.size() * sizeof(PbMeterDev));
+    }
+    if (!on_device) PB_CKMEM(h->pcm.ensure(pcm_bytes + 64), "pcm staging");
+    const int16_t* d_pcm = on_device ? pcm : (const int16_t*)h->pcm.p;
+
+    {
+        ScopedEv evt(h, EV_TOTAL);
+        if (do_pitch) PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
+        if (do_lufs) PB_CK(pbrt_memset(h->lufs.p, 0xff, (size_t)n * 8, h->stream), "memset");      // all-ones = NaN
+        if (!bp.lunits.empty()) {
+            ScopedEv ev(h, EV_H2D);
+            PB_CK(pbrt_h2d(h->meters.p, h->stage_meters.p, bp.meters.size() * sizeof(PbMeterDev), h->stream), "meter upload");
+        }
+        std::vector<pbEvent_t> seg_done((size_t)n_seg);
+        if (!on_device) {
+            // every upload is queued up front on the copy stream; the compute stream waits segment by segment
+            ScopedEv ev(h, EV_H2D, h->copy_stream);
+            for (int s = 0; s < n_seg; s++) {
+                const int64_t a = (int64_t)s * seg_samples, b = std::min<int64_t>(pcm_len, a + seg_samples);
+                if (b > a) PB_CK(pbrt_h2d((char*)h->pcm.p + a * 2, pcm + a, (size_t)(b - a) * 2, h->copy_stream), "pcm upload");
+                seg_done[(size_t)s] = *next_event(h);
+                pbrt_event_record(&seg_done[(size_t)s], h->copy_stream);
+            }
+        }
+        for (int s = 0; s < n_seg; s++) {
+            if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[(size_t)s]), "stream wait");
+            if (do_pitch) { rc = launch_pitch(h, d_pcm, u, p, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr); if (rc != PB_OK) return rc; }
+            if (do_lufs) { rc = launch_lufs(h, d_pcm, bp, lids[(size_t)s]); if (rc != PB_OK) return rc; }
+        }
+        ScopedEv evd(h, EV_D2H);
+        char* so = (char*)h->stage_out.p;
+        if (do_pitch) PB_CK(pbrt_d2h(so, h->med.p, (size_t)n * 8, h->stream) || pbrt_d2h(so + (size_t)n * 8, h->nvoiced.p, (size_t)n * 4, h->stream), "result download");
+        if (do_lufs) PB_CK(pbrt_d2h(so + (size_t)n * 12, h->lufs.p, (size_t)n * 8, h->stream), "result download");
+        if (want_frames && bp.total_frames > 0) {
+            const size_t fb = (size_t)bp.total_frames * 4;
+            if (o.frame_f0) PB_CK(pbrt_d2h(o.frame_f0, h->sel_f.p, fb, h->stream), "frame download");
+            if (o.frame_strength) PB_CK(pbrt_d2h(o.frame_strength, h->sel_s.p, fb, h->stream), "frame download");
+            if (o.frame_intensity) PB_CK(pbrt_d2h(o.frame_intensity, h->inten.p, fb, h->stream), "frame download");
+        }
+    }
+    // host arithmetic overlaps the GPU work
+    if (o.duration_s) for (int64_t i = 0; i < n; i++) {
+        int st; o.duration_s[i] = pb_part_duration(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], &st);
+    }
+    PB_CK(pbrt_stream_sync(h->stream), "stream sync");
+    if (!on_device) PB_CK(pbrt_stream_sync(h->copy_stream), "stream sync");
+    end_call(h);
+    const char* so = (const char*)h->stage_out.p;
+    if (do_pitch) { memcpy(o.median_f0, so, (size_t)n * 8); memcpy(o.n_voiced, so + (size_t)n * 8, (size_t)n * 4); }
+    if (do_lufs) {
+        memcpy(o.lufs, so + (size_t)n * 12, (size_t)n * 8);
+        for (auto& d : bp.dups) o.lufs[d.first] = o.lufs[d.second];
+    }
+    if (o.status) for (int64_t i = 0; i < n; i++) o.status[i] = pstat[(size_t)i] | lflags[(size_t)i];
     return PB_OK;
 }
 
@@ -458,7 +624,7 @@ int pb_create(int device, PbHandle** out) {
     PbHandle* h = new PbHandle();
     h->device = device;
     if (pbrt_props(device, &h->sm_count, &h->cc_major, &h->cc_minor, &h->total_mem)) { delete h; return PB_ENODEVICE; }
-    if (pbrt_stream_create(&h->own_stream)) { delete h; return PB_ECUDA; }
+    if (pbrt_stream_create(&h->own_stream) || pbrt_stream_create(&h->copy_stream)) { delete h; return PB_ECUDA; }
     h->stream = h->own_stream;
     memset(&h->last, 0, sizeof h->last);
     *out = h;
@@ -469,14 +635,17 @@ void pb_destroy(PbHandle* h) {
     if (!h) return;
     pbrt_set_device(h->device);
     pbrt_stream_sync(h->stream);
+    pbrt_stream_sync(h->copy_stream);
     DevBuf* dbs[] = {&h->pcm, &h->units, &h->pair_off, &h->cand_f, &h->cand_s, &h->ncand, &h->inten, &h->psi, &h->sel_f, &h->sel_s,
                      &h->med, &h->nvoiced, &h->lunits, &h->meters, &h->lstate, &h->lenergy, &h->lufs};
     for (auto* b : dbs) b->release();
     HostBuf* hbs[] = {&h->stage_units, &h->stage_pairs, &h->stage_lunits, &h->stage_meters, &h->stage_out};
     for (auto* b : hbs) b->release();
     for (auto& kv : h->tables) { kv.second->window.release(); kv.second->inv_wr.release(); kv.second->tw_a.release(); kv.second->tw_b.release(); delete kv.second; }
+    for (auto& kv : h->lufs_tables) { kv.second->release(); delete kv.second; }
     for (auto& e : h->ev_pool) pbrt_event_destroy(e);
     pbrt_stream_destroy(h->own_stream);
+    pbrt_stream_destroy(h->copy_stream);
     delete h;
 }
 
@@ -503,103 +672,24 @@ int pb_device_info(const PbHandle* h, int32_t* sm_count, int32_t* cc_major, int3
     return PB_OK;
 }
 
-void pb_pitch_params_default(PbPitchParams* p) {
-    if (!p) return;
-    p->time_step = 0.0; p->pitch_floor = 150.0; p->pitch_ceiling = 600.0;     // Code/audioPipeline.py:329,332
-    p->periods_per_window = 3.0; p->silence_threshold = 0.03; p->voicing_threshold = 0.45;
-    p->octave_cost = 0.01; p->octave_jump_cost = 0.35; p->voiced_unvoiced_cost = 0.14;
-    p->max_candidates = 15; p->reserved = 0;
-}
-
-int pb_pitch_plan(const PbPitchParams* p, const PbUnits* u, int32_t* status, int32_t* n_frames, int64_t* frame_off) {
-    if (!p || !u || !status || !n_frames) return PB_EINVAL;
-    std::map<double, std::pair<PbGeomHost, int>> geoms;
-    int64_t total = 0;
-    for (int64_t i = 0; i < u->n_units; i++) {
-        auto it = geoms.find(u->rate[i]);
-        if (it == geoms.end()) {
-            PbGeomHost g; int st = pb_geom_for_rate(u->rate[i], *p, g);
-            it = geoms.insert(std::make_pair(u->rate[i], std::make_pair(g, st))).first;
-        }
-        PbUnitPlan pl;
-        pb_plan_pitch_unit(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], *p, it->second.first, it->second.second, pl);
-        status[i] = pl.status; n_frames[i] = pl.n_frames;
-        if (frame_off) frame_off[i] = total;
-        if (pl.status == PB_UNIT_OK) total += pl.n_frames;
-    }
-    if (frame_off) frame_off[u->n_units] = total;
-    return PB_OK;
-}
-
-int pb_part_duration_batch(const PbUnits* u, double* duration_s, int32_t* status) {
-    if (!u || !duration_s) return PB_EINVAL;
-    for (int64_t i = 0; i < u->n_units; i++) {
-        int st;
-        duration_s[i] = pb_part_duration(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], &st);
-        if (status) status[i] = st;
-    }
-    return PB_OK;
-}
-
 int pb_median_pitch_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device, const PbUnits* u, const PbPitchParams* p,
                           double* median_f0, int32_t* n_voiced, int32_t* n_frames, int32_t* status,
                           float* frame_f0, float* frame_strength, float* frame_intensity) {
     if (!h) return PB_EINVAL;
     if (!pcm || !p || !median_f0 || !n_voiced || !n_frames || !status) return fail(h, PB_EINVAL, "%s", "null argument");
-    int rc = validate_units(h, u, pcm_len);
-    if (rc != PB_OK) return rc;
-    pbrt_set_device(h->device);
-    begin_call(h);
-    const int64_t n = u->n_units;
-    std::vector<int64_t> frame_off; int64_t total = 0;
-    {
-        ScopedEv evt(h, EV_TOTAL);
-        const int16_t* d_pcm = nullptr;
-        rc = stage_pcm(h, pcm, pcm_len, pcm_on_device, &d_pcm);
-        if (rc != PB_OK) return rc;
-        rc = enqueue_pitch(h, d_pcm, u, p, nullptr, status, n_frames, frame_off, &total);
-        if (rc != PB_OK) return rc;
-        ScopedEv evd(h, EV_D2H);
-        PB_CKMEM(h->stage_out.ensure((size_t)n * 12 + 64), "result staging");
-        PB_CK(pbrt_d2h(h->stage_out.p, h->med.p, (size_t)n * 8, h->stream) ||
-              pbrt_d2h((char*)h->stage_out.p + (size_t)n * 8, h->nvoiced.p, (size_t)n * 4, h->stream), "result download");
-        if (total > 0) {
-            if (frame_f0) PB_CK(pbrt_d2h(frame_f0, h->sel_f.p, (size_t)total * 4, h->stream), "frame download");
-            if (frame_strength) PB_CK(pbrt_d2h(frame_strength, h->sel_s.p, (size_t)total * 4, h->stream), "frame download");
-            if (frame_intensity) PB_CK(pbrt_d2h(frame_intensity, h->inten.p, (size_t)total * 4, h->stream), "frame download");
-        }
-    }
-    PB_CK(pbrt_stream_sync(h->stream), "stream sync");
-    end_call(h);
-    memcpy(median_f0, h->stage_out.p, (size_t)n * 8);
-    memcpy(n_voiced, (char*)h->stage_out.p + (size_t)n * 8, (size_t)n * 4);
-    return PB_OK;
+    BatchOut o;
+    o.median_f0 = median_f0; o.n_voiced = n_voiced; o.n_frames = n_frames; o.status = status;
+    o.frame_f0 = frame_f0; o.frame_strength = frame_strength; o.frame_intensity = frame_intensity;
+    return run_batch(h, pcm, pcm_len, pcm_on_device, u, p, nullptr, nullptr, o);
 }
 
 int pb_lufs_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device, const PbUnits* u, double* lufs, int32_t* status) {
     if (!h) return PB_EINVAL;
     if (!pcm || !lufs || !status) return fail(h, PB_EINVAL, "%s", "null argument");
-    int rc = validate_units(h, u, pcm_len);
-    if (rc != PB_OK) return rc;
-    pbrt_set_device(h->device);
-    begin_call(h);
-    const int64_t n = u->n_units;
-    {
-        ScopedEv evt(h, EV_TOTAL);
-        const int16_t* d_pcm = nullptr;
-        rc = stage_pcm(h, pcm, pcm_len, pcm_on_device, &d_pcm);
-        if (rc != PB_OK) return rc;
-        rc = enqueue_lufs(h, d_pcm, u, nullptr, status);
-        if (rc != PB_OK) return rc;
-        ScopedEv evd(h, EV_D2H);
-        PB_CKMEM(h->stage_out.ensure((size_t)n * 8 + 64), "result staging");
-        PB_CK(pbrt_d2h(h->stage_out.p, h->lufs.p, (size_t)n * 8, h->stream), "result download");
-    }
-    PB_CK(pbrt_stream_sync(h->stream), "stream sync");
-    end_call(h);
-    memcpy(lufs, h->stage_out.p, (size_t)n * 8);
-    for (auto& d : h->lufs_dups) lufs[d.first] = lufs[d.second];
-    return PB_OK;
+    BatchOut o;
+    o.lufs = lufs; o.status = status;
+    PbPitchParams p; pb_pitch_params_default(&p);
+    return run_batch(h, pcm, pcm_len, pcm_on_device, u, &p, nullptr, nullptr, o);
 }
 
 int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device, const PbUnits* u, const PbPitchParams* p,
@@ -607,105 +697,11 @@ int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_o
                      double* median_f0, int32_t* n_voiced, int32_t* n_frames, double* lufs, double* duration_s, int32_t* status) {
     if (!h) return PB_EINVAL;
     if (!pcm || !p || !status) return fail(h, PB_EINVAL, "%s", "null argument");
-    int rc = validate_units(h, u, pcm_len);
-    if (rc != PB_OK) return rc;
-    pbrt_set_device(h->device);
-    begin_call(h);
-    const int64_t n = u->n_units;
-    const bool do_pitch = median_f0 && n_voiced && n_frames, do_lufs = lufs != nullptr;
-    std::vector<int64_t> frame_off; int64_t total = 0;
-    std::vector<int32_t> lflags((size_t)n, 0), pstat((size_t)n, 0);
-    {
-        ScopedEv evt(h, EV_TOTAL);
-        const int16_t* d_pcm = nullptr;
-        rc = stage_pcm(h, pcm, pcm_len, pcm_on_device, &d_pcm);
-        if (rc != PB_OK) return rc;
-        if (do_pitch) { rc = enqueue_pitch(h, d_pcm, u, p, want_pitch, pstat.data(), n_frames, frame_off, &total); if (rc != PB_OK) return rc; }
-        if (do_lufs) { rc = enqueue_lufs(h, d_pcm, u, want_lufs, lflags.data()); if (rc != PB_OK) return rc; }
-        ScopedEv evd(h, EV_D2H);
-        PB_CKMEM(h->stage_out.ensure((size_t)n * 20 + 64), "result staging");
-        char* so = (char*)h->stage_out.p;
-        if (do_pitch) PB_CK(pbrt_d2h(so, h->med.p, (size_t)n * 8, h->stream) || pbrt_d2h(so + (size_t)n * 8, h->nvoiced.p, (size_t)n * 4, h->stream), "result download");
-        if (do_lufs) PB_CK(pbrt_d2h(so + (size_t)n * 12, h->lufs.p, (size_t)n * 8, h->stream), "result download");
-    }
-    // host arithmetic overlaps the GPU work
-    if (duration_s) for (int64_t i = 0; i < n; i++) {
-        int st; duration_s[i] = pb_part_duration(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], &st);
-    }
-    PB_CK(pbrt_stream_sync(h->stream), "stream sync");
-    end_call(h);
-    const char* so = (const char*)h->stage_out.p;
-    if (do_pitch) { memcpy(median_f0, so, (size_t)n * 8); memcpy(n_voiced, so + (size_t)n * 8, (size_t)n * 4); }
-    if (do_lufs) {
-        memcpy(lufs, so + (size_t)n * 12, (size_t)n * 8);
-        for (auto& d : h->lufs_dups) lufs[d.first] = lufs[d.second];
-    }
-    for (int64_t i = 0; i < n; i++) status[i] = pstat[(size_t)i] | lflags[(size_t)i];
-    return PB_OK;
+    BatchOut o;
+    o.median_f0 = median_f0; o.n_voiced = n_voiced; o.n_frames = n_frames; o.lufs = lufs; o.duration_s = duration_s; o.status = status;
+    return run_batch(h, pcm, pcm_len, pcm_on_device, u, p, want_pitch, want_lufs, o);
 }
 
-int pb_intensity_plan(const PbUnits* u, double minimum_pitch, double time_step, int32_t* status, int32_t* n_frames,
-                      int64_t* frame_off, double* t_first, double* dt_out) {
-    (void)u; (void)minimum_pitch; (void)time_step; (void)status; (void)n_frames; (void)frame_off; (void)t_first; (void)dt_out;
-    return PB_EUNSUPPORTED;
-}
-int pb_intensity_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device, const PbUnits* u, double minimum_pitch,
-                       double time_step, int subtract_mean, float* intensity_db, int32_t* status) {
-    (void)pcm; (void)pcm_len; (void)pcm_on_device; (void)u; (void)minimum_pitch; (void)time_step; (void)subtract_mean; (void)intensity_db; (void)status;
-    return fail(h, PB_EUNSUPPORTED, "%s", "pb_intensity_batch is not wired yet");
-}
-
-int pb_syntagme_deltas(int64_t n, const double* p_nat, const double* base_f0, const double* base_loud, const double* l_syn,
-                       const int32_t* word_count, const double* nat_total_s, const double* syn_total_s, const int32_t* pause_ms,
-                       const PbDeltaParams* prm, double* raw_pitch, double* raw_volume, double* raw_rate) {
-    if (n < 0 || !prm || (n && (!p_nat || !base_f0 || !base_loud || !l_syn || !word_count || !nat_total_s || !syn_total_s ||
-                                !pause_ms || !raw_pitch || !raw_volume || !raw_rate))) return PB_EINVAL;
-    // np.clip(x, lo, hi) == minimum(maximum(x, lo), hi), NaN-propagating
-    auto clip = [](double x, double lo, double hi) { if (x != x) return x; x = x < lo ? lo : x; return x > hi ? hi : x; };
-    for (int64_t i = 0; i < n; i++) {
-        const double pause_s = (double)pause_ms[i] / 1000.0;
-        double d_nat = nat_total_s[i] - pause_s; if (!(d_nat > 1e-4)) d_nat = 1e-4;      // max(x, 1e-4)
-        double d_syn = syn_total_s[i] - pause_s; if (!(d_syn > 1e-4)) d_syn = 1e-4;
-        double p_pct = 0.0;
-        if (p_nat[i] > 0.0) {
-            double st = 12.0 * log2(p_nat[i] / base_f0[i]);
-            st = clip(st, -prm->pitch_semitones * prm->pitch_lower_clip_factor, prm->pitch_semitones);
-            p_pct = (pow(2.0, st / 12.0) - 1.0) * 100.0;
-        }
-        const double db_diff = base_loud[i] - l_syn[i];
-        double v_pct = (pow(10.0, db_diff / 20.0) - 1.0) * 100.0;
-        v_pct = clip(v_pct, -prm->volume_pct, prm->volume_pct);
-        double rp = 0.0;
-        if (word_count[i] > 0) {
-            const double nat_r = (double)word_count[i] / d_nat, syn_r = (double)word_count[i] / d_syn;
-            rp = (nat_r - syn_r) / syn_r * 100.0;
-        }
-        const double length_s = d_nat;
-        double slow = 1.0, fast = 1.0;
-        if (!(length_s <= 1.0)) { slow = pow(length_s, 1.5); fast = sqrt(length_s); }
-        rp = rp < 0.0 ? rp * slow : rp / fast;
-        double over = length_s - prm->threshold_duration_before_slowing_down; if (!(over > 0.0)) over = 0.0;
-        rp = rp - over * prm->slow_floor_per_sec;
-        const double lo = length_s > 5.0 ? prm->rate_percent * 1.5 : prm->rate_percent;
-        const double hi = length_s > 5.0 ? prm->rate_percent * 0.5 : prm->rate_percent;
-        rp = clip(rp, -lo, hi);
-        raw_pitch[i] = p_pct; raw_volume[i] = v_pct; raw_rate[i] = rp;
-    }
-    return PB_OK;
-}
-
-int pb_ema_clamp(const double* x, int64_t n, double alpha, double max_jump, double* out) {
-    if (n < 0 || (n && (!x || !out))) return PB_EINVAL;
-    if (n == 0) return PB_OK;
-    const double beta = 1.0 - alpha;
-    double s = x[0];
-    out[0] = s;
-    for (int64_t i = 1; i < n; i++) { s = alpha * x[i] + beta * s; out[i] = s; }
-    for (int64_t i = 1; i < n; i++) {
-        const double d = out[i] - out[i - 1];
-        if (fabs(d) > max_jump) out[i] = out[i - 1] + (d > 0.0 ? 1.0 : -1.0) * max_jump;
-    }
-    return PB_OK;
-}
+#include "pb_api_host.inc"
 
 }  // extern "C"

@@ -22,8 +22,9 @@ struct PbMeterDev {           // one per distinct pyln.Meter(rate)
     double b2[3], a2[3];      // high pass
     double rate;
     int32_t L0;               // smallest chunk length with a precomputed transition matrix
-    int32_t pad;
+    int32_t Lmax;             // rows of H
     double M[PB_LUFS_NM][16]; // row-major 4x4, M[k] = A^(L0+k) on the state (p0,p1,q0,q1)
+    const double* H;          // [Lmax][4] device table: H[j] = A^j B, the state j samples after a unit impulse
 };
 
 struct PbLufsUnitDev {
@@ -70,12 +71,68 @@ __device__ __forceinline__ int pb_lufs_find_unit(const PbLufsUnitDev* __restrict
     return lo;
 }
 
-// Filters one chunk. ENERGY=false: from a zero state, returns the final state. ENERGY=true: from state_io, returns sum y^2.
-template <bool ENERGY>
+// (1) Zero-state contribution of every chunk.  The state after filtering x[0..L-1] from rest is the linear combination
+// sum_k x[k] * H[L-1-k] with H[j] = A^j B: four independent dot products, no recurrence — one warp per chunk, lanes
+// stride over the samples (coalesced s16 reads, coalesced table reads), shuffle-reduce at the end.
 __global__ void __launch_bounds__(128)
-pb_lufs_chunk_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
-                     const PbMeterDev* __restrict__ meters, long long n_chunks_total,
-                     double* __restrict__ state /* [n_chunks][4] */, double* __restrict__ energy /* [n_chunks] */) {
+pb_lufs_state_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
+                     const PbMeterDev* __restrict__ meters, long long n_chunks_total, double* __restrict__ state /* [n_chunks][4] */) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long ch = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ch < n_chunks_total; ch += (long long)gridDim.x * wpb) {
+        const int u = pb_lufs_find_unit(units, n_units, ch);
+        const PbLufsUnitDev ud = units[u];
+        const PbMeterDev* __restrict__ mt = meters + ud.meter;
+        const int c = (int)(ch - ud.chunk_off);
+        const long long nreal = ud.b - ud.a, n = nreal + ud.npad;
+        const long long lo = pb_lufs_bound(c, mt->rate, n), hi = pb_lufs_bound(c + 1, mt->rate, n);
+        const int L = (int)(hi - lo);
+        const int16_t* __restrict__ p = pcm + ud.pcm_off + ud.a;
+        const double* __restrict__ H = mt->H;
+        const double ip = ud.inv_peak;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (L <= mt->Lmax) {
+            for (int k = lane; k < L; k += 32) {
+                const long long i = lo + k;
+                if (i < nreal) {
+                    const double x = (double)p[i] * ip;
+                    const double* h = H + (size_t)(L - 1 - k) * 4;
+                    s0 += x * h[0]; s1 += x * h[1]; s2 += x * h[2]; s3 += x * h[3];
+                }
+            }
+        } else if (lane == 0) {          // never with the tables the host builds; kept so a bad table cannot corrupt results
+            for (long long i = lo; i < hi; i++) {
+                const double x = i < nreal ? (double)p[i] * ip : 0.0;
+                const double y1 = mt->b1[0] * x + s0;
+                s0 = mt->b1[1] * x - mt->a1[1] * y1 + s1; s1 = mt->b1[2] * x - mt->a1[2] * y1;
+                const double y2 = mt->b2[0] * y1 + s2;
+                s2 = mt->b2[1] * y1 - mt->a2[1] * y2 + s3; s3 = mt->b2[2] * y1 - mt->a2[2] * y2;
+            }
+        }
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(PB_FULL_MASK, s0, o); s1 += __shfl_xor_sync(PB_FULL_MASK, s1, o);
+            s2 += __shfl_xor_sync(PB_FULL_MASK, s2, o); s3 += __shfl_xor_sync(PB_FULL_MASK, s3, o);
+        }
+        if (lane == 0) { state[ch * 4 + 0] = s0; state[ch * 4 + 1] = s1; state[ch * 4 + 2] = s2; state[ch * 4 + 3] = s3; }
+    }
+}
+
+// (3) Energy of the K-weighted signal per chunk, from the chunk's true initial state.  One thread per chunk (the
+// recurrence is sequential); samples arrive eight at a time through aligned 16-byte loads.
+#define PB_LUFS_STEP(xv)                                                  \
+    {                                                                     \
+        const double x_ = (xv);                                           \
+        const double y1_ = b10 * x_ + p0;      /* scipy.signal.lfilter, direct form II transposed */ \
+        p0 = b11 * x_ - a11 * y1_ + p1;                                   \
+        p1 = b12 * x_ - a12 * y1_;                                        \
+        const double y2_ = b20 * y1_ + q0;                                \
+        q0 = b21 * y1_ - a21 * y2_ + q1;                                  \
+        q1 = b22 * y1_ - a22 * y2_;                                       \
+        e += y2_ * y2_;                                                   \
+    }
+__global__ void __launch_bounds__(128)
+pb_lufs_energy_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
+                      const PbMeterDev* __restrict__ meters, long long n_chunks_total,
+                      const double* __restrict__ state /* [n_chunks][4] */, double* __restrict__ energy /* [n_chunks] */) {
     for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < n_chunks_total; ch += (long long)gridDim.x * blockDim.x) {
         const int u = pb_lufs_find_unit(units, n_units, ch);
         const PbLufsUnitDev ud = units[u];
@@ -83,25 +140,25 @@ pb_lufs_chunk_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __res
         const int c = (int)(ch - ud.chunk_off);
         const long long nreal = ud.b - ud.a, n = nreal + ud.npad;
         const long long lo = pb_lufs_bound(c, mt->rate, n), hi = pb_lufs_bound(c + 1, mt->rate, n);
+        const long long real_hi = hi < nreal ? hi : nreal;
         const double b10 = mt->b1[0], b11 = mt->b1[1], b12 = mt->b1[2], a11 = mt->a1[1], a12 = mt->a1[2];
         const double b20 = mt->b2[0], b21 = mt->b2[1], b22 = mt->b2[2], a21 = mt->a2[1], a22 = mt->a2[2];
-        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0, e = 0.0;
-        if (ENERGY) { p0 = state[ch * 4 + 0]; p1 = state[ch * 4 + 1]; q0 = state[ch * 4 + 2]; q1 = state[ch * 4 + 3]; }
+        double p0 = state[ch * 4 + 0], p1 = state[ch * 4 + 1], q0 = state[ch * 4 + 2], q1 = state[ch * 4 + 3], e = 0.0;
         const int16_t* __restrict__ p = pcm + ud.pcm_off + ud.a;
         const double ip = ud.inv_peak;
-        for (long long i = lo; i < hi; i++) {
-            const double x = i < nreal ? (double)p[i] * ip : 0.0;
-            // scipy.signal.lfilter, direct form II transposed
-            const double y1 = b10 * x + p0;
-            p0 = b11 * x - a11 * y1 + p1;
-            p1 = b12 * x - a12 * y1;
-            const double y2 = b20 * y1 + q0;
-            q0 = b21 * y1 - a21 * y2 + q1;
-            q1 = b22 * y1 - a22 * y2;
-            if (ENERGY) e += y2 * y2;
+        long long i = lo;
+        while (i < real_hi && (((size_t)(p + i)) & 15)) { PB_LUFS_STEP((double)p[i] * ip); i++; }
+        while (i + 8 <= real_hi) {
+            const int4 v = *reinterpret_cast<const int4*>(p + i);
+            PB_LUFS_STEP((double)(short)(v.x & 0xffff) * ip); PB_LUFS_STEP((double)(v.x >> 16) * ip);
+            PB_LUFS_STEP((double)(short)(v.y & 0xffff) * ip); PB_LUFS_STEP((double)(v.y >> 16) * ip);
+            PB_LUFS_STEP((double)(short)(v.z & 0xffff) * ip); PB_LUFS_STEP((double)(v.z >> 16) * ip);
+            PB_LUFS_STEP((double)(short)(v.w & 0xffff) * ip); PB_LUFS_STEP((double)(v.w >> 16) * ip);
+            i += 8;
         }
-        if (ENERGY) energy[ch] = e;
-        else { state[ch * 4 + 0] = p0; state[ch * 4 + 1] = p1; state[ch * 4 + 2] = q0; state[ch * 4 + 3] = q1; }
+        while (i < real_hi) { PB_LUFS_STEP((double)p[i] * ip); i++; }
+        while (i < hi) { PB_LUFS_STEP(0.0); i++; }          // pydub's silent padding
+        energy[ch] = e;
     }
 }
 

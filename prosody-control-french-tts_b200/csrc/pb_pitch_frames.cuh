@@ -55,6 +55,59 @@ __device__ __forceinline__ float pb_parabola(float xa, float fa, float xb, float
     return den > 0.0f ? xb - 0.5f * __fdividef(num, den) : xb;
 }
 
+// ------------------------------------------------------------------------------------------------ rare path: too many maxima
+// More maxima than candidate slots (tonal high-frequency content): Praat's sequential insertion — each maximum gets
+// its first-pass frequency (parabola) and strength (sinc, depth 30) and replaces the weakest stored candidate, ranked
+// by strength - octaveCost*log2(minPitch/f), if it beats it.  One warp; returns the candidate count (= max_cand).
+// Kept out of line so the hot path stays compact in the instruction cache.
+__device__ PB_NOINLINE int pb_candidates_overflow(const float* __restrict__ r, float* scratch, const PbPitchGeomDev& gm, int lane) {
+    float* cf = scratch;
+    float* cs = scratch + PB_MAXC;
+    int* imax = (int*)(scratch + 2 * PB_MAXC);
+    const int B = gm.brent_ixmax, lim = gm.scan_lim, maxc = gm.max_cand;
+    const int sub = lane >> 3, sl = lane & 7;
+    int ncf = 1;
+    for (int base = 2; base < lim; base += 32) {
+        const int i = base + lane;
+        const bool pk = i < lim && r[i] > gm.half_voicing && r[i] > r[i - 1] && r[i] >= r[i + 1];
+        unsigned mask = __ballot_sync(PB_FULL_MASK, pk);
+        while (mask) {                                   // four maxima at a time, 8 lanes each
+            unsigned m = mask;
+            for (int q = 0; q < sub; q++) m &= m - 1;
+            const bool have = m != 0;
+            const int ip = have ? base + __ffs((int)m) - 1 : 2;
+            const float dr = 0.5f * (r[ip + 1] - r[ip - 1]), d2r = 2.0f * r[ip] - r[ip - 1] - r[ip + 1];
+            const float x0 = (float)ip + ((have && d2r > 0.0f) ? __fdividef(dr, d2r) : 0.0f);
+            float st = pb_sinc8(r, B, x0, have ? 30 : 0, sl);
+            if (st > 1.0f) st = __fdividef(1.0f, st);
+            const float fq0 = __fdividef(gm.sr, x0);
+            for (int q = 0; q < 4; q++) {
+                const int hv = __shfl_sync(PB_FULL_MASK, (int)have, q * 8);
+                if (!hv) break;
+                const float fq = __shfl_sync(PB_FULL_MASK, fq0, q * 8), sq = __shfl_sync(PB_FULL_MASK, st, q * 8);
+                const int iq = __shfl_sync(PB_FULL_MASK, ip, q * 8);
+                int place = 0;
+                if (ncf < maxc) place = ncf++;
+                else {
+                    // weakest of slots 1..maxc-1; the first minimum wins (Praat scans upward with a strict '<')
+                    float ls = 3.0e38f; int li = lane;
+                    if (lane >= 1 && lane < maxc) ls = cs[lane] - gm.octave_cost * log2f(gm.min_pitch / cf[lane]);
+                    PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
+                        const float os = __shfl_xor_sync(PB_FULL_MASK, ls, o);
+                        const int oi = __shfl_xor_sync(PB_FULL_MASK, li, o);
+                        if (os < ls || (os == ls && oi < li)) { ls = os; li = oi; }
+                    }
+                    if (sq - gm.octave_cost * log2f(gm.min_pitch / fq) > ls) place = li;
+                }
+                if (place && lane == 0) { cf[place] = fq; cs[place] = sq; imax[place] = iq; }
+                __syncwarp();
+            }
+            for (int q = 0; q < 4 && mask; q++) mask &= mask - 1;
+        }
+    }
+    return ncf;
+}
+
 // ------------------------------------------------------------------------------------------------ candidates of one frame
 // One warp. r: normalised autocorrelation for lags 0..B (shared memory). scratch: 3*PB_MAXC words of shared memory.
 // Maxima of r above voicingThreshold/2 between lag 2 and scan_lim-1 become candidates (the weakest is replaced when
@@ -73,62 +126,19 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
     int* imax = (int*)(scratch + 2 * PB_MAXC); // lag of the maximum
     const int B = gm.brent_ixmax, lim = gm.scan_lim, maxc = gm.max_cand;
     const int sub = lane >> 3, sl = lane & 7;
-    // ---- count the maxima
+    // ---- the maxima, in lag order; slot arrays hold PB_MAXC-1 of them, anything beyond max_cand-1 is the rare path
     int total = 0;
     for (int base = 2; base < lim; base += 32) {
         const int i = base + lane;
         const bool pk = i < lim && r[i] > gm.half_voicing && r[i] > r[i - 1] && r[i] >= r[i + 1];
-        total += __popc(__ballot_sync(PB_FULL_MASK, pk));
+        const unsigned mask = __ballot_sync(PB_FULL_MASK, pk);
+        const int slot = 1 + total + __popc(mask & ((1u << lane) - 1u));
+        if (pk && slot < maxc) imax[slot] = i;
+        total += __popc(mask);
     }
-    int ncf = 1;
     const bool overflow = total > maxc - 1;
-    if (total > 0) {
-        for (int base = 2; base < lim; base += 32) {
-            const int i = base + lane;
-            const bool pk = i < lim && r[i] > gm.half_voicing && r[i] > r[i - 1] && r[i] >= r[i + 1];
-            unsigned mask = __ballot_sync(PB_FULL_MASK, pk);
-            if (!overflow) {
-                // common case: every maximum gets its own slot, in lag order
-                if (pk) imax[ncf + __popc(mask & ((1u << lane) - 1u))] = i;
-                ncf += __popc(mask);
-            } else {
-                // rare (tonal high-frequency content): Praat's sequential insert / replace-the-weakest
-                while (mask) {
-                    unsigned m = mask;
-                    for (int q = 0; q < sub; q++) m &= m - 1;
-                    const bool have = m != 0;
-                    const int ip = have ? base + __ffs((int)m) - 1 : 2;
-                    const float dr = 0.5f * (r[ip + 1] - r[ip - 1]), d2r = 2.0f * r[ip] - r[ip - 1] - r[ip + 1];
-                    const float x0 = (float)ip + ((have && d2r > 0.0f) ? dr / d2r : 0.0f);
-                    float st = pb_sinc8(r, B, x0, 30, sl);
-                    if (st > 1.0f) st = 1.0f / st;
-                    const float fq0 = gm.sr / x0;
-                    for (int q = 0; q < 4; q++) {
-                        const int hv = __shfl_sync(PB_FULL_MASK, (int)have, q * 8);
-                        if (!hv) break;
-                        const float fq = __shfl_sync(PB_FULL_MASK, fq0, q * 8), sq = __shfl_sync(PB_FULL_MASK, st, q * 8);
-                        const int iq = __shfl_sync(PB_FULL_MASK, ip, q * 8);
-                        int place = 0;
-                        if (ncf < maxc) place = ncf++;
-                        else {
-                            // weakest of slots 1..maxc-1 by strength - octaveCost*log2(minPitch/f); first minimum wins
-                            float ls = 3.0e38f; int li = lane;
-                            if (lane >= 1 && lane < maxc) ls = cs[lane] - gm.octave_cost * log2f(gm.min_pitch / cf[lane]);
-                            PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
-                                const float os = __shfl_xor_sync(PB_FULL_MASK, ls, o);
-                                const int oi = __shfl_xor_sync(PB_FULL_MASK, li, o);
-                                if (os < ls || (os == ls && oi < li)) { ls = os; li = oi; }
-                            }
-                            if (sq - gm.octave_cost * log2f(gm.min_pitch / fq) > ls) place = li;
-                        }
-                        if (place && lane == 0) { cf[place] = fq; cs[place] = sq; imax[place] = iq; }
-                        __syncwarp();
-                    }
-                    for (int q = 0; q < 4 && mask; q++) mask &= mask - 1;
-                }
-            }
-        }
-    }
+    int ncf = 1 + total;
+    if (overflow) ncf = pb_candidates_overflow(r, scratch, gm, lane);      // out of line: tonal high-frequency content only
     __syncwarp();
     if (lane == 0) { out_f[0] = 0.0f; out_s[0] = 0.0f; *out_n = (uint8_t)ncf; }
     // ---- candidates that can never be voiced keep first-pass values (sorted by lag unless the overflow path ran)
@@ -215,9 +225,20 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
     const int pk_lo = max(0, gm.half_nw - gm.half_period), pk_hi = min(gm.nw, gm.half_nw + gm.half_period);   // [lo, hi)
     const int mean_n0 = gm.half_nw - gm.nsamp_period;   // local mean spans frame samples [mean_n0, mean_n0 + 2 P)
 
-    for (int item = blockIdx.x * C::GROUPS_PER_CTA + group; item < gm.n_pairs; item += gridDim.x * C::GROUPS_PER_CTA) {
-        const int u = pb_upper_unit(pair_off, gm.n_units, item);
-        const PbUnitDev ud = units[u];
+    // Blocked distribution: a group walks a contiguous range of frame pairs, so consecutive iterations stay in the same
+    // unit (one descriptor fetch) and re-read the 75 % of samples they share with the previous pair from L1.
+    const int n_groups = gridDim.x * C::GROUPS_PER_CTA;
+    const int per_group = (gm.n_pairs + n_groups - 1) / n_groups;
+    const int item_begin = (blockIdx.x * C::GROUPS_PER_CTA + group) * per_group;
+    const int item_end = min(gm.n_pairs, item_begin + per_group);
+    int u = item_begin < item_end ? pb_upper_unit(pair_off, gm.n_units, item_begin) : 0;
+    PbUnitDev ud = units[u];
+    int u_end = item_begin < item_end ? pair_off[u + 1] : 0;
+    for (int item = item_begin; item < item_end; item++) {
+        if (item >= u_end) {
+            do { u++; u_end = pair_off[u + 1]; } while (item >= u_end);
+            ud = units[u];
+        }
         const int fA = 2 * (item - ud.pair_off);
         const bool hasB = fA + 1 < ud.n_frames;
         const bool global_silent = ud.global_peak == 0.0;
@@ -305,8 +326,14 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
             {
                 // pass 1 reads natural order (pad5): the windowed frames (step 0) or the spectra (step 2);
                 // pass 2 reads the pass-1 layout and applies the inter-pass twiddles
-                const int sh = pass ? LR : 5;
-                PB_UNROLL for (int t = 0; t < R; t++) { const int i = g + t * (N / R); v[t] = buf[i + (i >> sh)]; }
+                if (R == 32) {
+                    // i = g + 32 G t  ->  i + (i >> 5) = g + (g >> 5) + 33 G t: one base, compile-time offsets
+                    const float2* src = buf + (g + (g >> 5));
+                    PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * (33 * G)];
+                } else {
+                    const int sh = pass ? LR : 5;
+                    PB_UNROLL for (int t = 0; t < R; t++) { const int i = g + t * (N / R); v[t] = buf[i + (i >> sh)]; }
+                }
                 if (step == 0) { PB_UNROLL for (int t = 0; t < R; t++) { v[t].x *= sA; v[t].y *= sB; } }
                 if (pass) {
                     const int k = g & (R - 1);
@@ -321,10 +348,17 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
             pb_dft<R>(v);
             {
                 // pass 1 (Ns = 1): out[g*R + t], skew (index >> LR);  pass 2 (Ns = R): out[(g/R) R^2 + g%R + t R], skew 5
-                const int ob = pass ? ((g >> LR) * (R * R) + (g & (R - 1))) : g * R;
-                const int os = pass ? R : 1;
-                const int osh = pass ? 5 : LR;
-                PB_UNROLL for (int t = 0; t < R; t++) { const int o = ob + t * os; buf[o + (o >> osh)] = v[pb_bitrev(t, LR)]; }
+                if (R == 32) {
+                    // pass 1: 32 g + t -> + (index >> 5) = 33 g + t;  pass 2: (g>>5) 1024 + (g&31) + 32 t -> (g>>5) 1056 + (g&31) + 33 t
+                    float2* dst = buf + (pass ? ((g >> 5) * 1056 + (g & 31)) : 33 * g);
+                    const int ds = pass ? 33 : 1;
+                    PB_UNROLL for (int t = 0; t < R; t++) dst[t * ds] = v[pb_bitrev(t, LR)];
+                } else {
+                    const int ob = pass ? ((g >> LR) * (R * R) + (g & (R - 1))) : g * R;
+                    const int os = pass ? R : 1;
+                    const int osh = pass ? 5 : LR;
+                    PB_UNROLL for (int t = 0; t < R; t++) { const int o = ob + t * os; buf[o + (o >> osh)] = v[pb_bitrev(t, LR)]; }
+                }
             }
             pb_group_sync<G>(bar_id);
             if (pass && C::F > 1) {

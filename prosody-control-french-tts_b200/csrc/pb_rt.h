@@ -14,7 +14,9 @@ typedef struct { double t; } pbEvent_t;
 #define PB_DYN_SMEM(name) unsigned char* name = (unsigned char*)pb_emu::g_blk->dyn_smem
 #define PB_GROUP_SYNC(id, nthreads) pb_emu::named_barrier((id), (nthreads))
 #define PB_UNROLL
+#define PB_NOINLINE __attribute__((noinline))
 #else
+#define PB_NOINLINE __noinline__
 #include <cuda_runtime.h>
 typedef cudaStream_t pbStream_t;
 typedef cudaEvent_t pbEvent_t;
@@ -41,6 +43,7 @@ static inline int pbrt_memset(void* d, int v, size_t n, pbStream_t) { memset(d, 
 static inline int pbrt_stream_create(pbStream_t* s) { *s = nullptr; return 0; }
 static inline int pbrt_stream_destroy(pbStream_t) { return 0; }
 static inline int pbrt_stream_sync(pbStream_t) { return 0; }
+static inline int pbrt_stream_wait_event(pbStream_t, pbEvent_t) { return 0; }
 static inline int pbrt_event_create(pbEvent_t* e) { e->t = 0; return 0; }
 static inline int pbrt_event_destroy(pbEvent_t) { return 0; }
 static inline int pbrt_event_record(pbEvent_t* e, pbStream_t) {
@@ -64,6 +67,7 @@ static inline int pbrt_memset(void* d, int v, size_t n, pbStream_t st) { return 
 static inline int pbrt_stream_create(pbStream_t* s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) != cudaSuccess; }
 static inline int pbrt_stream_destroy(pbStream_t s) { return cudaStreamDestroy(s) != cudaSuccess; }
 static inline int pbrt_stream_sync(pbStream_t s) { return cudaStreamSynchronize(s) != cudaSuccess; }
+static inline int pbrt_stream_wait_event(pbStream_t s, pbEvent_t e) { return cudaStreamWaitEvent(s, e, 0) != cudaSuccess; }
 static inline int pbrt_event_create(pbEvent_t* e) { return cudaEventCreate(e) != cudaSuccess; }
 static inline int pbrt_event_destroy(pbEvent_t e) { return cudaEventDestroy(e) != cudaSuccess; }
 static inline int pbrt_event_record(pbEvent_t* e, pbStream_t s) { return cudaEventRecord(*e, s) != cudaSuccess; }
