@@ -99,7 +99,7 @@ typedef struct PbTimings {
     int64_t n_frames;      /* pitch frames analysed */
     int64_t n_lufs_samples;/* samples filtered */
     int32_t n_launches;    /* kernels launched */
-    int32_t reserved;
+    float host_plan_ms;    /* host wall time spent planning the units before the first enqueue */
 } PbTimings;
 
 int pb_abi_version(void);

@@ -38,7 +38,7 @@ class PbUnits(C.Structure):
 class PbTimings(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("unit_stats_ms", C.c_float), ("frames_ms", C.c_float),
                 ("path_ms", C.c_float), ("lufs_ms", C.c_float), ("intensity_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("n_frames", C.c_int64), ("n_lufs_samples", C.c_int64), ("n_launches", C.c_int32), ("reserved", C.c_int32)]
+                ("n_frames", C.c_int64), ("n_lufs_samples", C.c_int64), ("n_launches", C.c_int32), ("host_plan_ms", C.c_float)]
 
 
 class PbDeltaParams(C.Structure):

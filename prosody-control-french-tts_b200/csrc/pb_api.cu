@@ -15,6 +15,7 @@
 #include "pb_lufs.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -363,8 +364,12 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
 // Enqueue the F0 path for the caller units `ids` (all planned OK). Frame arrays are reused by every launch group:
 // launches are stream-ordered, and per-frame values are only read back when there is a single segment.
 // Results land in h->med / h->nvoiced (device, caller-indexed).
-int launch_pitch(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const PbPitchParams* p, const BatchPlan& bp,
-                 const std::vector<int64_t>& ids, const std::vector<int64_t>* frame_off_by_unit) {
+struct PitchLaunch { int cls; size_t uoff, poff, m; int64_t pairs; };
+struct LufsLaunch { size_t off, m; int64_t chunks; };
+
+// Fill the pinned descriptor staging for the caller units `ids` (all planned OK), one launch group per geometry class.
+int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::vector<int64_t>& ids,
+                const std::vector<int64_t>* frame_off_by_unit, std::vector<PitchLaunch>& out) {
     if (ids.empty()) return PB_OK;
     const size_t ncls = bp.classes.size();
     std::vector<std::vector<int64_t>> by_class(ncls);
@@ -374,14 +379,11 @@ int launch_pitch(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const PbPi
         const std::vector<int64_t>& cid = by_class[ci];
         const size_t m = cid.size();
         if (!m) continue;
-        const PitchClass& pc = bp.classes[ci];
-        PitchTables* tb = nullptr;
-        int rc = get_tables(h, pc.g, &tb);
+        PitchTables* tb_unused = nullptr;                      // build / upload the tables now, before any PCM copy is queued
+        int rc = get_tables(h, bp.classes[ci].g, &tb_unused);
         if (rc != PB_OK) return rc;
         PbUnitDev* su = (PbUnitDev*)h->stage_units.p + h->su_off;
         int32_t* sp = (int32_t*)h->stage_pairs.p + h->sp_off;
-        PbUnitDev* du = (PbUnitDev*)h->units.p + h->su_off;
-        int32_t* dp = (int32_t*)h->pair_off.p + h->sp_off;
         int64_t pairs = 0;
         for (size_t k = 0; k < m; k++) {
             const int64_t i = cid[k];
@@ -397,11 +399,26 @@ int launch_pitch(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const PbPi
             if (pairs > 0x7ffffff0LL) return fail(h, PB_EUNSUPPORTED, "%s", "more than 2^31 frame pairs in one launch; split the batch");
         }
         sp[m] = (int32_t)pairs;
+        PitchLaunch L; L.cls = (int)ci; L.uoff = h->su_off; L.poff = h->sp_off; L.m = m; L.pairs = pairs;
+        out.push_back(L);
         h->su_off += m; h->sp_off += m + 1;
-        {
-            ScopedEv ev(h, EV_H2D);
-            PB_CK(pbrt_h2d(du, su, m * sizeof(PbUnitDev), h->stream) || pbrt_h2d(dp, sp, (m + 1) * 4, h->stream), "descriptor upload");
-        }
+    }
+    return PB_OK;
+}
+
+// Launch K0, K1+K2, K3 for one staged group (its descriptors are already on the device). Frame arrays are reused by
+// every group: launches are stream-ordered, and per-frame values are only read back when there is a single segment.
+// Results land in h->med / h->nvoiced (device, caller-indexed).
+int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p, const BatchPlan& bp, const PitchLaunch& L) {
+    {
+        const PitchClass& pc = bp.classes[(size_t)L.cls];
+        const size_t m = L.m;
+        const int64_t pairs = L.pairs;
+        PitchTables* tb = nullptr;
+        int rc = get_tables(h, pc.g, &tb);
+        if (rc != PB_OK) return rc;
+        PbUnitDev* du = (PbUnitDev*)h->units.p + L.uoff;
+        int32_t* dp = (int32_t*)h->pair_off.p + L.poff;
         PbPitchGeomDev gm;
         memset(&gm, 0, sizeof gm);
         gm.nw = (int)pc.g.nw; gm.half_nw = (int)pc.g.half_nw; gm.nsamp_period = (int)pc.g.nsamp_period; gm.half_period = (int)pc.g.half_period;
@@ -453,18 +470,20 @@ int launch_pitch(PbHandle* h, const int16_t* d_pcm, const PbUnits* u, const PbPi
 }
 
 // Enqueue the loudness path for the compact units `ids` (indices into bp.lunits). Results land in h->lufs.
-int launch_lufs(PbHandle* h, const int16_t* d_pcm, const BatchPlan& bp, const std::vector<int64_t>& ids) {
+void stage_lufs(PbHandle* h, const BatchPlan& bp, const std::vector<int64_t>& ids, LufsLaunch& L) {
     const size_t m = ids.size();
-    if (!m) return PB_OK;
     PbLufsUnitDev* su = (PbLufsUnitDev*)h->stage_lunits.p + h->sl_off;
-    PbLufsUnitDev* du = (PbLufsUnitDev*)h->lunits.p + h->sl_off;
     int64_t chunks = 0;
     for (size_t k = 0; k < m; k++) { su[k] = bp.lunits[(size_t)ids[k]]; su[k].chunk_off = chunks; chunks += su[k].n_chunks; }
+    L.off = h->sl_off; L.m = m; L.chunks = chunks;
     h->sl_off += m;
-    {
-        ScopedEv ev(h, EV_H2D);
-        PB_CK(pbrt_h2d(du, su, m * sizeof(PbLufsUnitDev), h->stream), "lufs descriptor upload");
-    }
+}
+
+int launch_lufs_group(PbHandle* h, const int16_t* d_pcm, const LufsLaunch& L) {
+    const size_t m = L.m;
+    if (!m) return PB_OK;
+    PbLufsUnitDev* du = (PbLufsUnitDev*)h->lunits.p + L.off;
+    const int64_t chunks = L.chunks;
     {
         ScopedEv ev(h, EV_LUFS);
         const PbMeterDev* dm = (const PbMeterDev*)h->meters.p;
@@ -502,6 +521,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     const bool do_pitch = o.median_f0 && o.n_voiced && o.n_frames, do_lufs = o.lufs != nullptr;
     const bool want_frames = o.frame_f0 || o.frame_strength || o.frame_intensity;
     std::vector<int32_t> pstat((size_t)n, 0), lflags((size_t)n, 0);
+    const auto t_plan0 = std::chrono::steady_clock::now();
     BatchPlan bp;
     if (do_pitch) {
         memset(o.n_frames, 0, (size_t)n * 4);
@@ -555,30 +575,45 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     }
     if (!on_device) PB_CKMEM(h->pcm.ensure(pcm_bytes + 64), "pcm staging");
     const int16_t* d_pcm = on_device ? pcm : (const int16_t*)h->pcm.p;
+    // ---- descriptors of every segment into pinned staging (host work only)
+    std::vector<std::vector<PitchLaunch>> pl((size_t)n_seg);
+    std::vector<LufsLaunch> ll((size_t)n_seg);
+    for (int s = 0; s < n_seg; s++) {
+        if (do_pitch) { rc = stage_pitch(h, u, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr, pl[(size_t)s]); if (rc != PB_OK) return rc; }
+        ll[(size_t)s].off = 0; ll[(size_t)s].m = 0; ll[(size_t)s].chunks = 0;
+        if (do_lufs && !lids[(size_t)s].empty()) stage_lufs(h, bp, lids[(size_t)s], ll[(size_t)s]);
+    }
+    h->last.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
 
     {
         ScopedEv evt(h, EV_TOTAL);
         if (do_pitch) PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
         if (do_lufs) PB_CK(pbrt_memset(h->lufs.p, 0xff, (size_t)n * 8, h->stream), "memset");      // all-ones = NaN
-        if (!bp.lunits.empty()) {
-            ScopedEv ev(h, EV_H2D);
-            PB_CK(pbrt_h2d(h->meters.p, h->stage_meters.p, bp.meters.size() * sizeof(PbMeterDev), h->stream), "meter upload");
-        }
+        // All host->device traffic goes through the copy stream, descriptors FIRST: H2D copies are served in FIFO order
+        // by the copy engine, so a small descriptor upload queued behind the PCM would hold every kernel back until
+        // the whole PCM has landed.  The compute stream itself never issues an H2D copy.
+        pbEvent_t desc_done = *next_event(h);
         std::vector<pbEvent_t> seg_done((size_t)n_seg);
-        if (!on_device) {
-            // every upload is queued up front on the copy stream; the compute stream waits segment by segment
+        {
             ScopedEv ev(h, EV_H2D, h->copy_stream);
-            for (int s = 0; s < n_seg; s++) {
+            if (h->su_off) PB_CK(pbrt_h2d(h->units.p, h->stage_units.p, h->su_off * sizeof(PbUnitDev), h->copy_stream) ||
+                                 pbrt_h2d(h->pair_off.p, h->stage_pairs.p, h->sp_off * 4, h->copy_stream), "descriptor upload");
+            if (h->sl_off) PB_CK(pbrt_h2d(h->lunits.p, h->stage_lunits.p, h->sl_off * sizeof(PbLufsUnitDev), h->copy_stream) ||
+                                 pbrt_h2d(h->meters.p, h->stage_meters.p, bp.meters.size() * sizeof(PbMeterDev), h->copy_stream), "descriptor upload");
+            pbrt_event_record(&desc_done, h->copy_stream);
+            if (!on_device) for (int s = 0; s < n_seg; s++) {
                 const int64_t a = (int64_t)s * seg_samples, b = std::min<int64_t>(pcm_len, a + seg_samples);
                 if (b > a) PB_CK(pbrt_h2d((char*)h->pcm.p + a * 2, pcm + a, (size_t)(b - a) * 2, h->copy_stream), "pcm upload");
                 seg_done[(size_t)s] = *next_event(h);
                 pbrt_event_record(&seg_done[(size_t)s], h->copy_stream);
             }
         }
+        PB_CK(pbrt_stream_wait_event(h->stream, desc_done), "stream wait");
         for (int s = 0; s < n_seg; s++) {
             if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[(size_t)s]), "stream wait");
-            if (do_pitch) { rc = launch_pitch(h, d_pcm, u, p, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr); if (rc != PB_OK) return rc; }
-            if (do_lufs) { rc = launch_lufs(h, d_pcm, bp, lids[(size_t)s]); if (rc != PB_OK) return rc; }
+            for (const PitchLaunch& L : pl[(size_t)s]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
+            rc = launch_lufs_group(h, d_pcm, ll[(size_t)s]);
+            if (rc != PB_OK) return rc;
         }
         ScopedEv evd(h, EV_D2H);
         char* so = (char*)h->stage_out.p;
@@ -596,7 +631,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         int st; o.duration_s[i] = pb_part_duration(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], &st);
     }
     PB_CK(pbrt_stream_sync(h->stream), "stream sync");
-    if (!on_device) PB_CK(pbrt_stream_sync(h->copy_stream), "stream sync");
+    PB_CK(pbrt_stream_sync(h->copy_stream), "stream sync");
     end_call(h);
     const char* so = (const char*)h->stage_out.p;
     if (do_pitch) { memcpy(o.median_f0, so, (size_t)n * 8); memcpy(o.n_voiced, so + (size_t)n * 8, (size_t)n * 4); }
