@@ -108,7 +108,9 @@ struct PbHandle {
     std::vector<pbEvent_t> ev_pool;
     size_t ev_used = 0;
     PbTimings last;
-    std::map<int, int> occ_cache;
+    std::map<std::pair<int, size_t>, int> occ_cache;      // (LOG2N, dynamic smem bytes) -> resident CTAs per SM
+    std::map<int, size_t> occ_last;                        // LOG2N -> footprint the function attributes were last set for
+    int64_t cur_pcm_len = 0;                               // samples in the pcm buffer of the call in progress
 };
 
 namespace {
@@ -334,23 +336,27 @@ template <int LOG2N>
 int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, const int32_t* d_pair_off, const PbPitchGeomDev& gm,
                   float* cand_f, float* cand_s, uint8_t* ncand, float* inten) {
     typedef PbFftCfg<LOG2N> C;
-    const size_t smem = (size_t)C::GROUPS_PER_CTA * (C::BUF + 8 * C::G) * sizeof(float2);
+    const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + 2 * (size_t)gm.pre_cap * sizeof(int16_t));
     const int threads = C::WARPS_PER_CTA * 32;
     auto kfn = pb_pitch_frames_kernel<LOG2N>;
     int per_sm = 2;
 #ifndef PB_SIMT_EMU
-    auto oc = h->occ_cache.find(LOG2N);
-    if (oc == h->occ_cache.end()) {
+    // function attributes persist, so they are (re)applied whenever the shared-memory footprint of this instantiation
+    // changes (another analysis geometry with the same FFT size)
+    const auto okey = std::make_pair((int)LOG2N, smem);
+    auto oc = h->occ_cache.find(okey);
+    if (oc == h->occ_cache.end() || h->occ_last[LOG2N] != smem) {
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail(h, PB_ECUDA, "cudaFuncSetAttribute: %s", pbrt_error());
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         // ask for just the shared memory the resident CTAs use: the rest of the 228 KB stays L1 for the lookup tables
-        // (window, 1/windowR, twiddles) and the samples consecutive frame pairs share
+        // (window, 1/windowR, twiddles)
         int pct = (int)((100 * ((size_t)per_sm * (smem + 1024)) + 228 * 1024 - 1) / (228 * 1024));
         if (pct > 100) pct = 100;
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        h->occ_cache[LOG2N] = per_sm;
+        h->occ_cache[okey] = per_sm;
+        h->occ_last[LOG2N] = smem;
     } else per_sm = oc->second;
 #endif
     long long need = ((long long)gm.n_pairs + C::GROUPS_PER_CTA - 1) / C::GROUPS_PER_CTA;
@@ -427,6 +433,15 @@ int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p
         gm.max_cand = pc.g.max_cand; gm.n_units = (int)m; gm.n_pairs = (int)pairs;
         // a maximum at lag i refines to a lag <= i+1: below this lag its frequency stays above the ceiling (never voiced)
         gm.min_refine_lag = (int)std::floor(1.0 / pc.g.dx / pc.g.ceiling) - 1;
+        {
+            // staging buffer of the sample prefetch: the frame samples a pair reads (window and local-mean span of frame A,
+            // the same shifted by one hop for frame B) plus up to 7 samples of 16-byte alignment slack on each side
+            const int mean_n0 = gm.half_nw - gm.nsamp_period;
+            const int span_lo = std::min(0, mean_n0), span_hi = std::max(gm.nw, mean_n0 + 2 * gm.nsamp_period);
+            const int hop_max = (int)std::ceil(pc.g.dt / pc.g.dx) + 2;
+            gm.pre_cap = ((span_hi - span_lo) + hop_max + 7 + 15) & ~7;
+            gm.pcm_len = h->cur_pcm_len;
+        }
         gm.sr = (float)(1.0 / pc.g.dx); gm.half_voicing = (float)(0.5 * p->voicing_threshold);
         gm.octave_cost = (float)p->octave_cost; gm.min_pitch = (float)p->pitch_floor;
         gm.dx = pc.g.dx; gm.dt = pc.g.dt; gm.ceiling = pc.g.ceiling; gm.silence_threshold = p->silence_threshold;
@@ -436,7 +451,7 @@ int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p
         gm.tw_a = (const float2*)tb->tw_a.p; gm.tw_b = (const float2*)tb->tw_b.p;
         {
             ScopedEv ev(h, EV_STATS);
-            int grid = (int)std::min<size_t>(m, (size_t)h->sm_count * 8);
+            int grid = (int)std::max<size_t>(1, std::min<size_t>((m + 7) / 8, (size_t)h->sm_count * 8));     // one warp per unit
             PB_LAUNCH(pb_unit_stats_kernel, dim3(grid), dim3(256), 0, h->stream, d_pcm, du, (int)m);
             h->last.n_launches++;
         }
@@ -488,13 +503,15 @@ int launch_lufs_group(PbHandle* h, const int16_t* d_pcm, const LufsLaunch& L) {
         ScopedEv ev(h, EV_LUFS);
         const PbMeterDev* dm = (const PbMeterDev*)h->meters.p;
         double* st = (double*)h->lstate.p; double* en = (double*)h->lenergy.p;
-        int g1 = (int)std::min<size_t>(m, (size_t)h->sm_count * 8);
+        int g1 = (int)std::max<size_t>(1, std::min<size_t>((m + 7) / 8, (size_t)h->sm_count * 8));           // one warp per unit
         PB_LAUNCH(pb_lufs_peak_kernel, dim3(g1), dim3(256), 0, h->stream, d_pcm, du, (int)m);
         int gc = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 127) / 128, (int64_t)h->sm_count * 16));
-        int gw = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 3) / 4, (int64_t)h->sm_count * 16));
+        const int64_t tiles = (chunks + PB_LUFS_CB - 1) / PB_LUFS_CB;                                        // one warp per tile of chunks
+        int gw = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + 3) / 4, (int64_t)h->sm_count * 16));
         PB_LAUNCH(pb_lufs_state_kernel, dim3(gw), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st);
         int gu = (int)std::max<size_t>(1, std::min<size_t>((m + 127) / 128, (size_t)h->sm_count * 16));
-        PB_LAUNCH(pb_lufs_scan_kernel, dim3(gu), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, st);
+        int gs = (int)std::max<size_t>(1, std::min<size_t>((m + 31) / 32, (size_t)h->sm_count * 16));         // 8 units per warp
+        PB_LAUNCH(pb_lufs_scan_kernel, dim3(gs), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, st);
         PB_LAUNCH(pb_lufs_energy_kernel, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks,
                   (const double*)st, en);
         PB_LAUNCH(pb_lufs_gate_kernel, dim3(gu), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, (const double*)en, (double*)h->lufs.p);
@@ -517,6 +534,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     if (rc != PB_OK) return rc;
     pbrt_set_device(h->device);
     begin_call(h);
+    h->cur_pcm_len = pcm_len;
     const int64_t n = u->n_units;
     const bool do_pitch = o.median_f0 && o.n_voiced && o.n_frames, do_lufs = o.lufs != nullptr;
     const bool want_frames = o.frame_f0 || o.frame_strength || o.frame_intensity;

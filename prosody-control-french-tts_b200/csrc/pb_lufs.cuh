@@ -46,22 +46,15 @@ __device__ __forceinline__ long long pb_lufs_bound(int c, double rate, long long
     return l > n ? n : l;
 }
 
+// Peak of every unit (the reference divides by max|samples| before metering). One warp per unit, 16-byte loads.
 __global__ void __launch_bounds__(256) pb_lufs_peak_kernel(const int16_t* __restrict__ pcm, PbLufsUnitDev* __restrict__ units, int n_units) {
-    __shared__ int s_max[8];
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int u = blockIdx.x * wpb + (threadIdx.x >> 5); u < n_units; u += gridDim.x * wpb) {
         const PbLufsUnitDev ud = units[u];
-        const int16_t* p = pcm + ud.pcm_off;
         int mx = 0;
-        for (long long i = ud.a + threadIdx.x; i < ud.b; i += blockDim.x) { int v = p[i]; v = v < 0 ? -v : v; mx = max(mx, v); }
+        pb_warp_foreach_s16(pcm + ud.pcm_off, ud.a, ud.b, lane, [&](int v) { mx = max(mx, v < 0 ? -v : v); });
         PB_UNROLL for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(PB_FULL_MASK, mx, o));
-        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int nwarp = (blockDim.x + 31) >> 5;
-            for (int k = 1; k < nwarp; k++) mx = max(mx, s_max[k]);
-            units[u].inv_peak = mx > 0 ? 1.0 / (double)mx : 1.0;
-        }
-        __syncthreads();
+        if (lane == 0) units[u].inv_peak = mx > 0 ? 1.0 / (double)mx : 1.0;
     }
 }
 
@@ -72,47 +65,81 @@ __device__ __forceinline__ int pb_lufs_find_unit(const PbLufsUnitDev* __restrict
 }
 
 // (1) Zero-state contribution of every chunk.  The state after filtering x[0..L-1] from rest is the linear combination
-// sum_k x[k] * H[L-1-k] with H[j] = A^j B: four independent dot products, no recurrence — one warp per chunk, lanes
-// stride over the samples (coalesced s16 reads, coalesced table reads), shuffle-reduce at the end.
+// sum_k x[k] * H[L-1-k] with H[j] = A^j B: four independent dot products, no recurrence.  Indexing by j = distance from
+// the END of the chunk makes the table row independent of the chunk length, so one warp takes PB_LUFS_CB consecutive
+// chunks and every H row it loads (32 B) serves all of them: lanes stride over j (coalesced s16 and table reads),
+// 4 DFMA per sample, shuffle-reduce at the end.
+#define PB_LUFS_CB 4
 __global__ void __launch_bounds__(128)
 pb_lufs_state_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
                      const PbMeterDev* __restrict__ meters, long long n_chunks_total, double* __restrict__ state /* [n_chunks][4] */) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    for (long long ch = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ch < n_chunks_total; ch += (long long)gridDim.x * wpb) {
-        const int u = pb_lufs_find_unit(units, n_units, ch);
-        const PbLufsUnitDev ud = units[u];
-        const PbMeterDev* __restrict__ mt = meters + ud.meter;
-        const int c = (int)(ch - ud.chunk_off);
-        const long long nreal = ud.b - ud.a, n = nreal + ud.npad;
-        const long long lo = pb_lufs_bound(c, mt->rate, n), hi = pb_lufs_bound(c + 1, mt->rate, n);
-        const int L = (int)(hi - lo);
-        const int16_t* __restrict__ p = pcm + ud.pcm_off + ud.a;
-        const double* __restrict__ H = mt->H;
-        const double ip = ud.inv_peak;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (L <= mt->Lmax) {
-            for (int k = lane; k < L; k += 32) {
-                const long long i = lo + k;
-                if (i < nreal) {
-                    const double x = (double)p[i] * ip;
-                    const double* h = H + (size_t)(L - 1 - k) * 4;
-                    s0 += x * h[0]; s1 += x * h[1]; s2 += x * h[2]; s3 += x * h[3];
+    const long long n_tiles = (n_chunks_total + PB_LUFS_CB - 1) / PB_LUFS_CB;
+    for (long long tile = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); tile < n_tiles; tile += (long long)gridDim.x * wpb) {
+        const int16_t* q[PB_LUFS_CB];      // last sample of the chunk
+        int len[PB_LUFS_CB], jmin[PB_LUFS_CB], met[PB_LUFS_CB];
+        double ip[PB_LUFS_CB], s[PB_LUFS_CB][4];
+        int maxlen = 0;
+        PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) {
+            const long long ch = tile * PB_LUFS_CB + c;
+            q[c] = pcm; len[c] = 0; jmin[c] = 0; met[c] = -1; ip[c] = 0.0;
+            s[c][0] = s[c][1] = s[c][2] = s[c][3] = 0.0;
+            if (ch < n_chunks_total) {
+                const int u = pb_lufs_find_unit(units, n_units, ch);
+                const PbLufsUnitDev ud = units[u];
+                const double rate = meters[ud.meter].rate;
+                const int cc = (int)(ch - ud.chunk_off);
+                const long long nreal = ud.b - ud.a, n = nreal + ud.npad;
+                const long long lo = pb_lufs_bound(cc, rate, n), hi = pb_lufs_bound(cc + 1, rate, n);
+                len[c] = (int)(hi - lo);
+                jmin[c] = hi > nreal ? (int)(hi - nreal) : 0;          // samples at or beyond nreal are pydub's zero padding
+                q[c] = pcm + ud.pcm_off + ud.a + (hi - 1);
+                met[c] = len[c] <= meters[ud.meter].Lmax ? ud.meter : -2 - ud.meter;   // -2-m: table too short (never): slow path
+                ip[c] = ud.inv_peak;
+                if (len[c] > maxlen) maxlen = len[c];
+            }
+        }
+        // sweep once per distinct meter among the chunks of the tile (normally one)
+        unsigned todo = 0;
+        PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) if (met[c] >= 0 && len[c] > 0) todo |= 1u << c;
+        while (todo) {
+            const int lead = __ffs((int)todo) - 1;
+            int m0 = 0;
+            PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) if (c == lead) m0 = met[c];
+            unsigned grp = 0;
+            PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) if ((todo >> c & 1u) && met[c] == m0) grp |= 1u << c;
+            const double* __restrict__ H = meters[m0].H;
+            for (int j = lane; j < maxlen; j += 32) {
+                const double* h = H + (size_t)j * 4;
+                const double h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3];
+                PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) {
+                    if ((grp >> c & 1u) && j < len[c] && j >= jmin[c]) {
+                        const double x = (double)q[c][-j] * ip[c];
+                        s[c][0] += x * h0; s[c][1] += x * h1; s[c][2] += x * h2; s[c][3] += x * h3;
+                    }
                 }
             }
-        } else if (lane == 0) {          // never with the tables the host builds; kept so a bad table cannot corrupt results
-            for (long long i = lo; i < hi; i++) {
-                const double x = i < nreal ? (double)p[i] * ip : 0.0;
-                const double y1 = mt->b1[0] * x + s0;
-                s0 = mt->b1[1] * x - mt->a1[1] * y1 + s1; s1 = mt->b1[2] * x - mt->a1[2] * y1;
-                const double y2 = mt->b2[0] * y1 + s2;
-                s2 = mt->b2[1] * y1 - mt->a2[1] * y2 + s3; s3 = mt->b2[2] * y1 - mt->a2[2] * y2;
+            todo &= ~grp;
+        }
+        PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) {
+            PB_UNROLL for (int r = 0; r < 4; r++) {
+                PB_UNROLL for (int o = 16; o > 0; o >>= 1) s[c][r] += __shfl_xor_sync(PB_FULL_MASK, s[c][r], o);
             }
+            const long long ch = tile * PB_LUFS_CB + c;
+            if (met[c] <= -2 && lane == 0) {     // never with the tables the host builds; kept so a bad table cannot corrupt results
+                const PbMeterDev* mt = meters + (-2 - met[c]);
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int k = len[c] - 1; k >= 0; k--) {
+                    const double x = k >= jmin[c] ? (double)q[c][-k] * ip[c] : 0.0;
+                    const double y1 = mt->b1[0] * x + a0;
+                    a0 = mt->b1[1] * x - mt->a1[1] * y1 + a1; a1 = mt->b1[2] * x - mt->a1[2] * y1;
+                    const double y2 = mt->b2[0] * y1 + a2;
+                    a2 = mt->b2[1] * y1 - mt->a2[1] * y2 + a3; a3 = mt->b2[2] * y1 - mt->a2[2] * y2;
+                }
+                s[c][0] = a0; s[c][1] = a1; s[c][2] = a2; s[c][3] = a3;
+            }
+            if (lane == 0 && ch < n_chunks_total) { state[ch * 4 + 0] = s[c][0]; state[ch * 4 + 1] = s[c][1]; state[ch * 4 + 2] = s[c][2]; state[ch * 4 + 3] = s[c][3]; }
         }
-        PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
-            s0 += __shfl_xor_sync(PB_FULL_MASK, s0, o); s1 += __shfl_xor_sync(PB_FULL_MASK, s1, o);
-            s2 += __shfl_xor_sync(PB_FULL_MASK, s2, o); s3 += __shfl_xor_sync(PB_FULL_MASK, s3, o);
-        }
-        if (lane == 0) { state[ch * 4 + 0] = s0; state[ch * 4 + 1] = s1; state[ch * 4 + 2] = s2; state[ch * 4 + 3] = s3; }
     }
 }
 
@@ -162,39 +189,57 @@ pb_lufs_energy_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __re
     }
 }
 
-// Per unit: turn the zero-state chunk contributions into true initial states: s_in[c+1] = A^len(c) s_in[c] + s_zs[c].
+// (2) Per unit: turn the zero-state chunk contributions into true initial states: s_in[c+1] = A^len(c) s_in[c] + s_zs[c].
+// Four lanes per unit (one state component each, the 4x4 product via shuffles), eight units per warp; the chunk
+// contributions are prefetched one chunk ahead so the sequential chain is only the four FMAs.
 __global__ void __launch_bounds__(128)
 pb_lufs_scan_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const PbMeterDev* __restrict__ meters, double* __restrict__ state) {
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
-        const PbLufsUnitDev ud = units[u];
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int r = lane & 3, slot = lane >> 2, base_lane = lane & ~3;
+    for (int ubase = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 8; ubase < n_units; ubase += gridDim.x * wpb * 8) {
+        const int u = ubase + slot;
+        const bool active = u < n_units;
+        const PbLufsUnitDev ud = units[active ? u : n_units - 1];
         const PbMeterDev* __restrict__ mt = meters + ud.meter;
+        const int nch = active ? ud.n_chunks : 0;
+        int maxch = nch;
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) maxch = max(maxch, __shfl_xor_sync(PB_FULL_MASK, maxch, o));
         const long long n = (ud.b - ud.a) + ud.npad;
-        double s[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int c = 0; c < ud.n_chunks; c++) {
-            double* st = state + (ud.chunk_off + c) * 4;
-            const double z0 = st[0], z1 = st[1], z2 = st[2], z3 = st[3];     // zero-state contribution of chunk c
-            st[0] = s[0]; st[1] = s[1]; st[2] = s[2]; st[3] = s[3];          // becomes its initial state
-            const long long lo = pb_lufs_bound(c, mt->rate, n), hi = pb_lufs_bound(c + 1, mt->rate, n);
-            int len = (int)(hi - lo);
-            // s <- A^len s
-            int k = len - mt->L0;
-            if (k >= 0) {
-                int extra = 0;
-                if (k >= PB_LUFS_NM) { extra = k - (PB_LUFS_NM - 1); k = PB_LUFS_NM - 1; }
-                const double* M = mt->M[k];
-                double t[4];
-                for (int r = 0; r < 4; r++) t[r] = M[r * 4 + 0] * s[0] + M[r * 4 + 1] * s[1] + M[r * 4 + 2] * s[2] + M[r * 4 + 3] * s[3];
-                for (int r = 0; r < 4; r++) s[r] = t[r];
-                len = extra;
+        const double rate = mt->rate;
+        const int L0 = mt->L0;
+        double* st = state + ud.chunk_off * 4 + r;
+        double s = 0.0;
+        double znext = nch > 0 ? st[0] : 0.0;
+        long long lo = pb_lufs_bound(0, rate, n);
+        for (int c = 0; c < maxch; c++) {
+            const bool on = c < nch;
+            const double z = znext;                     // zero-state contribution of chunk c (component r)
+            if (on) st[(size_t)c * 4] = s;              // becomes its initial state
+            if (c + 1 < nch) znext = st[(size_t)(c + 1) * 4];
+            const long long hi = pb_lufs_bound(c + 1, rate, n);
+            const int len = (int)(hi - lo);
+            lo = hi;
+            const double s0 = __shfl_sync(PB_FULL_MASK, s, base_lane + 0), s1 = __shfl_sync(PB_FULL_MASK, s, base_lane + 1);
+            const double s2 = __shfl_sync(PB_FULL_MASK, s, base_lane + 2), s3 = __shfl_sync(PB_FULL_MASK, s, base_lane + 3);
+            if (on) {
+                const int k = len - L0;
+                if (k >= 0 && k < PB_LUFS_NM) {
+                    const double* M = mt->M[k] + r * 4;
+                    s = M[0] * s0 + M[1] * s1 + M[2] * s2 + M[3] * s3;
+                } else {
+                    // a chunk clipped by the end of the unit: step the homogeneous recurrence (only empty chunks follow)
+                    double a0 = s0, a1 = s1, a2 = s2, a3 = s3;
+                    for (int i = 0; i < len; i++) {
+                        const double y1 = a0;
+                        const double np0 = -mt->a1[1] * y1 + a1, np1 = -mt->a1[2] * y1;
+                        const double y2 = mt->b2[0] * y1 + a2;
+                        const double nq0 = mt->b2[1] * y1 - mt->a2[1] * y2 + a3, nq1 = mt->b2[2] * y1 - mt->a2[2] * y2;
+                        a0 = np0; a1 = np1; a2 = nq0; a3 = nq1;
+                    }
+                    s = r == 0 ? a0 : r == 1 ? a1 : r == 2 ? a2 : a3;
+                }
+                s += z;
             }
-            for (int i = 0; i < len; i++) {       // short (clipped) chunks: step the homogeneous recurrence
-                const double y1 = s[0];
-                const double np0 = -mt->a1[1] * y1 + s[1], np1 = -mt->a1[2] * y1;
-                const double y2 = mt->b2[0] * y1 + s[2];
-                const double nq0 = mt->b2[1] * y1 - mt->a2[1] * y2 + s[3], nq1 = mt->b2[2] * y1 - mt->a2[2] * y2;
-                s[0] = np0; s[1] = np1; s[2] = nq0; s[3] = nq1;
-            }
-            s[0] += z0; s[1] += z1; s[2] += z2; s[3] += z3;
         }
     }
 }

@@ -14,9 +14,10 @@
 //   No tensor cores (nothing here is a dense contraction).
 #pragma once
 #include "pb_rt.h"
+#include "pb_stream.cuh"
 #include <math.h>
 
-#define PB_MAXC 32            // hard cap on candidates per frame (Praat default 15)
+#define PB_MAXC 32           // hard cap on candidates per frame (Praat default 15)
 #define PB_PI_F 3.14159265358979323846f
 
 struct PbUnitDev {
@@ -45,6 +46,9 @@ struct PbPitchGeomDev {
     int n_units;
     int n_pairs;
     int min_refine_lag;   // maxima at smaller lags stay above the ceiling whatever the refinement: never voiced
+    int pre_cap;          // samples per staging buffer of the cp.async prefetch (multiple of 8)
+    int pad1;
+    long long pcm_len;    // samples in the pcm buffer (prefetch copies stay inside it)
     float sr;             // 1/dx
     float half_voicing;   // 0.5 * voicingThreshold
     float octave_cost;
@@ -77,39 +81,30 @@ __device__ __forceinline__ int pb_upper_unit(const int32_t* __restrict__ off, in
 // ------------------------------------------------------------------------------------------------ K0
 // Per-unit mean and global peak (Praat: globalPeak = max |x - mean| over the whole analysed sound).
 // Integer sum / min / max of the int16 samples are exact, so mean and peak equal the float64 reference's.
+// One warp per unit, 16-byte loads (pb_stream.cuh): the kernel is a pure HBM stream of 2 B/sample.
 __global__ void __launch_bounds__(256) pb_unit_stats_kernel(const int16_t* __restrict__ pcm, PbUnitDev* __restrict__ units, int n_units) {
-    __shared__ long long s_sum[8];
-    __shared__ int s_min[8], s_max[8];
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        PbUnitDev ud = units[u];
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int u = blockIdx.x * wpb + (threadIdx.x >> 5); u < n_units; u += gridDim.x * wpb) {
+        const PbUnitDev ud = units[u];
         // the part of [ix1-1, ix1-1+nx) that lies inside the file
-        long long a = ud.ix1 - 1, b = a + ud.nx;
-        long long lo = a < 0 ? 0 : a, hi = b > ud.file_nx ? ud.file_nx : b;
-        bool padded = (lo > a) || (hi < b) || (hi <= lo);
+        const long long a = ud.ix1 - 1, b = a + ud.nx;
+        const long long lo = a < 0 ? 0 : a, hi = b > ud.file_nx ? ud.file_nx : b;
+        const bool padded = (lo > a) || (hi < b) || (hi <= lo);
         long long sum = 0; int mn = 32767, mx = -32768;
-        const int16_t* p = pcm + ud.pcm_off;
-        for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            int v = p[i]; sum += v; mn = min(mn, v); mx = max(mx, v);
-        }
+        pb_warp_foreach_s16(pcm + ud.pcm_off, lo, hi, lane, [&](int v) { sum += v; mn = min(mn, v); mx = max(mx, v); });
         PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
             sum += __shfl_xor_sync(PB_FULL_MASK, sum, o);
             mn = min(mn, __shfl_xor_sync(PB_FULL_MASK, mn, o));
             mx = max(mx, __shfl_xor_sync(PB_FULL_MASK, mx, o));
         }
-        int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-        if (l == 0) { s_sum[w] = sum; s_min[w] = mn; s_max[w] = mx; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int nwarp = (blockDim.x + 31) >> 5;
-            for (int k = 1; k < nwarp; k++) { sum += s_sum[k]; mn = min(mn, s_min[k]); mx = max(mx, s_max[k]); }
+        if (lane == 0) {
             if (padded) { mn = min(mn, 0); mx = max(mx, 0); }
             if (hi <= lo) { mn = 0; mx = 0; }
-            double mean = ((double)sum / 32768.0) / (double)ud.nx;
-            double p1 = fabs((double)mx / 32768.0 - mean), p2 = fabs((double)mn / 32768.0 - mean);
+            const double mean = ((double)sum / 32768.0) / (double)ud.nx;
+            const double p1 = fabs((double)mx / 32768.0 - mean), p2 = fabs((double)mn / 32768.0 - mean);
             units[u].mean = mean;
             units[u].global_peak = p1 > p2 ? p1 : p2;
         }
-        __syncthreads();
     }
 }
 

@@ -203,6 +203,71 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
     }
 }
 
+// ------------------------------------------------------------------------------------------------ sample prefetch (cp.async)
+__device__ __forceinline__ void pb_cp_async16(void* smem_dst, const void* gmem_src) {
+#ifdef PB_SIMT_EMU
+    memcpy(smem_dst, gmem_src, 16);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void pb_cp_async_commit() {
+#ifndef PB_SIMT_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING> __device__ __forceinline__ void pb_cp_async_wait() {
+#ifndef PB_SIMT_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+
+// Where a frame pair's samples sit: part index of frame A's sample 0, distance to frame B, and the offset of frame A's
+// sample `span_lo` inside the staged (16-byte aligned) range.
+struct PbPairPos { long long start0; int hop; int shift; };
+
+// Frame position, Praat's Sampled_indexToX / Sampled_xToLowIndex in float64 with explicit rounding (no FMA contraction):
+// returns the 1-based part index of frame sample n = 0.
+__device__ __forceinline__ long long pb_frame_start(double t1, double x1, int frame, const PbPitchGeomDev& gm) {
+    const double t = __dadd_rn(t1, __dmul_rn((double)frame, gm.dt));
+    const long long left = (long long)floor(__ddiv_rn(__dsub_rn(t, x1), gm.dx)) + 1;
+    return left + 1 - gm.half_nw;
+}
+
+// Stage the samples the pair (frames fA, fA+1 of unit u) will read into `dst` with 16-byte cp.async copies issued by the
+// GT threads of the group.  Only chunks entirely inside the pcm buffer are copied asynchronously; the (at most two) chunks
+// straddling its ends are filled sample by sample.  Values outside the unit's part / file are masked at read time.
+template <int GT>
+__device__ __forceinline__ PbPairPos pb_prefetch_pair(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, int u, int item,
+                                                      const PbPitchGeomDev& gm, int span_lo, int span_len, int16_t* dst, int g) {
+    const PbUnitDev* ud = units + u;
+    const int fA = 2 * (item - ud->pair_off);
+    const double x1 = ud->x1, t1 = ud->t1;
+    PbPairPos pos;
+    pos.start0 = pb_frame_start(t1, x1, fA, gm);
+    pos.hop = fA + 1 < ud->n_frames ? (int)(pb_frame_start(t1, x1, fA + 1, gm) - pos.start0) : 0;
+    // frame A sample n is part sample start0+n = pcm sample pcm_off + ix1 + start0 + n - 2
+    const long long gs = ud->pcm_off + ud->ix1 + pos.start0 - 2 + span_lo;
+    const long long byte0 = (long long)(size_t)pcm + 2 * gs;            // may lie outside the buffer: never dereferenced there
+    const long long a0 = byte0 & ~15LL;
+    pos.shift = (int)((byte0 - a0) >> 1);
+    const int chunks = (pos.shift + span_len + pos.hop + 7) >> 3;
+    const long long buf_lo = (long long)(size_t)pcm, buf_hi = buf_lo + 2 * gm.pcm_len;
+    for (int j = g; j < chunks; j += GT) {
+        const long long src = a0 + 16LL * j;
+        if (src >= buf_lo && src + 16 <= buf_hi) pb_cp_async16(dst + 8 * j, (const void*)(size_t)src);
+        else {
+            PB_UNROLL for (int e = 0; e < 8; e++) {
+                const long long b = src + 2 * e;
+                dst[8 * j + e] = (b >= buf_lo && b + 2 <= buf_hi) ? *(const int16_t*)(size_t)b : (int16_t)0;
+            }
+        }
+    }
+    pb_cp_async_commit();
+    return pos;
+}
+
 // ------------------------------------------------------------------------------------------------ K1 + K2
 template <int LOG2N>
 __global__ void __launch_bounds__(PbFftCfg<LOG2N>::WARPS_PER_CTA * 32, PbFftCfg<LOG2N>::MIN_CTAS)
@@ -216,29 +281,43 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
     const int group = warp / G, wg = warp % G;          // group in CTA, warp in group
     const int g = wg * 32 + lane;                       // thread in group = butterfly index
     const int bar_id = 1 + group;
-    // per-group shared memory: FFT buffer, then a small reduction scratch
-    float2* buf = (float2*)smem_raw + (size_t)group * (C::BUF + 8 * G);
+    // per-group shared memory: FFT buffer, a small reduction scratch, two sample staging buffers
+    const size_t group_bytes = (size_t)(C::BUF + 8 * G) * sizeof(float2) + 2 * (size_t)gm.pre_cap * sizeof(int16_t);
+    unsigned char* gbase = smem_raw + (size_t)group * group_bytes;
+    float2* buf = (float2*)gbase;
     float* red = (float*)(buf + C::BUF);                // [G][4] floats
+    int16_t* pre = (int16_t*)(buf + C::BUF + 8 * G);    // [2][pre_cap]
     const int B = gm.brent_ixmax;
     const int rstride = (B + 4) & ~1;
     float* rbase = (float*)buf;                         // r of frame A, r of frame B, then candidate scratch
     const int pk_lo = max(0, gm.half_nw - gm.half_period), pk_hi = min(gm.nw, gm.half_nw + gm.half_period);   // [lo, hi)
     const int mean_n0 = gm.half_nw - gm.nsamp_period;   // local mean spans frame samples [mean_n0, mean_n0 + 2 P)
+    const int span_lo = min(0, mean_n0);                // staged range of frame samples: [span_lo, span_lo + span_len)
+    const int span_len = max(gm.nw, mean_n0 + 2 * gm.nsamp_period) - span_lo;
 
     // Blocked distribution: a group walks a contiguous range of frame pairs, so consecutive iterations stay in the same
-    // unit (one descriptor fetch) and re-read the 75 % of samples they share with the previous pair from L1.
+    // unit and the next pair's samples can be staged (cp.async, double buffered) while the current pair is transformed.
     const int n_groups = gridDim.x * C::GROUPS_PER_CTA;
     const int per_group = (gm.n_pairs + n_groups - 1) / n_groups;
     const int item_begin = (blockIdx.x * C::GROUPS_PER_CTA + group) * per_group;
     const int item_end = min(gm.n_pairs, item_begin + per_group);
-    int u = item_begin < item_end ? pb_upper_unit(pair_off, gm.n_units, item_begin) : 0;
-    PbUnitDev ud = units[u];
-    int u_end = item_begin < item_end ? pair_off[u + 1] : 0;
+    if (item_begin >= item_end) return;
+    int u_next = pb_upper_unit(pair_off, gm.n_units, item_begin);
+    int u_next_end = pair_off[u_next + 1];
+    PbPairPos pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, item_begin, gm, span_lo, span_len, pre, g);
+    int u = -1;
+    PbUnitDev ud;
     for (int item = item_begin; item < item_end; item++) {
-        if (item >= u_end) {
-            do { u++; u_end = pair_off[u + 1]; } while (item >= u_end);
-            ud = units[u];
-        }
+        const PbPairPos pos = pos_next;
+        if (u != u_next) { u = u_next; ud = units[u]; }
+        const int16_t* sm = pre + (size_t)((item - item_begin) & 1) * gm.pre_cap;
+        if (item + 1 < item_end) {
+            if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); }
+            pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, item + 1, gm, span_lo, span_len,
+                                            pre + (size_t)((item + 1 - item_begin) & 1) * gm.pre_cap, g);
+            pb_cp_async_wait<1>();                      // everything but the copy just issued has landed
+        } else pb_cp_async_wait<0>();
+        pb_group_sync<G>(bar_id);                       // ... and is visible to every lane of the group
         const int fA = 2 * (item - ud.pair_off);
         const bool hasB = fA + 1 < ud.n_frames;
         const bool global_silent = ud.global_peak == 0.0;
@@ -252,30 +331,28 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
         for (int step = 0; step < 4; step++) {          // FFT (step >> 1), pass (step & 1): one copy of the butterfly code
             const int pass = step & 1;
             if (step == 0) {
-                // ---- frame positions (float64: Praat's Sampled_indexToX / Sampled_xToLowIndex), sample windows
-                const int16_t* fp[2]; int nlo[2], nhi[2]; float lmean[2];
+                // ---- which frame samples exist: sample n of frame f is part sample start+n = file sample ix1+start+n-2;
+                //      Praat zero-fills outside the part and outside the file
+                int nlo[2], nhi[2], sb[2]; float lmean[2];
                 PB_UNROLL for (int f = 0; f < 2; f++) {
-                    const double t = __dadd_rn(ud.t1, __dmul_rn((double)(fA + f), gm.dt));
-                    const long long left = (long long)floor(__ddiv_rn(__dsub_rn(t, ud.x1), gm.dx)) + 1;
-                    const long long start = left + 1 - gm.half_nw;     // part index (1-based) of frame sample n = 0
-                    // frame sample n is part sample start+n = file sample ix1+start+n-2; zero outside the part or the file
+                    const long long start = pos.start0 + (f ? pos.hop : 0);
                     long long lo = 1 - start, hi = ud.nx - start + 1;
                     const long long lo2 = 2 - ud.ix1 - start, hi2 = (long long)ud.file_nx - ud.ix1 - start + 2;
                     if (lo2 > lo) lo = lo2; if (hi2 < hi) hi = hi2;
                     const long long BIG = 1 << 30;
                     nlo[f] = (int)(lo < -BIG ? -BIG : (lo > BIG ? BIG : lo));
                     nhi[f] = (int)(hi < -BIG ? -BIG : (hi > BIG ? BIG : hi));
-                    fp[f] = pcm + ud.pcm_off + (ud.ix1 + start - 2);
+                    sb[f] = pos.shift - span_lo + (f ? pos.hop : 0);       // staged index of frame sample n is sb[f] + n
                     // local mean: one longest period to both sides of the frame centre (exact in integers)
                     int s = 0;
                     for (int q = lane; q < 2 * gm.nsamp_period; q += 32) {
                         const int n = mean_n0 + q;
-                        s += (n >= nlo[f] && n < nhi[f]) ? (int)fp[f][n] : 0;
+                        s += (n >= nlo[f] && n < nhi[f]) ? (int)sm[sb[f] + n] : 0;
                     }
                     s = pb_warp_sum_i(s);
                     lmean[f] = (float)(((double)s / 32768.0) / (double)(2 * gm.nsamp_period));
                 }
-                if (!hasB) { nlo[1] = 0; nhi[1] = 0; }
+                if (!hasB) { nlo[1] = 0; nhi[1] = 0; sb[1] = sb[0]; }
                 // ---- window both frames into the FFT buffer, z = a + i b (natural order, zero padded); a compact
                 //      rolled loop: the range checks live here once instead of in 32 unrolled copies
                 float mxA = 0.0f, mxB = 0.0f;
@@ -283,10 +360,10 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
                     float a = 0.0f, b = 0.0f;
                     if (n < gm.nw) {
                         const float w = __ldg(&gm.window[n]);
-                        const int sa = (n >= nlo[0] && n < nhi[0]) ? (int)fp[0][n] : 0;
-                        const int sb = (n >= nlo[1] && n < nhi[1]) ? (int)fp[1][n] : 0;
+                        const int sa = (n >= nlo[0] && n < nhi[0]) ? (int)sm[sb[0] + n] : 0;
+                        const int sbv = (n >= nlo[1] && n < nhi[1]) ? (int)sm[sb[1] + n] : 0;
                         a = ((float)sa * (1.0f / 32768.0f) - lmean[0]) * w;
-                        b = hasB ? ((float)sb * (1.0f / 32768.0f) - lmean[1]) * w : 0.0f;
+                        b = hasB ? ((float)sbv * (1.0f / 32768.0f) - lmean[1]) * w : 0.0f;
                         const float aa = fabsf(a), ab = fabsf(b);
                         mxA = fmaxf(mxA, aa); mxB = fmaxf(mxB, ab);
                         if (n >= pk_lo && n < pk_hi) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, ab); }
@@ -421,6 +498,6 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
                 }
             }
         }
-        pb_group_sync<G>(bar_id);     // buf is reused by the next item
+        pb_group_sync<G>(bar_id);     // buf and the staging buffer just consumed are reused by the next iterations
     }
 }
