@@ -51,7 +51,7 @@ struct HostBuf {
 };
 
 struct PitchTables {        // per (nw, log2n): lives for the life of the handle
-    DevBuf window, inv_wr, tw_a, tw_b;
+    DevBuf window, inv_wr, tw_a, tw_b, half_tab;
 };
 
 struct EvPair { pbEvent_t a, b; int kind; };   // kind: index into the PbTimings float fields
@@ -194,11 +194,18 @@ int get_tables(PbHandle* h, const PbGeomHost& g, PitchTables** out) {
         case 13: fill_twiddles<13>(ta, tb); break;
         default: return fail(h, PB_EUNSUPPORTED, "analysis window of %s samples needs an FFT beyond 8192 points", std::to_string(nw).c_str());
     }
+    // windowed-sinc coefficients of Praat's NUM_interpolate_sinc at phi = 1/2, depth 70 (both sides are identical there)
+    std::vector<float> ht(72, 0.0f);
+    for (int m = 0; m < 70; m++) {
+        const double d = 0.5 + m, c = (1.0 + cos(3.14159265358979323846 * d / 70.5)) / d / PI2;
+        ht[m] = (float)((m & 1) ? -c : c);
+    }
     PitchTables* t = new PitchTables();
-    if (t->window.ensure(wf.size() * 4) || t->inv_wr.ensure(iw.size() * 4) || t->tw_a.ensure(ta.size() * 8) || t->tw_b.ensure(tb.size() * 8)) {
+    if (t->half_tab.ensure(ht.size() * 4) || t->window.ensure(wf.size() * 4) || t->inv_wr.ensure(iw.size() * 4) || t->tw_a.ensure(ta.size() * 8) || t->tw_b.ensure(tb.size() * 8)) {
         delete t; return fail(h, PB_ENOMEM, "out of memory: %s", "pitch tables");
     }
     // pageable -> device copies of a few KB; synchronous on purpose (tables are built once per geometry)
+    pbrt_h2d(t->half_tab.p, ht.data(), ht.size() * 4, h->stream);
     pbrt_h2d(t->window.p, wf.data(), wf.size() * 4, h->stream);
     pbrt_h2d(t->inv_wr.p, iw.data(), iw.size() * 4, h->stream);
     pbrt_h2d(t->tw_a.p, ta.data(), ta.size() * 8, h->stream);
@@ -336,7 +343,7 @@ template <int LOG2N>
 int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, const int32_t* d_pair_off, const PbPitchGeomDev& gm,
                   float* cand_f, float* cand_s, uint8_t* ncand, float* inten) {
     typedef PbFftCfg<LOG2N> C;
-    const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + 2 * (size_t)gm.pre_cap * sizeof(int16_t));
+    const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + 2 * (size_t)gm.pre_cap * sizeof(int16_t)) + 72 * sizeof(float);
     const int threads = C::WARPS_PER_CTA * 32;
     auto kfn = pb_pitch_frames_kernel<LOG2N>;
     int per_sm = 2;
@@ -448,7 +455,7 @@ int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p
         gm.voicing_threshold = p->voicing_threshold; gm.octave_cost_d = p->octave_cost; gm.octave_jump_cost = p->octave_jump_cost;
         gm.voiced_unvoiced_cost = p->voiced_unvoiced_cost;
         gm.window = (const float*)tb->window.p; gm.inv_wr = (const float*)tb->inv_wr.p;
-        gm.tw_a = (const float2*)tb->tw_a.p; gm.tw_b = (const float2*)tb->tw_b.p;
+        gm.tw_a = (const float2*)tb->tw_a.p; gm.tw_b = (const float2*)tb->tw_b.p; gm.half_tab = (const float*)tb->half_tab.p;
         {
             ScopedEv ev(h, EV_STATS);
             int grid = (int)std::max<size_t>(1, std::min<size_t>((m + 7) / 8, (size_t)h->sm_count * 8));     // one warp per unit
@@ -694,7 +701,7 @@ void pb_destroy(PbHandle* h) {
     for (auto* b : dbs) b->release();
     HostBuf* hbs[] = {&h->stage_units, &h->stage_pairs, &h->stage_lunits, &h->stage_meters, &h->stage_out};
     for (auto* b : hbs) b->release();
-    for (auto& kv : h->tables) { kv.second->window.release(); kv.second->inv_wr.release(); kv.second->tw_a.release(); kv.second->tw_b.release(); delete kv.second; }
+    for (auto& kv : h->tables) { kv.second->window.release(); kv.second->inv_wr.release(); kv.second->tw_a.release(); kv.second->tw_b.release(); kv.second->half_tab.release(); delete kv.second; }
     for (auto& kv : h->lufs_tables) { kv.second->release(); delete kv.second; }
     for (auto& e : h->ev_pool) pbrt_event_destroy(e);
     pbrt_stream_destroy(h->own_stream);

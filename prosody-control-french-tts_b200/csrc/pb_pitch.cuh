@@ -59,6 +59,7 @@ struct PbPitchGeomDev {
     const float* inv_wr;  // [B+2]  1 / (normalised autocorrelation of the window)
     const float2* tw_a;   // [R][R]     pass-2 twiddles  exp(-2 pi i t k / R^2)
     const float2* tw_b;   // [F][R*R]   final-pass twiddles exp(-2 pi i t k / N)
+    const float* half_tab;// [70]  windowed-sinc coefficients at phi = 1/2, depth 70 (incl. the 1/(2 pi) factor)
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -155,7 +156,7 @@ template <int LOG2N> struct PbFftCfg {
     static constexpr int F = N / (R * R);                 // radix of the final pass (1 = none)
     static constexpr int G = (N / R) / 32;                // warps per group
     static constexpr int GT = 32 * G;                     // threads per group
-    static constexpr int BUF = N + (N >> 3);              // float2 slots per group (worst-case skew padding)
+    static constexpr int BUF = N + (N >> LR) + 8;         // float2 slots per group: N plus the skew padding (index >> LR)
     static constexpr int WARPS_PER_CTA = G >= 4 ? G : 4;
     static constexpr int GROUPS_PER_CTA = WARPS_PER_CTA / G;
     static constexpr int FB = F > 1 ? (N / F) / GT : 0;   // final-pass butterflies per thread

@@ -120,9 +120,7 @@ __device__ PB_NOINLINE int pb_candidates_overflow(const float* __restrict__ r, f
 // finder treats them as voiceless whatever their strength, so they keep their first-pass values.
 __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r, float* scratch, const PbPitchGeomDev& gm,
                                                     int lane, float* __restrict__ out_f, float* __restrict__ out_s,
-                                                    uint8_t* __restrict__ out_n) {
-    float* cf = scratch;                       // first-pass frequency
-    float* cs = scratch + PB_MAXC;             // first-pass strength
+                                                    uint8_t* __restrict__ out_n, const float* __restrict__ half_tab) {
     int* imax = (int*)(scratch + 2 * PB_MAXC); // lag of the maximum
     const int B = gm.brent_ixmax, lim = gm.scan_lim, maxc = gm.max_cand;
     const int sub = lane >> 3, sl = lane & 7;
@@ -167,13 +165,26 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
         const float den0 = 2.0f * r0 - rm - rp;
         const float x_first = fi + ((have && den0 > 0.0f) ? 0.5f * __fdividef(rp - rm, den0) : 0.0f);   // Praat's first guess
         const int depth = !have ? 0 : (x_first < (1.0f / 0.3f)) ? 700 : 70;                    // f > 0.3/dx; idle groups do no work
+        // The two half-sample points have phi = 1/2: their windowed-sinc coefficients do not depend on the candidate
+        // (depth 70, away from the end of r), so both are dot products against one 70-entry table — no MUFU.
+        const bool tab = have && depth == 70 && (B - i) >= 70;
+        float ta = 0.0f, tb = 0.0f;
+        if (tab) {
+            for (int m = sl; m < 70; m += 8) {
+                const float cm = half_tab[m];
+                ta = fmaf(cm, r[abs(i - 1 - m)] + r[i + m], ta);
+                tb = fmaf(cm, r[abs(i - m)] + r[i + 1 + m], tb);
+            }
+        }
+        PB_UNROLL for (int o = 1; o < 8; o <<= 1) { ta += __shfl_xor_sync(PB_FULL_MASK, ta, o); tb += __shfl_xor_sync(PB_FULL_MASK, tb, o); }
         // four evaluations through ONE call site (code size): y(i-.5), y(i+.5), y(x1), y(x2)
         float xe = fi - 0.5f, ya = 0.0f, xc = fi, yc = r0, yl = 0.0f, yr = 0.0f, x1 = fi, y1 = 0.0f, y2 = 0.0f;
 #ifndef PB_SIMT_EMU
 #pragma unroll 1
 #endif
         for (int e = 0; e < 4; e++) {
-            const float y = pb_sinc8(r, B, xe, depth, sl);
+            float y = pb_sinc8(r, B, xe, (tab && e < 2) ? 0 : depth, sl);
+            if (tab && e < 2) y = e ? tb : ta;
             if (e == 0) { ya = y; xe = fi + 0.5f; }
             else if (e == 1) {
                 // half-sample grid r[i-1], y(i-.5), r[i], y(i+.5), r[i+1]: best of the middle three and its neighbours
@@ -287,6 +298,10 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
     float2* buf = (float2*)gbase;
     float* red = (float*)(buf + C::BUF);                // [G][4] floats
     int16_t* pre = (int16_t*)(buf + C::BUF + 8 * G);    // [2][pre_cap]
+    // CTA-wide: the half-sample sinc coefficients (72 floats after the last group's region)
+    float* half_tab = (float*)(smem_raw + (size_t)C::GROUPS_PER_CTA * group_bytes);
+    if (threadIdx.x < 72) half_tab[threadIdx.x] = threadIdx.x < 70 ? __ldg(&gm.half_tab[threadIdx.x]) : 0.0f;
+    __syncthreads();
     const int B = gm.brent_ixmax;
     const int rstride = (B + 4) & ~1;
     float* rbase = (float*)buf;                         // r of frame A, r of frame B, then candidate scratch
@@ -494,7 +509,7 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
                     if (lane == 0) { of[0] = 0.0f; os[0] = 0.0f; ncand[fr] = 1; intensity[fr] = 0.0f; }
                 } else {
                     if (lane == 0) { const float it = pk / gpk; intensity[fr] = it > 1.0f ? 1.0f : it; }
-                    pb_frame_candidates(rbase + f * rstride, rbase + 2 * rstride + f * (3 * PB_MAXC), gm, lane, of, os, ncand + fr);
+                    pb_frame_candidates(rbase + f * rstride, rbase + 2 * rstride + f * (3 * PB_MAXC), gm, lane, of, os, ncand + fr, half_tab);
                 }
             }
         }
