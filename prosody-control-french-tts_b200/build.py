@@ -10,7 +10,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libprosody_b200.so"
 SOURCES = [CSRC / "pb_api.cu"]
-HEADERS = [CSRC / "pb_rt.h", CSRC / "pb_plan.h", CSRC / "pb_pitch.cuh", CSRC / "pb_pitch_frames.cuh", CSRC / "pb_pitch_path.cuh", CSRC / "pb_lufs.cuh",
+HEADERS = [CSRC / "pb_api_host.inc", CSRC / "pb_stream.cuh", CSRC / "pb_rt.h", CSRC / "pb_plan.h", CSRC / "pb_pitch.cuh", CSRC / "pb_pitch_frames.cuh", CSRC / "pb_pitch_path.cuh", CSRC / "pb_lufs.cuh",
            HERE.parent / "include" / "prosody_b200.h"]
 
 
@@ -23,7 +23,7 @@ def nvcc_path() -> str:
 
 def nvcc_command(out: Path = LIB, extra: list[str] | None = None) -> list[str]:
     return [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-            "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o", str(out)] + (extra or []) + [str(s) for s in SOURCES]
+            "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread", "-shared", "-o", str(out)] + (extra or []) + [str(s) for s in SOURCES]
 
 
 def is_stale() -> bool:

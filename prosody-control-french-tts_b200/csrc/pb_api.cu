@@ -20,6 +20,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -87,6 +88,16 @@ struct BatchPlan {
     std::vector<PbMeterDev> meters;
     std::vector<std::pair<int64_t, int64_t>> dups;     // (caller unit, caller unit it duplicates)
     int64_t lufs_samples = 0;
+    std::vector<int32_t> seen;                // dedup hash table (open addressing)
+    std::vector<LufsKey> seen_key;            // key of every compact unit
+    // per-call scratch kept here so its capacity (and its pages) survive from call to call
+    std::vector<int32_t> pstat, lflags;
+    std::vector<std::vector<int64_t>> pids, lids, by_class;
+    void reset() {
+        pplan.clear(); pclass.clear(); classes.clear(); max_cand = 0; total_frames = 0;
+        lunits.clear(); lneed.clear(); meters.clear(); dups.clear(); lufs_samples = 0;
+        seen_key.clear();
+    }
 };
 
 }  // namespace
@@ -110,6 +121,7 @@ struct PbHandle {
     PbTimings last;
     std::map<std::pair<int, size_t>, int> occ_cache;      // (LOG2N, dynamic smem bytes) -> resident CTAs per SM
     std::map<int, size_t> occ_last;                        // LOG2N -> footprint the function attributes were last set for
+    BatchPlan plan;                                        // host plan of the call in progress (scratch reused across calls)
     int64_t cur_pcm_len = 0;                               // samples in the pcm buffer of the call in progress
 };
 
@@ -290,8 +302,12 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
     std::map<double, int> meter_ix;
     // Units that resolve to the same samples and meter have the same loudness (the reference's < 0.4 s / empty-slice
     // fallbacks send every short syntagme of a file to that file's whole-file value): measure once, copy on the host.
-    std::unordered_map<LufsKey, int64_t, LufsKeyHash> seen;
-    seen.reserve((size_t)n);
+    // flat open-addressing table (slot = 1 + index into bp.lunits, 0 = empty), kept in the plan scratch across calls
+    size_t cap = 1024;
+    while (cap < (size_t)n * 2 + 16) cap <<= 1;
+    bp.seen.assign(cap, 0);
+    bp.seen_key.clear();
+    const LufsKeyHash hasher;
     for (int64_t i = 0; i < n; i++) {
         if (want && !want[i]) continue;
         const double mr = u->meter_rate ? u->meter_rate[i] : u->rate[i];
@@ -300,8 +316,16 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
         flags[i] = st;
         if (st & (PB_UNIT_LUFS_ERROR | PB_UNIT_SLICE_ERROR)) continue;
         const LufsKey key{u->file_off[i] + a, b - a, npad, mr};
-        auto ins = seen.emplace(key, i);
-        if (!ins.second) { bp.dups.push_back(std::make_pair(i, ins.first->second)); continue; }
+        size_t slot = hasher(key) & (cap - 1);
+        bool dup = false;
+        while (bp.seen[slot]) {
+            const size_t k = (size_t)bp.seen[slot] - 1;
+            if (bp.seen_key[k] == key) { bp.dups.push_back(std::make_pair(i, (int64_t)bp.lunits[k].out_index)); dup = true; break; }
+            slot = (slot + 1) & (cap - 1);
+        }
+        if (dup) continue;
+        bp.seen[slot] = (int32_t)bp.lunits.size() + 1;
+        bp.seen_key.push_back(key);
         auto it = meter_ix.find(mr);
         if (it == meter_ix.end()) {
             PbMeterDev md; memset(&md, 0, sizeof md);
@@ -385,7 +409,9 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
                 const std::vector<int64_t>* frame_off_by_unit, std::vector<PitchLaunch>& out) {
     if (ids.empty()) return PB_OK;
     const size_t ncls = bp.classes.size();
-    std::vector<std::vector<int64_t>> by_class(ncls);
+    std::vector<std::vector<int64_t>>& by_class = h->plan.by_class;       // scratch with reused capacity
+    if (by_class.size() < ncls) by_class.resize(ncls);
+    for (auto& v : by_class) v.clear();
     for (int64_t i : ids) by_class[(size_t)bp.pclass[(size_t)i]].push_back(i);
     int64_t frame_base = 0;
     for (size_t ci = 0; ci < ncls; ci++) {
@@ -545,9 +571,11 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     const int64_t n = u->n_units;
     const bool do_pitch = o.median_f0 && o.n_voiced && o.n_frames, do_lufs = o.lufs != nullptr;
     const bool want_frames = o.frame_f0 || o.frame_strength || o.frame_intensity;
-    std::vector<int32_t> pstat((size_t)n, 0), lflags((size_t)n, 0);
+    BatchPlan& bp = h->plan;
+    bp.reset();
+    std::vector<int32_t>& pstat = bp.pstat; std::vector<int32_t>& lflags = bp.lflags;
+    pstat.assign((size_t)n, 0); lflags.assign((size_t)n, 0);
     const auto t_plan0 = std::chrono::steady_clock::now();
-    BatchPlan bp;
     if (do_pitch) {
         memset(o.n_frames, 0, (size_t)n * 4);
         rc = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp);
@@ -562,7 +590,11 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     if (!on_device && !want_frames && pcm_bytes >= ((size_t)64 << 20)) n_seg = 8;
     const int64_t seg_samples = n_seg > 1 ? (((pcm_len + n_seg - 1) / n_seg + 127) & ~(int64_t)127) : (pcm_len > 0 ? pcm_len : 1);
     auto seg_of = [&](int64_t need_end) { int64_t s = need_end > 0 ? (need_end - 1) / seg_samples : 0; return (int)(s >= n_seg ? n_seg - 1 : s); };
-    std::vector<std::vector<int64_t>> pids((size_t)n_seg), lids((size_t)n_seg);
+    std::vector<std::vector<int64_t>>& pids = bp.pids; std::vector<std::vector<int64_t>>& lids = bp.lids;
+    if (pids.size() < (size_t)n_seg) pids.resize((size_t)n_seg);
+    if (lids.size() < (size_t)n_seg) lids.resize((size_t)n_seg);
+    for (auto& v : pids) v.clear();
+    for (auto& v : lids) v.clear();
     std::vector<int64_t> seg_frames((size_t)n_seg, 0), seg_chunks((size_t)n_seg, 0);
     size_t n_pok = 0;
     if (do_pitch) for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0) {

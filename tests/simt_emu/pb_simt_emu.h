@@ -137,6 +137,15 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) {
     int s = pb_emu::lane() - d; return pb_emu::shfl(v, s < 0 ? pb_emu::lane() : s);
 }
 static inline unsigned __ballot_sync(unsigned, int p) { return pb_emu::ballot(p); }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+    const int base = pb_emu::warp() * 32;
+    pb_emu::g_blk->xchg[base + pb_emu::lane()] = v;
+    pb_emu::warp_sync();
+    unsigned r = 0;
+    for (int i = 0; i < pb_emu::warp_width(); i++) r |= (unsigned)pb_emu::g_blk->xchg[base + i];
+    pb_emu::warp_sync();
+    return r;
+}
 static inline int __any_sync(unsigned, int p) { return pb_emu::ballot(p) != 0; }
 static inline int __all_sync(unsigned, int p) {
     unsigned full = pb_emu::warp_width() == 32 ? 0xffffffffu : ((1u << pb_emu::warp_width()) - 1);
