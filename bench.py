@@ -191,6 +191,7 @@ def main():
     import torch
     import torch.distributed as dist
     import prosody_b200 as pb
+    from prosody_b200 import shard
     from prosody_b200 import step as S
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
@@ -217,14 +218,9 @@ def main():
         if world > 1:
             # final gather of the per-syntagme results on rank 0 (the path's only exchange)
             rows = torch.from_numpy(np.stack([out["raw_pitch"], out["raw_volume"], out["raw_rate"], out["sm_pitch"], out["sm_rate"]], 1)).to(dev)
-            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev))
-            mx = int(max(int(s.item()) for s in sizes))
-            pad = torch.zeros(mx, 5, dtype=rows.dtype, device=dev); pad[:rows.shape[0]] = rows
-            bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-            dist.gather(pad, bufs, dst=0)
-            if rank == 0:
-                _ = [b[:int(s.item())].cpu() for b, s in zip(bufs, sizes)]
+            ids = torch.arange(rows.shape[0], device=dev, dtype=torch.int64) + rank * (1 << 32)
+            gathered = shard.gather_rows(rows, ids, dst=0)
+            assert rank != 0 or gathered.shape[1] == 5
         return out
 
     def timed(src, steps):
