@@ -201,3 +201,95 @@ def test_full_size_properties(gpu_extractor):
     assert np.max(np.abs(ra["lufs"] - rb["lufs"])) < 1e-9
     voiced_frac = r1["n_voiced"].sum() / r1["n_frames"].sum()
     assert 0.2 < voiced_frac < 0.95
+
+
+def test_long_form_unit_path_finder(gpu_extractor, oracle):
+    """BASELINE config 4 in miniature: one unsegmented 3-minute 22.05 kHz recording through the path finder
+    (17 997 frames in one Viterbi chain, 71 backtrack chunks), plus its loudness."""
+    import prosody_b200 as pb
+    sr = 22050
+    parts = speechlike(6, 30.0, sr, seed=77)
+    x = np.concatenate(list(parts))
+    units = pb.Units.from_list([(0, len(x), sr, 0.0, None, float(sr))])
+    r = gpu_extractor.median_pitch(x, units, pb.pitch_params(75.0, 600.0), frames=True)
+    o = oracle.pitch_track(x, sr, params=oracle.pitch_params(75.0, 600.0))
+    assert r["n_frames"][0] == o["n_frames"] == 17997
+    agree, rel = compare_tracks(r["frame_f0"], o["frequency"])
+    assert agree >= VOICING_AGREE and rel < F0_TOL, (agree, rel)
+    assert abs(r["median_f0"][0] - o["median"]) / o["median"] < F0_TOL
+    out, st = gpu_extractor.lufs(x, units)
+    assert abs(out[0] - oracle.lufs(x, sr, float(sr))) < 1e-9
+
+
+def test_mixed_rate_corpus_in_one_call(gpu_extractor, oracle):
+    """BASELINE config 5 in miniature: 16 / 24 / 44.1 kHz files in one batch (three analysis geometries, three meters),
+    reference parameters (floor 150, ceiling 600), whole files and slices."""
+    import prosody_b200 as pb
+    rng = np.random.default_rng(8)
+    bufs, rates = [], []
+    for sr, dur, n in ((16000, 3.0, 5), (24000, 2.5, 3), (44100, 2.0, 2)):
+        for row in speechlike(n, dur, sr, seed=200 + sr // 1000):
+            bufs.append(row); rates.append(sr)
+    order = rng.permutation(len(bufs))
+    bufs = [bufs[i] for i in order]; rates = [rates[i] for i in order]
+    offs = np.concatenate([[0], np.cumsum([len(b) for b in bufs])])
+    cat = np.concatenate(bufs)
+    items = []
+    for f, (b, sr) in enumerate(zip(bufs, rates)):
+        items.append((offs[f], len(b), sr, 0.0, None, float(sr)))
+        a = int(rng.integers(0, 800)); d = int(rng.integers(300, 1100))
+        items.append((offs[f], len(b), sr, a / 1000, (a + d) / 1000, 16000.0))
+    units = pb.Units.from_list(items)
+    r = gpu_extractor.extract(cat, units, pb.pitch_params(150.0, 600.0))
+    rf = gpu_extractor.median_pitch(cat, units, pb.pitch_params(150.0, 600.0), frames=True)
+    assert np.array_equal(r["median_f0"], rf["median_f0"])
+    tot = ok = 0
+    for k, it in enumerate(items):
+        x = cat[it[0]:it[0] + it[1]]
+        o = oracle.pitch_track(x, it[2], it[3], it[4], params=oracle.pitch_params(150.0, 600.0))
+        a, b = rf["frame_off"][k], rf["frame_off"][k + 1]
+        assert b - a == o["n_frames"]
+        agree, rel = compare_tracks(rf["frame_f0"][a:b], o["frequency"])
+        assert rel < F0_TOL
+        ok += agree * (b - a); tot += b - a
+        assert abs(r["lufs"][k] - oracle.lufs(x, it[2], it[5], it[3], it[4])) < 1e-9
+        assert r["duration_s"][k] == oracle.part_duration(len(x), it[2], it[3], it[4])
+    assert ok / tot >= VOICING_AGREE
+
+
+def test_step_24k_mfa_style_full_ssml(gpu_extractor, oracle):
+    """BASELINE config 3 in miniature: 24 kHz utterances with MFA-style word grids (empty marks = silence) and a paired
+    raw-synth stream, full SSML-delta output through the batched step vs the oracle's loop-by-loop step."""
+    import re
+    from oracle import flow as F
+    import prosody_b200 as pb
+    from prosody_b200 import ssml as SSML, step as S, synth
+    n_utt, sr = 6, 24000
+    nat = speechlike(n_utt, 6.0, sr, seed=91); syn = speechlike(n_utt, 5.6, sr, seed=92)
+    grids = synth.make_word_grid(n_utt, 6.0, seed=5)
+    bufs, segs, fsegs, off = [], [], [], 0
+    for i in range(n_utt):
+        bufs += [nat[i], syn[i]]
+        segs.append(S.Segment(f"segment_ph{i + 1}", off, len(nat[i]), sr, grids[i], off + len(nat[i]), len(syn[i]), sr))
+        fsegs.append(F.Segment(f"segment_ph{i + 1}", nat[i], sr, syn[i], sr, grids[i]))
+        off += len(nat[i]) + len(syn[i])
+    pcm = np.concatenate(bufs)
+    prm = dict(baseline_window=3, pitch_semitones=1.3, smoothing_alpha=0.2)
+    pl = S.plan(segs, prm)
+    out = S.measure(gpu_extractor, pcm, pl, prm)
+    ref = F.measure_and_build(fsegs, prm)
+    assert pl.syn_words == [r_["syntagme"] for r_ in ref["raw_rows"]]
+    np.testing.assert_allclose(out["raw_volume"], [r_["raw_volume"] for r_ in ref["raw_rows"]], atol=1e-9)
+    np.testing.assert_allclose(out["raw_rate"], [r_["raw_rate"] for r_ in ref["raw_rows"]], atol=1e-12)
+    np.testing.assert_allclose(out["raw_pitch"], [r_["raw_pitch"] for r_ in ref["raw_rows"]], atol=0.6)
+    names = [segs[i].name for i in pl.syn_seg]
+    final, syn_rows, synth_rows = SSML.build(names, pl.syn_words, pl.syn_pause_ms, out["sm_pitch"], out["sm_rate"], out["raw_volume"], "fr-FR-HenriNeural", 1)
+    num = re.compile(r'pitch="([+-][\d.]+)%" rate="([+-][\d.]+)%" volume="([+-][\d.]+)%"')
+    same_pitch = 0
+    for g, w in zip(syn_rows, ref["bdd_syntagme_ssml"]):
+        assert num.sub("P", g["ssml"]) == num.sub("P", w["ssml"])
+        (gp, gr, gv), (wp, wr, wv) = num.search(g["ssml"]).groups(), num.search(w["ssml"]).groups()
+        assert gr == wr and gv == wv
+        assert abs(float(gp) - float(wp)) <= 0.02
+        same_pitch += gp == wp
+    assert same_pitch >= 0.8 * len(syn_rows)          # identical except at the documented .2f rounding boundaries
