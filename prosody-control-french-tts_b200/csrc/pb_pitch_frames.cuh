@@ -16,7 +16,8 @@
 //                                                + r[il+1+m] (1 + cos(pi (1-phi+m) / (1-phi+D))) / (1-phi+m) ]
 // Lane sl takes one side (sl & 1) and every 4th m starting at sl >> 1, so side, sign and the window scale are
 // loop-invariant; the loop body is one shared load, two MUFU (cos, rcp) and a handful of FP32 ops.
-__device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, float x, int depth, int sl) {
+// `nl` (8, 16 or 32, warp-uniform) lanes cooperate on one evaluation; sl = lane within that group.
+__device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, float x, int depth, int sl, int nl = 8) {
     const float fl = floorf(x);
     const float phi = x - fl;
     const int il = (int)fl;
@@ -25,26 +26,25 @@ __device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, fl
     if (phi == 0.0f) {                                        // on a sample: Praat returns y[x] (no early return:
         if (sl == 0 && depth > 0) acc = r[abs(il)];           // the other groups of the warp still shuffle below)
     } else if (D > 0) {
-        const int side = sl & 1, j0 = sl >> 1;
+        const int side = sl & 1, j0 = sl >> 1, hs = nl >> 1;  // hs (4, 8, 16) is even: the sign of a lane's terms is fixed
         const float e = side ? 1.0f - phi : phi;
         const float k = __fdividef(PB_PI_F, e + (float)D);
+        const float fhs = (float)hs;
         float d = e + (float)j0;
         int idx = side ? il + 1 + j0 : il - j0;
-        const int step = side ? 4 : -4;
+        const int step = side ? hs : -hs;
 #ifndef PB_SIMT_EMU
 #pragma unroll 2
 #endif
-        for (int m = j0; m < D; m += 4) {
+        for (int m = j0; m < D; m += hs) {
             const float yv = r[abs(idx)];
             acc += __fdividef(yv * (1.0f + __cosf(d * k)), d);
-            d += 4.0f; idx += step;
+            d += fhs; idx += step;
         }
         if (j0 & 1) acc = -acc;
         acc *= sinpif(phi) * (0.5f / PB_PI_F);
     }
-    acc += __shfl_xor_sync(PB_FULL_MASK, acc, 1);
-    acc += __shfl_xor_sync(PB_FULL_MASK, acc, 2);
-    acc += __shfl_xor_sync(PB_FULL_MASK, acc, 4);
+    for (int o = 1; o < nl; o <<= 1) acc += __shfl_xor_sync(PB_FULL_MASK, acc, o);
     return acc;
 }
 // vertex of the parabola through (xa,fa),(xb,fb),(xc,fc), xa < xb < xc; xb if not concave
@@ -123,7 +123,6 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
                                                     uint8_t* __restrict__ out_n, const float* __restrict__ half_tab) {
     int* imax = (int*)(scratch + 2 * PB_MAXC); // lag of the maximum
     const int B = gm.brent_ixmax, lim = gm.scan_lim, maxc = gm.max_cand;
-    const int sub = lane >> 3, sl = lane & 7;
     // ---- the maxima, in lag order; slot arrays hold PB_MAXC-1 of them, anything beyond max_cand-1 is the rare path
     int total = 0;
     for (int base = 2; base < lim; base += 32) {
@@ -155,8 +154,13 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
         }
         c_first = 1 + pb_warp_sum_i(nskip);
     }
-    // ---- refine the others on the sinc curve: 4 candidates at a time, 8 lanes each
-    for (int c0 = c_first; c0 < ncf; c0 += 4) {
+    // ---- refine the others on the sinc curve; the lanes are split evenly over the candidates of a round:
+    //      32 lanes for a single candidate, 16 each for two, otherwise 8 each and 4 candidates per round
+    const int nref = ncf - c_first;
+    const int nl = nref <= 1 ? 32 : nref == 2 ? 16 : 8;
+    const int per_round = 32 / nl;
+    const int sub = lane / nl, sl = lane & (nl - 1);
+    for (int c0 = c_first; c0 < ncf; c0 += per_round) {
         const int c = c0 + sub;
         const bool have = c < ncf;
         const int i = have ? imax[c] : 2;
@@ -170,20 +174,20 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
         const bool tab = have && depth == 70 && (B - i) >= 70;
         float ta = 0.0f, tb = 0.0f;
         if (tab) {
-            for (int m = sl; m < 70; m += 8) {
+            for (int m = sl; m < 70; m += nl) {
                 const float cm = half_tab[m];
                 ta = fmaf(cm, r[abs(i - 1 - m)] + r[i + m], ta);
                 tb = fmaf(cm, r[abs(i - m)] + r[i + 1 + m], tb);
             }
         }
-        PB_UNROLL for (int o = 1; o < 8; o <<= 1) { ta += __shfl_xor_sync(PB_FULL_MASK, ta, o); tb += __shfl_xor_sync(PB_FULL_MASK, tb, o); }
+        for (int o = 1; o < nl; o <<= 1) { ta += __shfl_xor_sync(PB_FULL_MASK, ta, o); tb += __shfl_xor_sync(PB_FULL_MASK, tb, o); }
         // four evaluations through ONE call site (code size): y(i-.5), y(i+.5), y(x1), y(x2)
         float xe = fi - 0.5f, ya = 0.0f, xc = fi, yc = r0, yl = 0.0f, yr = 0.0f, x1 = fi, y1 = 0.0f, y2 = 0.0f;
 #ifndef PB_SIMT_EMU
 #pragma unroll 1
 #endif
         for (int e = 0; e < 4; e++) {
-            float y = pb_sinc8(r, B, xe, (tab && e < 2) ? 0 : depth, sl);
+            float y = pb_sinc8(r, B, xe, (tab && e < 2) ? 0 : depth, sl, nl);
             if (tab && e < 2) y = e ? tb : ta;
             if (e == 0) { ya = y; xe = fi + 0.5f; }
             else if (e == 1) {
