@@ -114,7 +114,6 @@ struct PbHandle {
     HostBuf stage_units, stage_pairs, stage_lunits, stage_meters, stage_out;
     size_t su_off = 0, sp_off = 0, sl_off = 0;           // running offsets (elements) into the pinned staging buffers
     std::map<std::pair<int64_t, int>, PitchTables*> tables;
-    std::map<double, DevBuf*> lufs_tables;                // per meter rate: impulse-state table H
     std::vector<EvPair> evs;
     std::vector<pbEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -228,33 +227,6 @@ int get_tables(PbHandle* h, const PbGeomHost& g, PitchTables** out) {
     return PB_OK;
 }
 
-int get_lufs_table(PbHandle* h, PbMeterDev& md) {
-    // H[j] = A^j B: the state j samples after a unit impulse into a filter at rest (device table, cached per rate)
-    const double mr = md.rate;
-    md.Lmax = (int)std::floor(0.1 * mr) + 3;
-    auto ht = h->lufs_tables.find(mr);
-    if (ht == h->lufs_tables.end()) {
-        std::vector<double> H((size_t)md.Lmax * 4);
-        double s[4] = {0, 0, 0, 0};
-        for (int j = 0; j < md.Lmax; j++) {
-            const double x = j == 0 ? 1.0 : 0.0;
-            const double y1 = md.b1[0] * x + s[0];
-            const double np0 = md.b1[1] * x - md.a1[1] * y1 + s[1], np1 = md.b1[2] * x - md.a1[2] * y1;
-            const double y2 = md.b2[0] * y1 + s[2];
-            const double nq0 = md.b2[1] * y1 - md.a2[1] * y2 + s[3], nq1 = md.b2[2] * y1 - md.a2[2] * y2;
-            s[0] = np0; s[1] = np1; s[2] = nq0; s[3] = nq1;
-            for (int r = 0; r < 4; r++) H[(size_t)j * 4 + r] = s[r];
-        }
-        DevBuf* db = new DevBuf();
-        if (db->ensure(H.size() * 8)) { delete db; return fail(h, PB_ENOMEM, "out of memory: %s", "loudness tables"); }
-        pbrt_h2d(db->p, H.data(), H.size() * 8, h->stream);
-        pbrt_stream_sync(h->stream);
-        ht = h->lufs_tables.insert(std::make_pair(mr, db)).first;
-    }
-    md.H = (const double*)ht->second->p;
-    return PB_OK;
-}
-
 // ------------------------------------------------------------------------------------------------ planning (host only)
 int validate_units(PbHandle* h, const PbUnits* u, int64_t pcm_len) {
     if (!u || u->n_units < 0) return fail(h, PB_EINVAL, "%s", "units is null or n_units < 0");
@@ -345,8 +317,6 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
                     if (step >= L0) for (int r = 0; r < 4; r++) md.M[step - L0][r * 4 + c] = s[r];
                 }
             }
-            int rc = get_lufs_table(h, md);
-            if (rc != PB_OK) return rc;
             bp.meters.push_back(md);
             it = meter_ix.insert(std::make_pair(mr, (int)bp.meters.size() - 1)).first;
         }
@@ -539,14 +509,12 @@ int launch_lufs_group(PbHandle* h, const int16_t* d_pcm, const LufsLaunch& L) {
         int g1 = (int)std::max<size_t>(1, std::min<size_t>((m + 7) / 8, (size_t)h->sm_count * 8));           // one warp per unit
         PB_LAUNCH(pb_lufs_peak_kernel, dim3(g1), dim3(256), 0, h->stream, d_pcm, du, (int)m);
         int gc = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 127) / 128, (int64_t)h->sm_count * 16));
-        const int64_t tiles = (chunks + PB_LUFS_CB - 1) / PB_LUFS_CB;                                        // one warp per tile of chunks
-        int gw = (int)std::max<int64_t>(1, std::min<int64_t>((tiles + 3) / 4, (int64_t)h->sm_count * 16));
-        PB_LAUNCH(pb_lufs_state_kernel, dim3(gw), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st);
+        auto k_state = pb_lufs_chunk_kernel<false>; auto k_energy = pb_lufs_chunk_kernel<true>;
+        PB_LAUNCH(k_state, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
         int gu = (int)std::max<size_t>(1, std::min<size_t>((m + 127) / 128, (size_t)h->sm_count * 16));
         int gs = (int)std::max<size_t>(1, std::min<size_t>((m + 31) / 32, (size_t)h->sm_count * 16));         // 8 units per warp
         PB_LAUNCH(pb_lufs_scan_kernel, dim3(gs), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, st);
-        PB_LAUNCH(pb_lufs_energy_kernel, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks,
-                  (const double*)st, en);
+        PB_LAUNCH(k_energy, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
         PB_LAUNCH(pb_lufs_gate_kernel, dim3(gu), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, (const double*)en, (double*)h->lufs.p);
         h->last.n_launches += 5;
     }
@@ -734,7 +702,6 @@ void pb_destroy(PbHandle* h) {
     HostBuf* hbs[] = {&h->stage_units, &h->stage_pairs, &h->stage_lunits, &h->stage_meters, &h->stage_out};
     for (auto* b : hbs) b->release();
     for (auto& kv : h->tables) { kv.second->window.release(); kv.second->inv_wr.release(); kv.second->tw_a.release(); kv.second->tw_b.release(); kv.second->half_tab.release(); delete kv.second; }
-    for (auto& kv : h->lufs_tables) { kv.second->release(); delete kv.second; }
     for (auto& e : h->ev_pool) pbrt_event_destroy(e);
     pbrt_stream_destroy(h->own_stream);
     pbrt_stream_destroy(h->copy_stream);

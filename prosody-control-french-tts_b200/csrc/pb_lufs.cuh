@@ -22,9 +22,8 @@ struct PbMeterDev {           // one per distinct pyln.Meter(rate)
     double b2[3], a2[3];      // high pass
     double rate;
     int32_t L0;               // smallest chunk length with a precomputed transition matrix
-    int32_t Lmax;             // rows of H
+    int32_t pad;
     double M[PB_LUFS_NM][16]; // row-major 4x4, M[k] = A^(L0+k) on the state (p0,p1,q0,q1)
-    const double* H;          // [Lmax][4] device table: H[j] = A^j B, the state j samples after a unit impulse
 };
 
 struct PbLufsUnitDev {
@@ -64,87 +63,12 @@ __device__ __forceinline__ int pb_lufs_find_unit(const PbLufsUnitDev* __restrict
     return lo;
 }
 
-// (1) Zero-state contribution of every chunk.  The state after filtering x[0..L-1] from rest is the linear combination
-// sum_k x[k] * H[L-1-k] with H[j] = A^j B: four independent dot products, no recurrence.  Indexing by j = distance from
-// the END of the chunk makes the table row independent of the chunk length, so one warp takes PB_LUFS_CB consecutive
-// chunks and every H row it loads (32 B) serves all of them: lanes stride over j (coalesced s16 and table reads),
-// 4 DFMA per sample, shuffle-reduce at the end.
-#define PB_LUFS_CB 4
-__global__ void __launch_bounds__(128)
-pb_lufs_state_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
-                     const PbMeterDev* __restrict__ meters, long long n_chunks_total, double* __restrict__ state /* [n_chunks][4] */) {
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const long long n_tiles = (n_chunks_total + PB_LUFS_CB - 1) / PB_LUFS_CB;
-    for (long long tile = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); tile < n_tiles; tile += (long long)gridDim.x * wpb) {
-        const int16_t* q[PB_LUFS_CB];      // last sample of the chunk
-        int len[PB_LUFS_CB], jmin[PB_LUFS_CB], met[PB_LUFS_CB];
-        double ip[PB_LUFS_CB], s[PB_LUFS_CB][4];
-        int maxlen = 0;
-        PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) {
-            const long long ch = tile * PB_LUFS_CB + c;
-            q[c] = pcm; len[c] = 0; jmin[c] = 0; met[c] = -1; ip[c] = 0.0;
-            s[c][0] = s[c][1] = s[c][2] = s[c][3] = 0.0;
-            if (ch < n_chunks_total) {
-                const int u = pb_lufs_find_unit(units, n_units, ch);
-                const PbLufsUnitDev ud = units[u];
-                const double rate = meters[ud.meter].rate;
-                const int cc = (int)(ch - ud.chunk_off);
-                const long long nreal = ud.b - ud.a, n = nreal + ud.npad;
-                const long long lo = pb_lufs_bound(cc, rate, n), hi = pb_lufs_bound(cc + 1, rate, n);
-                len[c] = (int)(hi - lo);
-                jmin[c] = hi > nreal ? (int)(hi - nreal) : 0;          // samples at or beyond nreal are pydub's zero padding
-                q[c] = pcm + ud.pcm_off + ud.a + (hi - 1);
-                met[c] = len[c] <= meters[ud.meter].Lmax ? ud.meter : -2 - ud.meter;   // -2-m: table too short (never): slow path
-                ip[c] = ud.inv_peak;
-                if (len[c] > maxlen) maxlen = len[c];
-            }
-        }
-        // sweep once per distinct meter among the chunks of the tile (normally one)
-        unsigned todo = 0;
-        PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) if (met[c] >= 0 && len[c] > 0) todo |= 1u << c;
-        while (todo) {
-            const int lead = __ffs((int)todo) - 1;
-            int m0 = 0;
-            PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) if (c == lead) m0 = met[c];
-            unsigned grp = 0;
-            PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) if ((todo >> c & 1u) && met[c] == m0) grp |= 1u << c;
-            const double* __restrict__ H = meters[m0].H;
-            for (int j = lane; j < maxlen; j += 32) {
-                const double* h = H + (size_t)j * 4;
-                const double h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3];
-                PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) {
-                    if ((grp >> c & 1u) && j < len[c] && j >= jmin[c]) {
-                        const double x = (double)q[c][-j] * ip[c];
-                        s[c][0] += x * h0; s[c][1] += x * h1; s[c][2] += x * h2; s[c][3] += x * h3;
-                    }
-                }
-            }
-            todo &= ~grp;
-        }
-        PB_UNROLL for (int c = 0; c < PB_LUFS_CB; c++) {
-            PB_UNROLL for (int r = 0; r < 4; r++) {
-                PB_UNROLL for (int o = 16; o > 0; o >>= 1) s[c][r] += __shfl_xor_sync(PB_FULL_MASK, s[c][r], o);
-            }
-            const long long ch = tile * PB_LUFS_CB + c;
-            if (met[c] <= -2 && lane == 0) {     // never with the tables the host builds; kept so a bad table cannot corrupt results
-                const PbMeterDev* mt = meters + (-2 - met[c]);
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                for (int k = len[c] - 1; k >= 0; k--) {
-                    const double x = k >= jmin[c] ? (double)q[c][-k] * ip[c] : 0.0;
-                    const double y1 = mt->b1[0] * x + a0;
-                    a0 = mt->b1[1] * x - mt->a1[1] * y1 + a1; a1 = mt->b1[2] * x - mt->a1[2] * y1;
-                    const double y2 = mt->b2[0] * y1 + a2;
-                    a2 = mt->b2[1] * y1 - mt->a2[1] * y2 + a3; a3 = mt->b2[2] * y1 - mt->a2[2] * y2;
-                }
-                s[c][0] = a0; s[c][1] = a1; s[c][2] = a2; s[c][3] = a3;
-            }
-            if (lane == 0 && ch < n_chunks_total) { state[ch * 4 + 0] = s[c][0]; state[ch * 4 + 1] = s[c][1]; state[ch * 4 + 2] = s[c][2]; state[ch * 4 + 3] = s[c][3]; }
-        }
-    }
-}
-
-// (3) Energy of the K-weighted signal per chunk, from the chunk's true initial state.  One thread per chunk (the
-// recurrence is sequential); samples arrive eight at a time through aligned 16-byte loads.
+// (1) and (3): one thread per chunk runs the K-weighting recurrence over its samples, eight at a time through aligned
+// 16-byte loads.  ENERGY = false: from rest, keeping only the final state (the chunk's zero-state contribution);
+// ENERGY = true: from the chunk's true initial state, accumulating the energy of the weighted signal.
+// (A chain-free formulation of pass 1 — the final state as four dot products against A^j B, one warp per chunk — was
+// tried and lost: 2-byte strided loads gave it no memory-level parallelism, 79 % long-scoreboard stalls, 6.6 ms vs 2.4 ms
+// for this kernel on the same data; profiles/r01_lufs_state_dot_ncu_summary.csv.)
 #define PB_LUFS_STEP(xv)                                                  \
     {                                                                     \
         const double x_ = (xv);                                           \
@@ -156,10 +80,11 @@ pb_lufs_state_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __res
         q1 = b22 * y1_ - a22 * y2_;                                       \
         e += y2_ * y2_;                                                   \
     }
+template <bool ENERGY>
 __global__ void __launch_bounds__(128)
-pb_lufs_energy_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
-                      const PbMeterDev* __restrict__ meters, long long n_chunks_total,
-                      const double* __restrict__ state /* [n_chunks][4] */, double* __restrict__ energy /* [n_chunks] */) {
+pb_lufs_chunk_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
+                     const PbMeterDev* __restrict__ meters, long long n_chunks_total,
+                     double* __restrict__ state /* [n_chunks][4] */, double* __restrict__ energy /* [n_chunks] */) {
     for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < n_chunks_total; ch += (long long)gridDim.x * blockDim.x) {
         const int u = pb_lufs_find_unit(units, n_units, ch);
         const PbLufsUnitDev ud = units[u];
@@ -170,7 +95,8 @@ pb_lufs_energy_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __re
         const long long real_hi = hi < nreal ? hi : nreal;
         const double b10 = mt->b1[0], b11 = mt->b1[1], b12 = mt->b1[2], a11 = mt->a1[1], a12 = mt->a1[2];
         const double b20 = mt->b2[0], b21 = mt->b2[1], b22 = mt->b2[2], a21 = mt->a2[1], a22 = mt->a2[2];
-        double p0 = state[ch * 4 + 0], p1 = state[ch * 4 + 1], q0 = state[ch * 4 + 2], q1 = state[ch * 4 + 3], e = 0.0;
+        double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0, e = 0.0;
+        if (ENERGY) { p0 = state[ch * 4 + 0]; p1 = state[ch * 4 + 1]; q0 = state[ch * 4 + 2]; q1 = state[ch * 4 + 3]; }
         const int16_t* __restrict__ p = pcm + ud.pcm_off + ud.a;
         const double ip = ud.inv_peak;
         long long i = lo;
@@ -185,7 +111,8 @@ pb_lufs_energy_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __re
         }
         while (i < real_hi) { PB_LUFS_STEP((double)p[i] * ip); i++; }
         while (i < hi) { PB_LUFS_STEP(0.0); i++; }          // pydub's silent padding
-        energy[ch] = e;
+        if (ENERGY) energy[ch] = e;
+        else { state[ch * 4 + 0] = p0; state[ch * 4 + 1] = p1; state[ch * 4 + 2] = q0; state[ch * 4 + 3] = q1; }
     }
 }
 
