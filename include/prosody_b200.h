@@ -19,7 +19,8 @@
  *   - A "file" is mono 16-bit PCM (what the reference pipeline writes); all files of a call live in one
  *     concatenated int16 buffer, file f occupying [file_off[f], file_off[f]+file_nx[f]).
  *   - `pcm_on_device` selects whether `pcm` is a device pointer (HBM-resident input) or a host pointer
- *     (the library stages it through its own stream; pin it for full PCIe speed).
+ *     (the library stages it through its own stream; pin it for full PCIe speed).  The library works on its own
+ *     streams: device PCM must be complete when the call is made (synchronise the stream that produced it).
  *   - Unit descriptors and per-unit results are HOST arrays owned by the caller.  Optional per-frame outputs
  *     are host arrays sized with pb_pitch_plan().
  *   - The library owns only the handle: tables per analysis geometry and a scratch arena that grows on demand.

@@ -88,6 +88,9 @@ def _pcm_pointer(pcm):
         if pcm.dtype != torch.int16:
             raise TypeError("pcm tensor must be int16")
         pcm = pcm.contiguous()
+        if pcm.is_cuda:
+            # the library reads the tensor on its own stream: whatever torch still has queued to produce it must be done
+            torch.cuda.current_stream(pcm.device).synchronize()
         return pcm.data_ptr(), pcm.numel(), int(pcm.is_cuda), pcm
     raise TypeError("pcm must be a numpy int16 array or a torch int16 tensor")
 

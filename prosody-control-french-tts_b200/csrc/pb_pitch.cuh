@@ -165,6 +165,8 @@ template <int LOG2N> struct PbFftCfg {
 };
 
 template <int G> __device__ __forceinline__ void pb_group_sync(int bar_id) {
-    if (G == 1) __syncwarp(); else PB_GROUP_SYNC(bar_id, 32 * G);
+    // A named barrier even for a single warp: ptxas clones code across __syncwarp() (it kept a second copy of the
+    // unrolled butterfly network for the first loop iteration) but not across bar.sync.
+    PB_GROUP_SYNC(bar_id, 32 * G);
 }
 __device__ __forceinline__ int pb_pad5(int i) { return i + (i >> 5); }

@@ -344,12 +344,8 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
         float pkA = 0.0f, pkB = 0.0f, sA = 1.0f, sB = 1.0f;
         bool active = false;
 
-#ifndef PB_SIMT_EMU
-#pragma unroll 1
-#endif
-        for (int step = 0; step < 4; step++) {          // FFT (step >> 1), pass (step & 1): one copy of the butterfly code
-            const int pass = step & 1;
-            if (step == 0) {
+        {
+            {
                 // ---- which frame samples exist: sample n of frame f is part sample start+n = file sample ix1+start+n-2;
                 //      Praat zero-fills outside the part and outside the file
                 int nlo[2], nhi[2], sb[2]; float lmean[2];
@@ -400,14 +396,28 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
                     pb_group_sync<G>(bar_id);
                 }
                 active = !global_silent && (pkA > 0.0f || pkB > 0.0f);
-                if (!active) break;
                 // bring both frames to comparable magnitude (power-of-two scales are exact and cancel in r = ac/ac[0]):
                 // keeps the weaker frame of a pair out of the stronger one's rounding noise
                 // (exponent arithmetic on the float bits: scale = 2^-(exponent of the maximum))
                 sA = mxA > 0.0f ? __int_as_float((254 - ((__float_as_int(mxA) >> 23) & 0xff)) << 23) : 1.0f;
                 sB = mxB > 0.0f ? __int_as_float((254 - ((__float_as_int(mxB) >> 23) & 0xff)) << 23) : 1.0f;
                 pb_group_sync<G>(bar_id);               // the windowed frames are in the buffer
-            } else if (step == 2) {
+            }
+        }
+        // ---- two FFTs x two passes through ONE copy of the butterfly code: FFT (step >> 1), pass (step & 1).  The step
+        //      index is made opaque so the optimiser neither peels nor unswitches the loop (either duplicates ~450
+        //      instructions of butterflies, and instruction fetch is what this kernel stalls on).
+#ifndef PB_SIMT_EMU
+#pragma unroll 1
+#endif
+        int n_steps = active ? 4 : 0;
+        asm volatile("" : "+r"(n_steps));
+        for (int it = 0; it < n_steps; it++) {
+            int step = it;
+            asm volatile("" : "+r"(step));
+            int pass = step & 1;
+            asm volatile("" : "+r"(pass));              // ... nor thread the step == 2 path (where pass is known) through a private copy
+            if (step == 2) {
                 // ---- power spectra of both frames: P_a = |Z_k + conj Z_-k|^2 / 4, P_b = |Z_k - conj Z_-k|^2 / 4
                 for (int k = g; k <= N / 2; k += GT) {
                     const int k2 = (N - k) & (N - 1);
