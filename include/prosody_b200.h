@@ -81,7 +81,8 @@ typedef struct PbUnits {
     const int64_t* file_off;   /* sample offset of the unit's file inside pcm */
     const int64_t* file_nx;    /* samples in that file */
     const double* rate;        /* file sample rate (Hz) */
-    const int32_t* has_t1;     /* 0: whole file (t1 is None); 1: slice [t0, t1] */
+    const int32_t* has_t1;     /* 0: whole file (t1 is None); 1: slice [t0, t1]; 2 (pitch only): slice with
+                                  extract_part(preserve_times=False), the legacy callers' form */
     const double* t0;          /* seconds (the reference passes start_ms/1000) */
     const double* t1;
     const double* meter_rate;  /* pyln.Meter(rate) the reference built for this call; may be NULL for pitch-only */
@@ -149,6 +150,13 @@ int pb_intensity_plan(const PbUnits* u, double minimum_pitch, double time_step, 
 int pb_intensity_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
                        const PbUnits* u, double minimum_pitch, double time_step, int subtract_mean,
                        float* intensity_db, int32_t* status);
+
+/* The legacy loudness of Code/Pipeline/compute_pitch_adjustments.py:157-164 (_calculate_loudness), batched:
+ * 20*log10(sqrt(|mean(samples**2)|)) over audio[start*1000:end*1000] (pydub FLOAT-millisecond slice; t0/t1 carry
+ * start/end in seconds), with numpy's int16 wrap-around of samples**2 reproduced bit for bit.  An empty slice
+ * yields NaN and a silent one -inf, as numpy does. */
+int pb_legacy_loudness_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
+                             const PbUnits* u, double* loudness_db);
 
 /* ---- host-side arithmetic of the step (float64, same libm calls and operation order as the reference's Python) */
 

@@ -110,21 +110,25 @@ def read_wav(path) -> tuple[np.ndarray, int]:
 
 
 # ------------------------------------------------------------------------------------------ Praat pitch
-def pitch_geometry(file_nx: int, sr: float, t0=0.0, t1=None, params: PoPitchParams | None = None):
+def _has_t1(t1, preserve_times):
+    return 0 if t1 is None else (1 if preserve_times else 2)
+
+
+def pitch_geometry(file_nx: int, sr: float, t0=0.0, t1=None, params: PoPitchParams | None = None, preserve_times=True):
     params = params or pitch_params()
     g = PoPitchGeom()
     ix1, nx, x1 = C.c_int64(), C.c_int64(), C.c_double()
-    st = lib().po_pitch_unit_geometry(file_nx, float(sr), int(t1 is not None), float(t0), float(t1 or 0.0),
+    st = lib().po_pitch_unit_geometry(file_nx, float(sr), _has_t1(t1, preserve_times), float(t0), float(t1 or 0.0),
                                       C.byref(params), C.byref(g), C.byref(ix1), C.byref(nx), C.byref(x1))
     return st, g, ix1.value, nx.value, x1.value
 
 
 def pitch_track(pcm: np.ndarray, sr: float, t0=0.0, t1=None, params: PoPitchParams | None = None,
-                want_candidates=False) -> dict:
+                want_candidates=False, preserve_times=True) -> dict:
     """Full ``to_pitch`` on (a slice of) an in-memory file. Raises PraatError where Praat throws."""
     params = params or pitch_params()
     pcm = np.ascontiguousarray(pcm, dtype=np.int16)
-    st, g, ix1, nx, x1 = pitch_geometry(len(pcm), sr, t0, t1, params)
+    st, g, ix1, nx, x1 = pitch_geometry(len(pcm), sr, t0, t1, params, preserve_times)
     if st != PO_OK:
         raise PraatError(f"Praat would throw (status {st}) for slice t0={t0} t1={t1}")
     nF, maxC = g.nFrames, g.maxnCandidates
@@ -132,7 +136,7 @@ def pitch_track(pcm: np.ndarray, sr: float, t0=0.0, t1=None, params: PoPitchPara
     pre_f = np.zeros((nF, maxC)) if want_candidates else None
     pre_s = np.zeros((nF, maxC)) if want_candidates else None
     med, nv, nfr = C.c_double(), C.c_int32(), C.c_int32()
-    st = lib().po_median_pitch_i16(_p(pcm, C.c_int16), len(pcm), float(sr), int(t1 is not None), float(t0),
+    st = lib().po_median_pitch_i16(_p(pcm, C.c_int16), len(pcm), float(sr), _has_t1(t1, preserve_times), float(t0),
                                    float(t1 or 0.0), C.byref(params), C.byref(med), C.byref(nv), C.byref(nfr),
                                    _p(sel_f, C.c_double), _p(sel_s, C.c_double), _p(ncand, C.c_int32),
                                    _p(inten, C.c_double),
@@ -273,3 +277,97 @@ def counters() -> dict:
 
 def max_threads() -> int:
     return lib().po_max_threads()
+
+
+# ------------------------------------------------------------------------------------------ "next" rows
+def bessel_i0_f(x: float) -> float:
+    """Praat NUMbessel_i0_f (melder/NUMspecfunc.cpp): Abramowitz & Stegun 9.8.1 / 9.8.2."""
+    x = abs(x)
+    if x < 3.75:
+        t = (x / 3.75) ** 2
+        return 1.0 + t * (3.5156229 + t * (3.0899424 + t * (1.2067492 + t * (0.2659732 + t * (0.0360768 + t * 0.0045813)))))
+    t = 3.75 / x
+    return math.exp(x) / math.sqrt(x) * (0.39894228 + t * (0.01328592 + t * (0.00225319 + t * (-0.00157565 + t * (
+        0.00916281 + t * (-0.02057706 + t * (0.02635537 + t * (-0.01647633 + t * 0.00392377))))))))
+
+
+def intensity_geometry(nx: int, sr: float, minimum_pitch=100.0, time_step=0.0):
+    """Praat Sound_to_Intensity geometry -> (status, n_frames, t_first, dt, half_window_samples)."""
+    dx, x1 = 1.0 / sr, 0.5 / sr
+    dt = time_step if time_step > 0 else 0.8 / minimum_pitch
+    window = 6.4 / minimum_pitch
+    half = int(math.floor(0.5 * window / dx))
+    duration = dx * nx
+    if window > duration:
+        return PO_ERR_TOO_SHORT, 0, 0.0, dt, half
+    n_frames = int(math.floor((duration - window) / dt)) + 1
+    mid = x1 - 0.5 * dx + 0.5 * duration
+    t_first = mid - 0.5 * (n_frames * dt) + 0.5 * dt
+    return PO_OK, n_frames, t_first, dt, half
+
+
+def intensity(pcm: np.ndarray, sr: float, minimum_pitch=100.0, time_step=0.0, subtract_mean=True) -> np.ndarray:
+    """≙ parselmouth Sound.to_intensity().values[0] (Praat fon/Sound_to_Intensity.cpp) for a mono s16 file, dB re 4e-10."""
+    x = np.asarray(pcm, np.float64) / 32768.0
+    nx = len(x)
+    st, n_frames, t_first, dt, half = intensity_geometry(nx, sr, minimum_pitch, time_step)
+    if st != PO_OK:
+        raise PraatError("Praat: sound shorter than the intensity window")
+    dx, x1 = 1.0 / sr, 0.5 / sr
+    half_dur = 0.5 * 6.4 / minimum_pitch
+    i = np.arange(-half, half + 1)
+    xx = i * dx / half_dur
+    root = np.sqrt(np.clip(1.0 - xx * xx, 0.0, None))
+    window = np.array([bessel_i0_f((2.0 * math.pi * math.pi + 0.5) * r) for r in root])
+    out = np.empty(n_frames)
+    for f in range(n_frames):
+        t = t_first + f * dt
+        mid = int(math.floor((t - x1) / dx + 1.0 + 0.5))
+        left, right = max(1, mid - half), min(nx, mid + half)
+        a = x[left - 1:right].copy()
+        w = window[left - mid + half:right - mid + half + 1]
+        if subtract_mean:
+            a -= a.sum() / (right - left + 1)
+        inten = float((a * a * w).sum() / w.sum()) / 4e-10
+        out[f] = -300.0 if inten < 1e-30 else 10.0 * math.log10(inten)
+    return out
+
+
+def legacy_loudness(pcm: np.ndarray, rate: int, start: float, end: float) -> float:
+    """≙ _calculate_loudness (Code/Pipeline/compute_loudness_adjustments.py:8-25): RMS dB of the slice with the
+    reference's int16 wrap-around in ``samples ** 2``. pydub slice positions are ``start*1000`` / ``end*1000`` (float ms)."""
+    n = len(pcm)
+    L = pydub_len_ms(n, rate)
+    s_ms, e_ms = min(start * 1000, L), min(end * 1000, L)
+    per_ms = rate / 1000.0
+    sf, ef = int(s_ms * per_ms), int(e_ms * per_ms)
+    a = min(sf, n); b = max(a, min(ef, n))
+    seg = np.asarray(pcm[a:b], np.int16)
+    missing = max(ef - sf, 0) - (b - a)               # pydub pads an overshoot of < 2 ms with zeros, else raises
+    if missing:
+        if missing > 2 * per_ms:
+            return float("nan")
+        if len(seg):
+            seg = np.concatenate([seg, np.zeros(missing, np.int16)])
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        S = seg ** 2                                   # int16: wraps modulo 2^16 exactly like the reference
+        rms = np.sqrt(np.abs(np.mean(S))) if len(S) else float("nan")
+        return float(20 * np.log10(rms))
+
+
+def legacy_pitch_segment(pcm: np.ndarray, sr: float, start: float, end: float) -> float:
+    """≙ calculate_pitch_segment (Code/Pipeline/compute_pitch_adjustments.py:167-208): extract_part (times not preserved),
+    first pitch floor of [75, 100, 150, 200] that yields a voiced frame, geometric mean of the voiced frequencies."""
+    import statistics
+    total = len(pcm) / sr
+    if start >= end or start < 0 or end > total:
+        return 0
+    for floor in (75, 100, 150, 200):
+        try:
+            tr = pitch_track(pcm, sr, start, end, pitch_params(float(floor), 600.0), preserve_times=False)
+        except PraatError:
+            continue
+        v = tr["frequency"][tr["frequency"] != 0]
+        if len(v):
+            return statistics.geometric_mean(v)
+    return 0

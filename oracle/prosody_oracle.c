@@ -504,7 +504,8 @@ done:
 /*
  * ≙ get_median_pitch (audioPipeline.py:326-335) on an in-memory mono s16 file.
  *   pcm[0..file_nx-1], sample rate sr. has_t1==0 -> whole file (to_pitch on the Sound itself);
- *   else extract_part(from_time=t0, to_time=t1, rectangular, relwidth 1, preserve_times=True).
+ *   1 -> extract_part(from_time=t0, to_time=t1, rectangular, relwidth 1, preserve_times=True);
+ *   2 -> the same with preserve_times=False (parselmouth's default, used by the legacy compute_pitch_adjustments.py).
  * Praat WAV decode: s16 / 32768. Sound: dx=1/sr, x1=0.5/sr, xmin=0, xmax=nx*dx.
  * Returns status; *median = np.median(freqs[freqs>0]) or 0.0; counts out.
  * If sel_f != NULL it must hold the frames (use po_pitch_unit_nframes first).
@@ -521,6 +522,7 @@ static int po_extract_geometry(int64_t file_nx, double sr, int has_t1, double t0
     if (i2 < i1) return PO_ERR_NO_SAMPLES;
     *ix1 = i1; *nx = i2 - i1 + 1;
     *x1_part = x1 + (double)(i1 - 1) * dx;
+    if (has_t1 == 2) *x1_part -= t0;   /* preserve_times = false (Praat: thy xmin = 0; thy xmax -= t1; thy x1 -= t1) */
     return PO_OK;
 }
 

@@ -200,6 +200,43 @@ class Extractor:
         return dict(median_f0=med, n_voiced=nv, n_frames=nf, lufs=lu, duration_s=du, status=st)
 
 
+    def intensity(self, pcm, units: Units, minimum_pitch: float = 100.0, time_step: float = 0.0, subtract_mean: bool = True) -> dict:
+        """parselmouth ``Sound.to_intensity(minimum_pitch, time_step, subtract_mean)`` for every (whole-file) unit.
+        Returns the dB values of all files back to back plus frame_off / t_first / dt to place them in time."""
+        addr, n_samp, on_dev, keep = _pcm_pointer(pcm)
+        st, nf, fo, t1, dt = intensity_plan(units, minimum_pitch, time_step, self._lib)
+        out = np.zeros(int(fo[-1]), np.float32)
+        st2 = np.zeros(len(units), np.int32)
+        cu = units.c_struct()
+        rc = self._lib.pb_intensity_batch(self._h, C.c_void_p(addr), n_samp, on_dev, C.byref(cu), float(minimum_pitch), float(time_step),
+                                          int(bool(subtract_mean)), _ptr(out, C.c_float), _ptr(st2, C.c_int32))
+        N.check(self._lib, self._h, rc, "pb_intensity_batch")
+        del keep
+        return dict(intensity_db=out, frame_off=fo, n_frames=nf, t_first=t1, dt=dt, status=st2)
+
+    def legacy_loudness(self, pcm, units: Units) -> np.ndarray:
+        """_calculate_loudness(path, start, end) of the legacy DataFrame pipeline for every unit (t0/t1 = start/end seconds)."""
+        addr, n_samp, on_dev, keep = _pcm_pointer(pcm)
+        out = np.zeros(len(units))
+        cu = units.c_struct()
+        rc = self._lib.pb_legacy_loudness_batch(self._h, C.c_void_p(addr), n_samp, on_dev, C.byref(cu), _ptr(out, C.c_double))
+        N.check(self._lib, self._h, rc, "pb_legacy_loudness_batch")
+        del keep
+        return out
+
+
+def intensity_plan(units: Units, minimum_pitch: float = 100.0, time_step: float = 0.0, lib=None):
+    """Host-only: (status, n_frames, frame_off, t_first, dt) of Praat's Sound_to_Intensity per whole-file unit."""
+    lib = lib if lib is not None else N.load()
+    n = len(units)
+    st = np.zeros(n, np.int32); nf = np.zeros(n, np.int32); fo = np.zeros(n + 1, np.int64); t1 = np.zeros(n); dt = np.zeros(n)
+    cu = units.c_struct()
+    rc = lib.pb_intensity_plan(C.byref(cu), float(minimum_pitch), float(time_step), _ptr(st, C.c_int32), _ptr(nf, C.c_int32),
+                               _ptr(fo, C.c_int64), _ptr(t1, C.c_double), _ptr(dt, C.c_double))
+    N.check(lib, None, rc, "pb_intensity_plan")
+    return st, nf, fo, t1, dt
+
+
 def pitch_plan(units: Units, params: N.PbPitchParams | None = None, lib=None):
     """Host-only: (status, n_frames, frame_off) per unit, as Praat would see them."""
     lib = lib if lib is not None else N.load()

@@ -762,5 +762,6 @@ int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_o
 }
 
 #include "pb_api_host.inc"
+#include "pb_api_next.inc"
 
 }  // extern "C"

@@ -13,6 +13,7 @@
 // All filter state is float64 (the 38 Hz high-pass has a double pole at radius ~0.99).
 #pragma once
 #include "pb_rt.h"
+#include "pb_stream.cuh"
 #include <math.h>
 
 #define PB_LUFS_NM 6          // transition matrices A^(L0) .. A^(L0+NM-1) kept per meter rate
@@ -204,34 +205,42 @@ pb_lufs_gate_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const 
 }
 
 // ------------------------------------------------------------------------------------------------ K4b: Praat Sound_to_Intensity
-// One warp per frame: Kaiser-Bessel-like window (Praat's bessel_i0 window), mean-subtracted energy, dB re 4e-10.
+// parselmouth Sound.to_intensity() (Code/visualisation/Compare_speech_noenhanced.py:19-26) = Praat Sound_to_Intensity:
+// per frame, the samples within +-halfWindow of the frame centre (clipped to the sound), mean-subtracted, weighted by
+// Praat's Bessel window, mean energy re 4e-10 in dB.  One warp per frame, float64 accumulation; the integer sum for the
+// mean is exact.  (Frames overlap 8x; the 2 B/sample re-reads come from L1/L2.)
 struct PbIntensityUnitDev {
-    int64_t pcm_off; int64_t frame_off; double x1; double t1; int32_t nx; int32_t n_frames; int32_t out_index; int32_t pad;
+    int64_t pcm_off;      // file start in the pcm buffer
+    int64_t frame_off;    // first frame of this unit in the output
+    double t1;            // time of the first frame
+    int32_t nx;           // samples in the file
+    int32_t n_frames;
 };
 __global__ void __launch_bounds__(128)
-pb_intensity_kernel(const int16_t* __restrict__ pcm, const PbIntensityUnitDev* __restrict__ units, const int64_t* __restrict__ frame_off,
-                    int n_units, long long n_frames_total, const float* __restrict__ window /* [2*half+1] */, int half,
-                    double dx, double dt, int subtract_mean, float* __restrict__ out_db) {
+pb_intensity_kernel(const int16_t* __restrict__ pcm, const PbIntensityUnitDev* __restrict__ units, int n_units, long long n_frames_total,
+                    const double* __restrict__ window /* [2*half+1] */, int half, double dx, double dt, int subtract_mean,
+                    float* __restrict__ out_db) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (long long fr = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); fr < n_frames_total; fr += (long long)gridDim.x * wpb) {
         int lo = 0, hi = n_units;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (frame_off[mid] <= fr) lo = mid; else hi = mid; }
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (units[mid].frame_off <= fr) lo = mid; else hi = mid; }
         const PbIntensityUnitDev ud = units[lo];
         const int f = (int)(fr - ud.frame_off);
+        const double x1 = 0.5 * dx;
         const double t = __dadd_rn(ud.t1, __dmul_rn((double)f, dt));
         // Sampled_xToNearestIndex: round((t - x1)/dx + 1)
-        const long long mid = (long long)floor(__dadd_rn(__ddiv_rn(__dsub_rn(t, ud.x1), dx), 1.0) + 0.5);
+        const long long mid = (long long)floor(__dadd_rn(__dadd_rn(__ddiv_rn(__dsub_rn(t, x1), dx), 1.0), 0.5));
         long long l = mid - half, r = mid + half;
-        if (l < 1) l = 1; if (r > ud.nx) r = ud.nx;
-        const int16_t* p = pcm + ud.pcm_off;
-        // mean over the clipped span (exact in integers)
+        if (l < 1) l = 1;
+        if (r > ud.nx) r = ud.nx;
+        const int16_t* __restrict__ p = pcm + ud.pcm_off;
         long long s = 0;
         for (long long i = l + lane; i <= r; i += 32) s += p[i - 1];
         PB_UNROLL for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(PB_FULL_MASK, s, o);
-        const double mean = subtract_mean && r >= l ? ((double)s / 32768.0) / (double)(r - l + 1) : 0.0;
+        const double mean = (subtract_mean && r >= l) ? ((double)s / 32768.0) / (double)(r - l + 1) : 0.0;
         double sumxw = 0.0, sumw = 0.0;
         for (long long i = l + lane; i <= r; i += 32) {
-            const double w = (double)window[(int)(i - mid + half)];
+            const double w = window[(int)(i - mid + half)];
             const double x = (double)p[i - 1] / 32768.0 - mean;
             sumxw += x * x * w; sumw += w;
         }
@@ -243,5 +252,21 @@ pb_intensity_kernel(const int16_t* __restrict__ pcm, const PbIntensityUnitDev* _
             I /= 4.0e-10;
             out_db[fr] = I < 1.0e-30 ? -300.0f : (float)(10.0 * log10(I));
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ legacy RMS loudness
+// _calculate_loudness (Code/Pipeline/compute_loudness_adjustments.py:8-25) squares the samples in int16, so every
+// square wraps modulo 2^16 before the mean is taken.  One warp per unit: exact int64 sum of the wrapped squares.
+struct PbRangeDev { int64_t first; int64_t count; };
+__global__ void __launch_bounds__(256)
+pb_wrapped_square_sum_kernel(const int16_t* __restrict__ pcm, const PbRangeDev* __restrict__ ranges, int n, long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int u = blockIdx.x * wpb + (threadIdx.x >> 5); u < n; u += gridDim.x * wpb) {
+        const PbRangeDev rg = ranges[u];
+        long long sum = 0;
+        pb_warp_foreach_s16(pcm, rg.first, rg.first + rg.count, lane, [&](int v) { sum += (long long)(short)(v * v); });
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(PB_FULL_MASK, sum, o);
+        if (lane == 0) out[u] = sum;
     }
 }

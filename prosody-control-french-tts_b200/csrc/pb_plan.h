@@ -67,6 +67,7 @@ static inline int pb_extract_part(int64_t file_nx, double sr, int has_t1, double
     const int64_t i2 = 1 + (int64_t)std::floor((t1 - x1) / dx);
     if (i2 < i1) return PB_UNIT_NO_SAMPLES;
     *ix1 = i1; *nx = i2 - i1 + 1; *x1_part = x1 + (double)(i1 - 1) * dx;
+    if (has_t1 == 2) *x1_part -= t0;      // preserve_times = false: Praat shifts the part's time axis to start at 0
     return PB_UNIT_OK;
 }
 
@@ -89,15 +90,14 @@ static inline void pb_plan_pitch_unit(int64_t file_nx, double sr, int has_t1, do
 // ---- pydub
 static inline int64_t pb_pydub_len_ms(int64_t n_frames, double rate) { return (int64_t)std::nearbyint(1000.0 * ((double)n_frames / rate)); }
 
-// audio[int(t0*1000):int(t1*1000)] -> real samples [a, b) followed by npad zeros. Returns 0 or PB_UNIT_SLICE_ERROR.
-static inline int pb_pydub_slice(int64_t n_frames, double rate, double t0, double t1, int64_t* a, int64_t* b, int64_t* npad) {
-    const int64_t L = pb_pydub_len_ms(n_frames, rate);
-    int64_t s_ms = (int64_t)(t0 * 1000.0), e_ms = (int64_t)(t1 * 1000.0);
+// audio[s_ms:e_ms] -> real samples [a, b) followed by npad zeros, with the millisecond positions as pydub receives them (ints on the step's path, floats on the legacy one)
+static inline int pb_pydub_slice_ms(int64_t n_frames, double rate, double s_ms, double e_ms, int64_t* a, int64_t* b, int64_t* npad) {
+    const double L = (double)pb_pydub_len_ms(n_frames, rate);
     *a = *b = *npad = 0;
-    if (s_ms < 0 || e_ms < 0) return PB_UNIT_SLICE_ERROR;          // outside the reference's usage
+    if (!(s_ms >= 0.0) || !(e_ms >= 0.0)) return PB_UNIT_SLICE_ERROR;   // outside the reference's usage
     if (s_ms > L) s_ms = L; if (e_ms > L) e_ms = L;
     const double per_ms = rate / 1000.0;
-    const int64_t sf = (int64_t)((double)s_ms * per_ms), ef = (int64_t)((double)e_ms * per_ms);
+    const int64_t sf = (int64_t)(s_ms * per_ms), ef = (int64_t)(e_ms * per_ms);
     const int64_t aa = sf < n_frames ? sf : n_frames;
     int64_t bb = ef < n_frames ? ef : n_frames; if (bb < aa) bb = aa;
     const int64_t expected = ef > sf ? ef - sf : 0;
@@ -108,6 +108,11 @@ static inline int pb_pydub_slice(int64_t n_frames, double rate, double t0, doubl
         *npad = (bb - aa) > 0 ? missing : 0;                        // silence is cloned from the first frame: none if empty
     }
     return PB_UNIT_OK;
+}
+
+// audio[int(t0*1000):int(t1*1000)] -> real samples [a, b) followed by npad zeros. Returns 0 or PB_UNIT_SLICE_ERROR.
+static inline int pb_pydub_slice(int64_t n_frames, double rate, double t0, double t1, int64_t* a, int64_t* b, int64_t* npad) {
+    return pb_pydub_slice_ms(n_frames, rate, (double)(int64_t)(t0 * 1000.0), (double)(int64_t)(t1 * 1000.0), a, b, npad);
 }
 
 static inline double pb_part_duration(int64_t n_frames, double rate, int has_t1, double t0, double t1, int* status) {

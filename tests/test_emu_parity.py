@@ -44,3 +44,43 @@ def test_emulated_lufs_kernels_match_oracle(emu, oracle):
         ref = oracle.lufs(x, it[2], it[5], it[3], it[4])
         assert abs(out[k] - ref) < 1e-9
     assert st[2] & 16
+
+
+def test_emulated_intensity_matches_oracle(emu, oracle):
+    import prosody_b200 as pb
+    a = speechlike(1, 0.5, 16000, seed=5)[0]
+    b = speechlike(1, 0.3, 8000, seed=6)[0]
+    short = speechlike(1, 0.05, 16000, seed=7)[0]            # shorter than the 64 ms window: Praat refuses
+    pcm = np.concatenate([a, b, short])
+    units = pb.Units.from_list([(0, len(a), 16000, 0.0, None), (len(a), len(b), 8000, 0.0, None), (len(a) + len(b), len(short), 16000, 0.0, None)])
+    for subtract in (True, False):
+        r = emu.intensity(pcm, units, subtract_mean=subtract)
+        assert list(r["status"]) == [0, 0, 1]
+        for i, (x, sr) in enumerate(((a, 16000), (b, 8000))):
+            o = oracle.intensity(x, sr, subtract_mean=subtract)
+            st, nfr, t_first, dt, _ = oracle.intensity_geometry(len(x), sr)
+            lo, hi = r["frame_off"][i], r["frame_off"][i + 1]
+            assert hi - lo == len(o) == nfr and abs(r["t_first"][i] - t_first) < 1e-12 and abs(r["dt"][i] - dt) < 1e-15
+            assert np.max(np.abs(r["intensity_db"][lo:hi] - o)) < 2e-4
+
+
+def test_emulated_legacy_measurements_match_oracle(emu, oracle):
+    import prosody_b200 as pb
+    from prosody_b200 import legacy
+    sr = 16000
+    x = speechlike(1, 0.9, sr, seed=8)[0]
+    loud = (x.astype(np.int32) * 3).clip(-32768, 32767).astype(np.int16)     # squares overflow int16 almost everywhere
+    pcm = np.concatenate([x, loud])
+    n = len(x)
+    spans = [(0.0, 0.9), (0.1033, 0.5071), (0.25, 0.25), (0.3, 0.2), (0.5, 0.9004), (0.85, 5.0)]
+    units = pb.Units.from_list([(off, n, sr, s, e) for off in (0, n) for s, e in spans])
+    got = legacy.loudness_segments(emu, pcm, units)
+    for k, (off, (s, e)) in enumerate((off, se) for off in (0, n) for se in spans):
+        ref = oracle.legacy_loudness(pcm[off:off + n], sr, s, e)
+        assert (math.isnan(ref) and math.isnan(got[k])) or got[k] == ref, (k, got[k], ref)
+    spans = [(0.0, 0.9), (0.1033, 0.5071), (0.3, 0.2), (0.2, 0.95), (0.41, 0.43), (-0.1, 0.5)]
+    units = pb.Units.from_list([(0, n, sr, s, e) for s, e in spans])
+    got = legacy.pitch_segments(emu, pcm, units)
+    for k, (s, e) in enumerate(spans):
+        ref = oracle.legacy_pitch_segment(x, sr, s, e)
+        assert (ref == 0 and got[k] == 0) or abs(got[k] - ref) / ref < 5e-3, (k, got[k], ref)

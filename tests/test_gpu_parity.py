@@ -293,3 +293,54 @@ def test_step_24k_mfa_style_full_ssml(gpu_extractor, oracle):
         assert abs(float(gp) - float(wp)) <= 0.02
         same_pitch += gp == wp
     assert same_pitch >= 0.8 * len(syn_rows)          # identical except at the documented .2f rounding boundaries
+
+
+# ------------------------------------------------------------------ the "next" rows of SURVEY.md §8(f)
+def test_intensity_matches_oracle(gpu_extractor, oracle):
+    """Sound.to_intensity() as the reference's comparison plots call it (Code/visualisation/Compare_speech_noenhanced.py:19-26)."""
+    import prosody_b200 as pb
+    import torch
+    files = [(speechlike(1, d, sr, seed=200 + k)[0], sr) for k, (d, sr) in enumerate([(3.0, 16000), (1.0, 24000), (2.0, 44100), (0.05, 16000), (0.7, 8000)])]
+    pcm = np.concatenate([f for f, _ in files])
+    off = np.cumsum([0] + [len(f) for f, _ in files])
+    units = pb.Units.from_list([(int(off[i]), len(f), sr, 0.0, None) for i, (f, sr) in enumerate(files)])
+    dev = torch.from_numpy(pcm).cuda()
+    for subtract in (True, False):
+        r = gpu_extractor.intensity(pcm, units, subtract_mean=subtract)
+        r_dev = gpu_extractor.intensity(dev, units, subtract_mean=subtract)
+        assert np.array_equal(r["intensity_db"], r_dev["intensity_db"])
+        assert list(r["status"]) == [0, 0, 0, 1, 0]
+        for i, (x, sr) in enumerate(files):
+            if r["status"][i]:
+                assert r["n_frames"][i] == 0
+                continue
+            o = oracle.intensity(x, sr, subtract_mean=subtract)
+            lo, hi = r["frame_off"][i], r["frame_off"][i + 1]
+            assert hi - lo == len(o)
+            assert np.max(np.abs(r["intensity_db"][lo:hi] - o)) < 0.01          # dB; float32 output
+
+
+def test_legacy_dataframe_measurements_match_oracle(gpu_extractor, oracle):
+    """calculate_pitch_segment / _calculate_loudness of the DataFrame pipeline, one unit per syntagme row."""
+    import prosody_b200 as pb
+    from prosody_b200 import legacy
+    rng = np.random.default_rng(9)
+    sr = 16000
+    x = speechlike(8, 3.0, sr, seed=300)
+    x[1] = (x[1].astype(np.int32) * 4).clip(-32768, 32767).astype(np.int16)     # int16 squares wrap
+    x[2] = 0                                                                      # silence: -inf dB, pitch 0
+    n = x.shape[1]
+    rows = []
+    for f in range(x.shape[0]):
+        cuts = np.sort(rng.uniform(0.0, 3.0, 5))
+        for s, e in zip(cuts[:-1], cuts[1:]):
+            rows.append((f, float(s), float(e)))
+        rows += [(f, 0.0, 3.0), (f, 1.0, 1.0), (f, 2.0, 1.5), (f, 2.5, 3.2), (f, 1.2, 1.23)]
+    units = pb.Units.from_list([(f * n, n, sr, s, e) for f, s, e in rows])
+    loud = legacy.loudness_segments(gpu_extractor, x.reshape(-1), units)
+    pitch = legacy.pitch_segments(gpu_extractor, x.reshape(-1), units)
+    for k, (f, s, e) in enumerate(rows):
+        ref = oracle.legacy_loudness(x[f], sr, s, e)
+        assert (math.isnan(ref) and math.isnan(loud[k])) or loud[k] == ref, (k, loud[k], ref)      # integer sums: bit-exact
+        refp = oracle.legacy_pitch_segment(x[f], sr, s, e)
+        assert (refp == 0 and pitch[k] == 0) or abs(pitch[k] - refp) / refp < F0_TOL, (k, pitch[k], refp)
