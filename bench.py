@@ -275,6 +275,12 @@ def main():
         fp32_peak = info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12        # FFMA lanes x 2 flop x max SM clock (nominal)
         alg_bytes = 2.0 * SR * 0.01 + 8.0      # per frame: s16 in once (10 ms hop) + f32 F0 + f32 strength
         hbm_gbs = alg_bytes * frames_per_launch / (kernel_ms * 1e-3) / 1e9
+        traffic = None       # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        try:
+            tr = json.loads((ROOT / "profiles" / "r01_frames_traffic.json").read_text())
+            traffic = tr["bytes_per_frame"] * frames_per_launch
+        except Exception:
+            pass
         line = dict(
             metric=METRIC, value=value, unit="audio-s/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=1e3 * dt_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -291,7 +297,7 @@ def main():
             gpu_launches=int(acc["n_launches"]),
             kernels_ms_per_step={k: acc[k] / args.steps for k in ("unit_stats_ms", "frames_ms", "path_ms", "lufs_ms", "h2d_ms")},
             roofline=dict(bound="fp32", kernel="pb_pitch_frames_kernel<10>", achieved=achieved_tflops, peak=fp32_peak, unit="TFLOP/s",
-                          frac=achieved_tflops / fp32_peak, traffic=None,
+                          frac=achieved_tflops / fp32_peak, traffic=traffic,
                           note="non-tensor FP32 pipe: no stage is a dense contraction; peak = SMs x 128 FFMA lanes x 2 x max SM clock "
                                "(nominal; MEASURED_PEAKS.json has no FP32 figure). achieved = the REFERENCE algorithm's flops per frame "
                                f"({fpf:.0f}, oracle-counted on this input) x frames per launch / CUDA-event kernel time",

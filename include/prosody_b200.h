@@ -154,9 +154,11 @@ int pb_intensity_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm
 /* The legacy loudness of Code/Pipeline/compute_pitch_adjustments.py:157-164 (_calculate_loudness), batched:
  * 20*log10(sqrt(|mean(samples**2)|)) over audio[start*1000:end*1000] (pydub FLOAT-millisecond slice; t0/t1 carry
  * start/end in seconds), with numpy's int16 wrap-around of samples**2 reproduced bit for bit.  An empty slice
- * yields NaN and a silent one -inf, as numpy does. */
+ * yields NaN and a silent one -inf, as numpy does.  sum_sq / count (optional, may be NULL) receive the exact
+ * integer sum of the wrapped squares and the mean's denominator, for hosts that must finish the formula with
+ * their own log10 (numpy's differs from libm's in the last bit). */
 int pb_legacy_loudness_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
-                             const PbUnits* u, double* loudness_db);
+                             const PbUnits* u, double* loudness_db, int64_t* sum_sq, int64_t* count);
 
 /* ---- host-side arithmetic of the step (float64, same libm calls and operation order as the reference's Python) */
 

@@ -70,7 +70,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.pb_extract_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, P, u8p, u8p, dp, i32p, i32p, dp, dp, i32p]
     lib.pb_intensity_plan.argtypes = [U, C.c_double, C.c_double, i32p, i32p, i64p, dp, dp]
     lib.pb_intensity_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, C.c_double, C.c_double, C.c_int, fp, i32p]
-    lib.pb_legacy_loudness_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, dp]
+    lib.pb_legacy_loudness_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, dp, i64p, i64p]
     lib.pb_syntagme_deltas.argtypes = [C.c_int64, dp, dp, dp, dp, i32p, dp, dp, i32p, C.POINTER(PbDeltaParams), dp, dp, dp]
     lib.pb_ema_clamp.argtypes = [dp, C.c_int64, C.c_double, C.c_double, dp]
     for name in EXPORTS:

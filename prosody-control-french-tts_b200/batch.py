@@ -217,12 +217,17 @@ class Extractor:
     def legacy_loudness(self, pcm, units: Units) -> np.ndarray:
         """_calculate_loudness(path, start, end) of the legacy DataFrame pipeline for every unit (t0/t1 = start/end seconds)."""
         addr, n_samp, on_dev, keep = _pcm_pointer(pcm)
-        out = np.zeros(len(units))
+        out = np.zeros(len(units)); sums = np.zeros(len(units), np.int64); cnt = np.zeros(len(units), np.int64)
         cu = units.c_struct()
-        rc = self._lib.pb_legacy_loudness_batch(self._h, C.c_void_p(addr), n_samp, on_dev, C.byref(cu), _ptr(out, C.c_double))
+        rc = self._lib.pb_legacy_loudness_batch(self._h, C.c_void_p(addr), n_samp, on_dev, C.byref(cu), _ptr(out, C.c_double),
+                                                _ptr(sums, C.c_int64), _ptr(cnt, C.c_int64))
         N.check(self._lib, self._h, rc, "pb_legacy_loudness_batch")
         del keep
-        return out
+        # the reference finishes with numpy (np.mean -> np.sqrt -> np.log10); do the same on the exact integer sums so
+        # the last bit matches numpy's log10 rather than libm's
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mean = np.where(cnt > 0, sums.astype(np.float64) / np.maximum(cnt, 1), np.nan)
+            return 20 * np.log10(np.sqrt(np.abs(mean)))
 
 
 def intensity_plan(units: Units, minimum_pitch: float = 100.0, time_step: float = 0.0, lib=None):
