@@ -160,6 +160,18 @@ int pb_intensity_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm
 int pb_legacy_loudness_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
                              const PbUnits* u, double* loudness_db, int64_t* sum_sq, int64_t* count);
 
+/* pydub.silence.split_on_silence(audio, min_silence_len, silence_thresh, keep_silence), seek_step 1, batched over
+ * whole mono files (Code/Preprocessing/preprocess_audio.py:41-46; config.yaml silence: 1000 ms / -50 dBFS / 300 ms).
+ * keep_silence_ms < 0 means keep_silence=True (keep everything).  File f yields segments
+ * [seg_off[f], seg_off[f+1]): the [start_ms, end_ms) of the final audio[start:end] slices, and (optional outputs)
+ * the sample range first/n_samples inside the file plus the n_pad zeros pydub appends when the last millisecond
+ * overshoots the data.  capacity = entries in the seg_* arrays, at least pb_split_on_silence_bound(). */
+int64_t pb_split_on_silence_bound(const PbUnits* files, int min_silence_len_ms);
+int pb_split_on_silence_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device, const PbUnits* files,
+                              int min_silence_len_ms, double silence_thresh_db, int keep_silence_ms, int64_t capacity,
+                              int64_t* seg_off, int32_t* seg_start_ms, int32_t* seg_end_ms,
+                              int64_t* seg_first_sample, int32_t* seg_n_samples, int32_t* seg_n_pad);
+
 /* ---- host-side arithmetic of the step (float64, same libm calls and operation order as the reference's Python) */
 
 /* prosody settings read by the step (Code/audioPipeline.py:127-139, config.yaml prosody_settings) */

@@ -371,3 +371,109 @@ def legacy_pitch_segment(pcm: np.ndarray, sr: float, start: float, end: float) -
         if len(v):
             return statistics.geometric_mean(v)
     return 0
+
+
+# ------------------------------------------------------------------ pydub.silence (pydub 0.25.1 silence.py), mono s16
+def _audioop_rms(seg: np.ndarray) -> int:
+    """audioop.rms: ``(unsigned int) sqrt(sum_squares / n)`` with the sum accumulated in a C double (exact here)."""
+    if len(seg) == 0:
+        return 0
+    s = int(np.sum(seg.astype(np.int64) ** 2))
+    return int(math.sqrt(float(s) / float(len(seg))))
+
+
+def _pydub_slice_samples(pcm: np.ndarray, rate: int, s_ms, e_ms) -> np.ndarray:
+    """AudioSegment.__getitem__(slice) on mono s16 data: clip to len(), int(ms * rate/1000) frames, pad < 2 ms of zeros."""
+    n = len(pcm)
+    L = pydub_len_ms(n, rate)
+    s_ms, e_ms = min(s_ms, L), min(e_ms, L)
+    per_ms = rate / 1000.0
+    sf, ef = int(s_ms * per_ms), int(e_ms * per_ms)
+    a = min(sf, n); b = max(a, min(ef, n))
+    seg = np.asarray(pcm[a:b], np.int16)
+    missing = max(ef - sf, 0) - (b - a)
+    if missing:
+        if missing > 2 * per_ms:
+            raise ValueError("TooManyMissingFrames")
+        if len(seg):
+            seg = np.concatenate([seg, np.zeros(missing, np.int16)])
+    return seg
+
+
+def detect_silence(pcm: np.ndarray, rate: int, min_silence_len=1000, silence_thresh=-16, seek_step=1, naive=False):
+    """≙ pydub.silence.detect_silence.  naive=True slices and squares every window like pydub does (small inputs only);
+    otherwise window sums come from an exact int64 prefix sum (same integers, so the same decisions)."""
+    n = len(pcm)
+    seg_len = pydub_len_ms(n, rate)
+    if seg_len < min_silence_len:
+        return []
+    thresh = (10 ** (silence_thresh / 20.0)) * 32768          # db_to_float(silence_thresh) * max_possible_amplitude
+    last_slice_start = seg_len - min_silence_len
+    starts = list(range(0, last_slice_start + 1, seek_step))
+    if last_slice_start % seek_step:
+        starts.append(last_slice_start)
+    per_ms = rate / 1000.0
+    if not naive:
+        P = np.concatenate([[0], np.cumsum(np.asarray(pcm, np.int64) ** 2)])
+    silence_starts = []
+    for i in starts:
+        if naive:
+            rms = _audioop_rms(_pydub_slice_samples(pcm, rate, i, i + min_silence_len))
+        else:
+            sf, ef = int(i * per_ms), int(min(i + min_silence_len, seg_len) * per_ms)
+            a = min(sf, n); b = max(a, min(ef, n))
+            cnt = (ef - sf) if b > a else 0
+            rms = int(math.sqrt(float(int(P[b] - P[a])) / float(cnt))) if cnt else 0
+        if rms <= thresh:
+            silence_starts.append(i)
+    if not silence_starts:
+        return []
+    silent_ranges = []
+    prev_i = silence_starts.pop(0)
+    current_range_start = prev_i
+    for silence_start_i in silence_starts:
+        continuous = (silence_start_i == prev_i + seek_step)
+        silence_has_gap = silence_start_i > (prev_i + min_silence_len)
+        if not continuous and silence_has_gap:
+            silent_ranges.append([current_range_start, prev_i + min_silence_len])
+            current_range_start = silence_start_i
+        prev_i = silence_start_i
+    silent_ranges.append([current_range_start, prev_i + min_silence_len])
+    return silent_ranges
+
+
+def detect_nonsilent(pcm, rate, min_silence_len=1000, silence_thresh=-16, seek_step=1, naive=False):
+    """≙ pydub.silence.detect_nonsilent."""
+    silent_ranges = detect_silence(pcm, rate, min_silence_len, silence_thresh, seek_step, naive)
+    len_seg = pydub_len_ms(len(pcm), rate)
+    if not silent_ranges:
+        return [[0, len_seg]]
+    if silent_ranges[0][0] == 0 and silent_ranges[0][1] == len_seg:
+        return []
+    prev_end_i = 0
+    nonsilent_ranges = []
+    for start_i, end_i in silent_ranges:
+        nonsilent_ranges.append([prev_end_i, start_i])
+        prev_end_i = end_i
+    if end_i != len_seg:
+        nonsilent_ranges.append([prev_end_i, len_seg])
+    if nonsilent_ranges[0] == [0, 0]:
+        nonsilent_ranges.pop(0)
+    return nonsilent_ranges
+
+
+def split_on_silence(pcm, rate, min_silence_len=1000, silence_thresh=-16, keep_silence=100, seek_step=1, naive=False):
+    """≙ pydub.silence.split_on_silence (Code/Preprocessing/preprocess_audio.py:41-46 calls it with 1000 ms / -50 dBFS / 300 ms).
+    Returns the [start_ms, end_ms) ranges that the final ``audio_segment[max(start,0):min(end,len)]`` slices use."""
+    len_seg = pydub_len_ms(len(pcm), rate)
+    if isinstance(keep_silence, bool):
+        keep_silence = len_seg if keep_silence else 0
+    output_ranges = [[s - keep_silence, e + keep_silence]
+                     for s, e in detect_nonsilent(pcm, rate, min_silence_len, silence_thresh, seek_step, naive)]
+    for k in range(len(output_ranges) - 1):
+        range_i, range_ii = output_ranges[k], output_ranges[k + 1]
+        last_end, next_start = range_i[1], range_ii[0]
+        if next_start < last_end:
+            range_i[1] = (last_end + next_start) // 2
+            range_ii[0] = range_i[1]
+    return [(max(s, 0), min(e, len_seg)) for s, e in output_ranges]

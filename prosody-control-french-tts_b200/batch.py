@@ -230,6 +230,27 @@ class Extractor:
             return 20 * np.log10(np.sqrt(np.abs(mean)))
 
 
+    def split_on_silence(self, pcm, units: Units, min_silence_len: int = 1000, silence_thresh: float = -16, keep_silence=100) -> dict:
+        """pydub.silence.split_on_silence for every (whole, mono) file of the batch; defaults are pydub's.
+        Returns seg_off (n+1), start_ms / end_ms of every segment and its sample range (first, n_samples, n_pad) in the file."""
+        addr, n_samp, on_dev, keep = _pcm_pointer(pcm)
+        n = len(units)
+        keep_ms = (-1 if keep_silence else 0) if isinstance(keep_silence, bool) else int(keep_silence)
+        cu = units.c_struct()
+        cap = int(self._lib.pb_split_on_silence_bound(C.byref(cu), int(min_silence_len)))
+        if cap < 0:
+            raise ValueError("min_silence_len must be >= 1 ms")
+        so = np.zeros(n + 1, np.int64); s_ms = np.zeros(cap, np.int32); e_ms = np.zeros(cap, np.int32)
+        first = np.zeros(cap, np.int64); ns = np.zeros(cap, np.int32); npad = np.zeros(cap, np.int32)
+        rc = self._lib.pb_split_on_silence_batch(self._h, C.c_void_p(addr), n_samp, on_dev, C.byref(cu), int(min_silence_len),
+                                                 float(silence_thresh), keep_ms, cap, _ptr(so, C.c_int64), _ptr(s_ms, C.c_int32),
+                                                 _ptr(e_ms, C.c_int32), _ptr(first, C.c_int64), _ptr(ns, C.c_int32), _ptr(npad, C.c_int32))
+        N.check(self._lib, self._h, rc, "pb_split_on_silence_batch")
+        del keep
+        m = int(so[-1])
+        return dict(seg_off=so, start_ms=s_ms[:m], end_ms=e_ms[:m], first_sample=first[:m], n_samples=ns[:m], n_pad=npad[:m])
+
+
 def intensity_plan(units: Units, minimum_pitch: float = 100.0, time_step: float = 0.0, lib=None):
     """Host-only: (status, n_frames, frame_off, t_first, dt) of Praat's Sound_to_Intensity per whole-file unit."""
     lib = lib if lib is not None else N.load()

@@ -13,6 +13,7 @@
 #include "pb_pitch_frames.cuh"
 #include "pb_pitch_path.cuh"
 #include "pb_lufs.cuh"
+#include "pb_silence.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -122,6 +123,7 @@ struct PbHandle {
     std::map<int, size_t> occ_last;                        // LOG2N -> footprint the function attributes were last set for
     BatchPlan plan;                                        // host plan of the call in progress (scratch reused across calls)
     int64_t cur_pcm_len = 0;                               // samples in the pcm buffer of the call in progress
+    size_t sil_smem = 0; int sil_per_sm = 2;               // K5: footprint its function attribute was set for, resident CTAs per SM
 };
 
 namespace {
@@ -763,5 +765,6 @@ int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_o
 
 #include "pb_api_host.inc"
 #include "pb_api_next.inc"
+#include "pb_api_silence.inc"
 
 }  // extern "C"

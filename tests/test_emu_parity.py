@@ -84,3 +84,37 @@ def test_emulated_legacy_measurements_match_oracle(emu, oracle):
     for k, (s, e) in enumerate(spans):
         ref = oracle.legacy_pitch_segment(x, sr, s, e)
         assert (ref == 0 and got[k] == 0) or abs(got[k] - ref) / ref < 5e-3, (k, got[k], ref)
+
+
+def _gappy(sr, dur, gaps, seed, level=3000, floor=60):
+    rng = np.random.default_rng(seed)
+    n = int(sr * dur) + 7
+    x = rng.normal(0, level, n).clip(-32768, 32767).astype(np.int16)
+    for a, b in gaps:
+        i, j = int(a * sr), min(int(b * sr), n)
+        x[i:j] = rng.normal(0, floor, j - i).astype(np.int16)
+    return x
+
+
+def test_emulated_silence_split_matches_oracle(emu, oracle):
+    import prosody_b200 as pb
+    files = [(_gappy(8000, 2.3, ((0.0, 0.25), (0.6, 0.95), (1.3, 1.42), (1.9, 2.4)), 0), 8000),
+             (_gappy(22050, 1.7, ((0.3, 0.62), (0.9, 1.25)), 1), 22050),
+             (_gappy(16000, 0.15, (), 2), 16000),                              # shorter than the window: one segment
+             (np.zeros(16000, np.int16), 16000),                              # all silent: no segment
+             (_gappy(16000, 1.0, ((0.0, 0.4), (0.7, 1.1)), 3), 16000)]          # silent at both ends
+    pcm = np.concatenate([f for f, _ in files])
+    off = np.cumsum([0] + [len(f) for f, _ in files])
+    units = pb.Units.from_list([(int(off[i]), len(f), sr, 0.0, None) for i, (f, sr) in enumerate(files)])
+    for W, th, keep in ((200, -50, 30), (100, -45, 300), (300, -50, True), (250, -50, False)):
+        r = emu.split_on_silence(pcm, units, W, th, keep)
+        for i, (x, sr) in enumerate(files):
+            ref = oracle.split_on_silence(x, sr, W, th, keep)
+            lo, hi = r["seg_off"][i], r["seg_off"][i + 1]
+            got = list(zip(r["start_ms"][lo:hi].tolist(), r["end_ms"][lo:hi].tolist()))
+            assert got == ref, (W, th, keep, i, got, ref)
+            for k, (s, e) in enumerate(ref):
+                seg = oracle._pydub_slice_samples(x, sr, s, e)
+                assert r["n_samples"][lo + k] + r["n_pad"][lo + k] == len(seg)
+                a = r["first_sample"][lo + k]
+                assert np.array_equal(x[a:a + r["n_samples"][lo + k]], seg[:r["n_samples"][lo + k]])

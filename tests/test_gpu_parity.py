@@ -344,3 +344,51 @@ def test_legacy_dataframe_measurements_match_oracle(gpu_extractor, oracle):
         assert (math.isnan(ref) and math.isnan(loud[k])) or loud[k] == ref, (k, loud[k], ref)      # integer sums: bit-exact
         refp = oracle.legacy_pitch_segment(x[f], sr, s, e)
         assert (refp == 0 and pitch[k] == 0) or abs(pitch[k] - refp) / refp < F0_TOL, (k, pitch[k], refp)
+
+
+def _gappy(sr, dur, gaps, seed, level=3000, floor=60):
+    rng = np.random.default_rng(seed)
+    n = int(sr * dur) + 7
+    x = rng.normal(0, level, n).clip(-32768, 32767).astype(np.int16)
+    for a, b in gaps:
+        i, j = int(a * sr), min(int(b * sr), n)
+        x[i:j] = rng.normal(0, floor, j - i).astype(np.int16)
+    return x
+
+
+def test_split_on_silence_matches_oracle(gpu_extractor, oracle):
+    """pydub.split_on_silence as Code/Preprocessing/preprocess_audio.py:41-46 calls it (1000 ms, -50 dBFS, keep 300), plus
+    other parameters; files long enough to span several CTA tiles with silences across the tile seams."""
+    import prosody_b200 as pb
+    import torch
+    rng = np.random.default_rng(11)
+    files = []
+    for k, (sr, dur) in enumerate([(22050, 61.0), (16000, 33.0), (8000, 20.0), (44100, 9.0), (24000, 0.7), (16000, 2.0)]):
+        t = np.sort(rng.uniform(0, dur, 14)).reshape(-1, 2)
+        gaps = [(a, max(b, a + rng.uniform(0.2, 2.5))) for a, b in t]
+        gaps += [(7.0, 8.3), (14.2, 15.9)]                                  # across the 7168-window tile seams at W = 1000
+        files.append((_gappy(sr, dur, [(a, min(b, dur)) for a, b in gaps if a < dur], 40 + k), sr))
+    files.append((np.zeros(48000, np.int16), 16000))
+    files[5] = (_gappy(16000, 2.0, (), 46, level=104, floor=104), 16000)     # rms riding the -50 dBFS threshold (103.6)
+    pcm = np.concatenate([f for f, _ in files])
+    off = np.cumsum([0] + [len(f) for f, _ in files])
+    units = pb.Units.from_list([(int(off[i]), len(f), sr, 0.0, None) for i, (f, sr) in enumerate(files)])
+    dev = torch.from_numpy(pcm).cuda()
+    for W, th, keep in ((1000, -50, 300), (500, -50, 100), (1000, -45, True), (2000, -50, 0), (3, -50, 2), (1, -50, 0)):
+        r = gpu_extractor.split_on_silence(dev, units, W, th, keep)
+        r_host = gpu_extractor.split_on_silence(pcm[1:], pb.Units(units.file_off[1:] - 1, units.file_nx[1:], units.rate[1:], units.has_t1[1:],
+                                                                    units.t0[1:], units.t1[1:]), W, th, keep)   # host PCM, odd alignment
+        n_seg = 0
+        for i, (x, sr) in enumerate(files):
+            ref = oracle.split_on_silence(x, sr, W, th, keep)
+            lo, hi = r["seg_off"][i], r["seg_off"][i + 1]
+            got = list(zip(r["start_ms"][lo:hi].tolist(), r["end_ms"][lo:hi].tolist()))
+            assert got == ref, (W, th, keep, i, got[:6], ref[:6])
+            n_seg += len(ref)
+            if i >= 1:
+                lo2, hi2 = r_host["seg_off"][i - 1], r_host["seg_off"][i]
+                assert list(zip(r_host["start_ms"][lo2:hi2].tolist(), r_host["end_ms"][lo2:hi2].tolist())) == ref
+            for k, (s, e) in enumerate(ref[:50]):
+                seg = oracle._pydub_slice_samples(x, sr, s, e)
+                assert r["n_samples"][lo + k] + r["n_pad"][lo + k] == len(seg)
+        assert n_seg == r["seg_off"][-1]
