@@ -440,13 +440,13 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
                     const int sh = pass ? LR : 5;
                     PB_UNROLL for (int t = 0; t < R; t++) { const int i = g + t * (N / R); v[t] = buf[i + (i >> sh)]; }
                 }
-                if (step == 0) { PB_UNROLL for (int t = 0; t < R; t++) { v[t].x *= sA; v[t].y *= sB; } }
+                if (step == 0) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
                 if (pass) {
                     const int k = g & (R - 1);
                     PB_UNROLL for (int t = 1; t < R; t++) {
                         const float2 w = __ldg(&gm.tw_a[t * R + k]);
                         const float2 x = v[t];
-                        v[t] = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+                        v[t] = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(x.x, x.x), w));   // x * w
                     }
                 }
                 pb_group_sync<G>(bar_id);               // every load of this step is done before any store

@@ -30,12 +30,22 @@ struct PbSilFileDev {
 #define PB_SIL_WARPS 16
 #define PB_SIL_PADW(w) ((w) + ((w) >> 5))       // one pad word per 32: lane-strided bin reads stay (nearly) conflict-free
 
-// pydub frame_count(ms) = ms * (frame_rate / 1000.0), truncated by int()
-__device__ __forceinline__ long long pb_sil_frame(int ms, double per_ms) { return (long long)__dmul_rn((double)ms, per_ms); }
+// pydub frame_count(ms) = ms * (frame_rate / 1000.0), truncated by int(); files are < 2^31 - 2^16 samples (host check)
+#define PB_SIL_NV 6     // 16-byte vectors one lane keeps in flight per 32-bin group: 32 * 6 * 8 samples, i.e. rates up to 48 kHz
+
+__device__ __forceinline__ int pb_sil_frame32(int ms, double per_ms) { return __double2int_rz(__dmul_rn((double)ms, per_ms)); }
+
+__device__ __forceinline__ int4 pb_sil_load_vec(const int16_t* __restrict__ pcm, const int4* __restrict__ pal, long long mis, long long pcm_len, long long v) {
+    const long long s0 = (v << 3) - mis;
+    if (s0 >= 0 && s0 + 8 <= pcm_len) return pal[v];
+    int x[8];                                                   // first / last vector of a buffer that is not 16-byte aligned
+    PB_UNROLL for (int k = 0; k < 8; k++) x[k] = (s0 + k >= 0 && s0 + k < pcm_len) ? (int)pcm[s0 + k] & 0xffff : 0;
+    return make_int4(x[0] | (x[1] << 16), x[2] | (x[3] << 16), x[4] | (x[5] << 16), x[6] | (x[7] << 16));
+}
 
 // tile_windows: window starts per CTA tile; the tile needs tile_windows + win_ms + 1 bins (+1 window of halo each side).
 // smem layout: u64 bins[nb_cap + 1] | u64 warp_tot[PB_SIL_WARPS] | u8 flags[tile_windows + 2] | u32 stage[PB_SIL_WARPS][words_per_warp]
-__global__ void __launch_bounds__(PB_SIL_WARPS * 32)
+__global__ void __launch_bounds__(PB_SIL_WARPS * 32, 2)
 pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const PbSilFileDev* __restrict__ files, int n_files,
                        long long n_tiles, int tile_windows, int win_ms, int nb_cap, int words_per_warp, long long limit_per_sample,
                        unsigned long long* __restrict__ run_keys, unsigned long long run_cap, unsigned long long* __restrict__ run_count) {
@@ -58,51 +68,83 @@ pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const
         const int base = max(j0 - 1, 0);                                      // first bin (one window of halo to the left)
         const int wend = min(j0 + jn + 1, F.n_win);                           // one past the last window whose flag we need
         const int nb = (wend - 1 + win_ms) - base;                            // bins [base, base + nb)
-        // ---- 1. per-millisecond energies: each warp stages the samples of 32 consecutive bins, each lane sums one bin
-        for (int g = warp; g * 32 < nb; g += PB_SIL_WARPS) {
-            const int i = base + g * 32 + lane;
-            const int ic = min(i, base + nb), ie = min(i + 1, base + nb);
-            long long a = pb_sil_frame(ic, F.per_ms), b = pb_sil_frame(ie, F.per_ms);
-            a = a < F.nx ? a : F.nx; b = b < F.nx ? b : F.nx;
-            const long long A = __shfl_sync(PB_FULL_MASK, a, 0);
-            long long B = pb_sil_frame(min(base + g * 32 + 32, base + nb), F.per_ms);
-            B = B < F.nx ? B : F.nx;
-            const long long gA = F.pcm_off + A + mis, gB = F.pcm_off + B + mis; // sample positions counted from the aligned base
-            const long long v0 = gA >> 3, v1 = (gB + 7) >> 3;
-            for (long long v = v0 + lane; v < v1; v += 32) {
-                const long long s0 = (v << 3) - mis;
-                int4 q;
-                if (s0 >= 0 && s0 + 8 <= pcm_len) q = pal[v];
-                else {
-                    int x[8];
-                    PB_UNROLL for (int k = 0; k < 8; k++) x[k] = (s0 + k >= 0 && s0 + k < pcm_len) ? (int)pcm[s0 + k] & 0xffff : 0;
-                    q.x = x[0] | (x[1] << 16); q.y = x[2] | (x[3] << 16); q.z = x[4] | (x[5] << 16); q.w = x[6] | (x[7] << 16);
+        // ---- 1. per-millisecond energies: each warp stages the samples of 32 consecutive bins, each lane sums one bin.
+        // The 16-byte loads of the warp's NEXT group are issued before the current group is summed (registers q).
+        {
+            // frames [a, b) of this lane's bin, first vector and vector count of the group
+            auto geom = [&](int gg, int& ga, int& gb, long long& gv0, int& gnvec) {
+                const int i0 = base + gg * 32, iend = min(i0 + 32, base + nb);
+                const int fa = min(pb_sil_frame32(min(i0 + lane, iend), F.per_ms), F.nx);
+                const int fB = min(pb_sil_frame32(iend, F.per_ms), F.nx);
+                int fb = __shfl_down_sync(PB_FULL_MASK, fa, 1);
+                if (lane == 31) fb = fB;
+                const int fA = __shfl_sync(PB_FULL_MASK, fa, 0);
+                ga = fa; gb = fb;
+                gv0 = (F.pcm_off + fA + mis) >> 3;
+                gnvec = (int)(((F.pcm_off + fB + mis + 7) >> 3) - gv0);
+            };
+            int4 q[PB_SIL_NV];
+            auto load = [&](long long gv0, int gnvec) {
+                PB_UNROLL for (int c = 0; c < PB_SIL_NV; c++) {
+                    const int vi = c * 32 + lane;
+                    if (vi < gnvec) q[c] = pb_sil_load_vec(pcm, pal, mis, pcm_len, gv0 + vi);
                 }
-                const int w = (int)(v - v0) * 4;
-                stage[PB_SIL_PADW(w)] = (uint32_t)q.x; stage[PB_SIL_PADW(w + 1)] = (uint32_t)q.y;
-                stage[PB_SIL_PADW(w + 2)] = (uint32_t)q.z; stage[PB_SIL_PADW(w + 3)] = (uint32_t)q.w;
+            };
+            int g = warp, a = 0, b = 0, nvec = 0;
+            long long v0 = 0;
+            if (g * 32 < nb) { geom(g, a, b, v0, nvec); load(v0, nvec); }
+            while (g * 32 < nb) {
+                PB_UNROLL for (int c = 0; c < PB_SIL_NV; c++) {
+                    const int vi = c * 32 + lane, w = vi * 4;
+                    if (vi < nvec) {
+                        stage[PB_SIL_PADW(w)] = (uint32_t)q[c].x; stage[PB_SIL_PADW(w + 1)] = (uint32_t)q[c].y;
+                        stage[PB_SIL_PADW(w + 2)] = (uint32_t)q[c].z; stage[PB_SIL_PADW(w + 3)] = (uint32_t)q[c].w;
+                    }
+                }
+                for (int vi = PB_SIL_NV * 32 + lane; vi < nvec; vi += 32) {   // rates above 48 kHz: the rest, unpipelined
+                    const int4 r = pb_sil_load_vec(pcm, pal, mis, pcm_len, v0 + vi);
+                    const int w = vi * 4;
+                    stage[PB_SIL_PADW(w)] = (uint32_t)r.x; stage[PB_SIL_PADW(w + 1)] = (uint32_t)r.y;
+                    stage[PB_SIL_PADW(w + 2)] = (uint32_t)r.z; stage[PB_SIL_PADW(w + 3)] = (uint32_t)r.w;
+                }
+                __syncwarp();
+                const int gn = g + PB_SIL_WARPS;
+                int an = 0, bn = 0, nvecn = 0;
+                long long v0n = 0;
+                if (gn * 32 < nb) { geom(gn, an, bn, v0n, nvecn); load(v0n, nvecn); }
+                int k = (int)(F.pcm_off + a + mis - (v0 << 3));
+                const int e = k + (b - a);
+                unsigned long long sum = 0;
+                if (k < e) {
+                    if (k & 1) { const int x = (int)stage[PB_SIL_PADW(k >> 1)] >> 16; sum = (unsigned long long)((long long)x * x); k++; }
+                    const int wl = e >> 1;
+#pragma unroll 4
+                    for (int w = k >> 1; w < wl; w++) {
+                        const uint32_t wd = stage[PB_SIL_PADW(w)];
+                        const int x0 = (int)(short)(wd & 0xffff), x1 = (int)wd >> 16;
+                        sum += (unsigned long long)((long long)x0 * x0);
+                        sum += (unsigned long long)((long long)x1 * x1);
+                    }
+                    if (e & 1) { const int x = (int)(short)(stage[PB_SIL_PADW(wl)] & 0xffff); sum += (unsigned long long)((long long)x * x); }
+                }
+                if (g * 32 + lane < nb) bins[g * 32 + lane] = sum;
+                __syncwarp();
+                g = gn; a = an; b = bn; v0 = v0n; nvec = nvecn;
             }
-            __syncwarp();
-            int k = (int)(F.pcm_off + a + mis - (v0 << 3));
-            const int e = k + (int)(b - a);
-            unsigned long long sum = 0;
-            if (k < e && (k & 1)) { const int x = (int)stage[PB_SIL_PADW(k >> 1)] >> 16; sum += (unsigned)(x * x); k++; }
-            for (; k + 1 < e; k += 2) {
-                const uint32_t wd = stage[PB_SIL_PADW(k >> 1)];
-                const int x0 = (int)(short)(wd & 0xffff), x1 = (int)wd >> 16;
-                sum += (unsigned)(x0 * x0); sum += (unsigned)(x1 * x1);
-            }
-            if (k < e) { const int x = (int)(short)(stage[PB_SIL_PADW(k >> 1)] & 0xffff); sum += (unsigned)(x * x); }
-            if (g * 32 + lane < nb) bins[g * 32 + lane] = sum;
-            __syncwarp();
         }
         if (threadIdx.x == 0) bins[nb] = 0;
         __syncthreads();
-        // ---- 2. exclusive prefix sums over bins[0 .. nb]: every warp scans one contiguous segment, 32 bins per step
-        const int seg = (((nb + 1) + PB_SIL_WARPS - 1) / PB_SIL_WARPS + 31) & ~31;
+        // ---- 2. exclusive prefix sums over bins[0 .. nb]: every warp owns one contiguous segment (total first, then scan)
         {
-            unsigned long long carry = 0;
+            const int seg = (((nb + 1) + PB_SIL_WARPS - 1) / PB_SIL_WARPS + 31) & ~31;
             const int s_lo = warp * seg, s_hi = min(s_lo + seg, nb + 1);
+            unsigned long long tot = 0;
+            for (int k = s_lo + lane; k < s_hi; k += 32) tot += bins[k];
+            PB_UNROLL for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(PB_FULL_MASK, tot, o);
+            if (lane == 0) warp_tot[warp] = tot;
+            __syncthreads();
+            unsigned long long carry = 0;
+            for (int w = 0; w < warp; w++) carry += warp_tot[w];
             for (int k0 = s_lo; k0 < s_hi; k0 += 32) {
                 const int k = k0 + lane;
                 const unsigned long long v = k < s_hi ? bins[k] : 0;
@@ -111,19 +153,15 @@ pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const
                 if (k < s_hi) bins[k] = carry + inc - v;
                 carry += __shfl_sync(PB_FULL_MASK, inc, 31);
             }
-            if (lane == 0) warp_tot[warp] = carry;
         }
         __syncthreads();
         // ---- 3. one flag per window start j in [base .. wend): silent <=> S < limit * n  (or an empty slice: rms 0)
         for (int k = threadIdx.x; k < wend - base; k += blockDim.x) {
             const int j = base + k;
-            unsigned long long off_a = 0, off_b = 0;
-            const int sa = k / seg, sb = (k + win_ms) / seg;
-            for (int w = 0; w < PB_SIL_WARPS; w++) { const unsigned long long wt = warp_tot[w]; if (w < sa) off_a += wt; if (w < sb) off_b += wt; }
-            const unsigned long long S = (bins[k + win_ms] + off_b) - (bins[k] + off_a);
-            const long long sf = pb_sil_frame(j, F.per_ms), ef = pb_sil_frame(j + win_ms, F.per_ms);
-            const long long real = (ef < F.nx ? ef : F.nx) - (sf < F.nx ? sf : F.nx);
-            const long long cnt = real > 0 ? ef - sf : 0;
+            const unsigned long long S = bins[k + win_ms] - bins[k];
+            const int sf = pb_sil_frame32(j, F.per_ms), ef = pb_sil_frame32(j + win_ms, F.per_ms);
+            const int real = min(ef, F.nx) - min(sf, F.nx);
+            const long long cnt = real > 0 ? (long long)(ef - sf) : 0;
             flags[k + 1 - (j0 - base)] = (cnt == 0 || (long long)S < limit_per_sample * cnt) ? 1 : 0;   // flags[0] <-> window j0 - 1
         }
         if (threadIdx.x == 0) {

@@ -43,6 +43,10 @@ struct int4 { int x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
 struct double2 { double x, y; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+// sm_100 packed-pair arithmetic (FADD2 / FMUL2 / FFMA2)
+static inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{__builtin_fmaf(a.x, b.x, c.x), __builtin_fmaf(a.y, b.y, c.y)}; }
 static inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
 
 namespace pb_emu {
@@ -205,6 +209,7 @@ static inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); retur
 static inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }
 static inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline int __float2int_rd(float f) { return (int)floorf(f); }
+static inline int __double2int_rz(double d) { return (int)d; }
 static inline long long __double2ll_rd(double d) { return (long long)floor(d); }
 static inline long long __double2ll_ru(double d) { return (long long)ceil(d); }
 using std::max;
