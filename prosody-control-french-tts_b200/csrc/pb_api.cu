@@ -438,6 +438,7 @@ int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p
         gm.max_cand = pc.g.max_cand; gm.n_units = (int)m; gm.n_pairs = (int)pairs;
         // a maximum at lag i refines to a lag <= i+1: below this lag its frequency stays above the ceiling (never voiced)
         gm.min_refine_lag = (int)std::floor(1.0 / pc.g.dx / pc.g.ceiling) - 1;
+        { const char* e = getenv("PB_PHASE_SYNC"); gm.phase_sync = e ? atoi(e) : 1; }
         {
             // staging buffer of the sample prefetch: the frame samples a pair reads (window and local-mean span of frame A,
             // the same shifted by one hop for frame B) plus up to 7 samples of 16-byte alignment slack on each side

@@ -17,6 +17,9 @@
 #include "pb_stream.cuh"
 #include <math.h>
 
+#ifndef PB_WPC
+#define PB_WPC 4            // warps per CTA of the frames kernel (when one group needs fewer)
+#endif
 #define PB_MAXC 32           // hard cap on candidates per frame (Praat default 15)
 #define PB_PI_F 3.14159265358979323846f
 
@@ -47,7 +50,7 @@ struct PbPitchGeomDev {
     int n_pairs;
     int min_refine_lag;   // maxima at smaller lags stay above the ceiling whatever the refinement: never voiced
     int pre_cap;          // samples per staging buffer of the cp.async prefetch (multiple of 8)
-    int pad1;
+    int phase_sync;          // 1: the CTA's warps start every work item together (instruction-cache locality)
     long long pcm_len;    // samples in the pcm buffer (prefetch copies stay inside it)
     float sr;             // 1/dx
     float half_voicing;   // 0.5 * voicingThreshold
@@ -159,11 +162,11 @@ template <int LOG2N> struct PbFftCfg {
     static constexpr int G = (N / R) / 32;                // warps per group
     static constexpr int GT = 32 * G;                     // threads per group
     static constexpr int BUF = N + (N >> LR) + 8;         // float2 slots per group: N plus the skew padding (index >> LR)
-    static constexpr int WARPS_PER_CTA = G >= 4 ? G : 4;
+    static constexpr int WARPS_PER_CTA = G >= PB_WPC ? G : PB_WPC;
     static constexpr int GROUPS_PER_CTA = WARPS_PER_CTA / G;
     static constexpr int FB = F > 1 ? (N / F) / GT : 0;   // final-pass butterflies per thread
     static constexpr int RPL = (N / 3 + 2 + GT - 1) / GT + 1;   // lags per thread when extracting r
-    static constexpr int MIN_CTAS = LOG2N <= 10 ? 4 : 2;  // occupancy target for __launch_bounds__
+    static constexpr int MIN_CTAS = (LOG2N <= 10 ? 16 : 8) / WARPS_PER_CTA > 0 ? (LOG2N <= 10 ? 16 : 8) / WARPS_PER_CTA : 1;  // occupancy target
 };
 
 template <int G> __device__ __forceinline__ void pb_group_sync(int bar_id) {

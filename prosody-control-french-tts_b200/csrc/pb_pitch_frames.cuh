@@ -295,7 +295,7 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = warp / G, wg = warp % G;          // group in CTA, warp in group
     const int g = wg * 32 + lane;                       // thread in group = butterfly index
-    const int bar_id = 1 + group;
+    const int bar_id = 1 + (G == 1 ? (group & 7) : group);   // one-warp groups may share an id: every arrival completes the barrier
     // per-group shared memory: FFT buffer, a small reduction scratch, two sample staging buffers
     const size_t group_bytes = (size_t)(C::BUF + 8 * G) * sizeof(float2) + 2 * (size_t)gm.pre_cap * sizeof(int16_t);
     unsigned char* gbase = smem_raw + (size_t)group * group_bytes;
@@ -320,13 +320,29 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
     const int per_group = (gm.n_pairs + n_groups - 1) / n_groups;
     const int item_begin = (blockIdx.x * C::GROUPS_PER_CTA + group) * per_group;
     const int item_end = min(gm.n_pairs, item_begin + per_group);
-    if (item_begin >= item_end) return;
-    int u_next = pb_upper_unit(pair_off, gm.n_units, item_begin);
-    int u_next_end = pair_off[u_next + 1];
-    PbPairPos pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, item_begin, gm, span_lo, span_len, pre, g);
+    const bool has_items = item_begin < item_end;
+    if (!has_items && !gm.phase_sync) return;
+    int u_next = 0, u_next_end = 0;
+    PbPairPos pos_next = {0, 0, 0};
+    if (has_items) {
+        u_next = pb_upper_unit(pair_off, gm.n_units, item_begin);
+        u_next_end = pair_off[u_next + 1];
+        pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, item_begin, gm, span_lo, span_len, pre, g);
+    }
     int u = -1;
     PbUnitDev ud;
-    for (int item = item_begin; item < item_end; item++) {
+    for (int it = 0; it < per_group; it++) {
+        // The loop body is ~60 KB of code, twice the SM's 32 KB instruction cache.  Starting every iteration together keeps
+        // the CTA's warps within a few hundred instructions of each other, so one warp's instruction fetches serve all.
+        if (gm.phase_sync) __syncthreads();
+        const int item = item_begin + it;
+        if (item >= item_end) {
+            if (!gm.phase_sync) break;
+#ifdef PB_MID_SYNC
+            __syncthreads();
+#endif
+            continue;
+        }
         const PbPairPos pos = pos_next;
         if (u != u_next) { u = u_next; ud = units[u]; }
         const int16_t* sm = pre + (size_t)((item - item_begin) & 1) * gm.pre_cap;
@@ -360,9 +376,14 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
                     sb[f] = pos.shift - span_lo + (f ? pos.hop : 0);       // staged index of frame sample n is sb[f] + n
                     // local mean: one longest period to both sides of the frame centre (exact in integers)
                     int s = 0;
-                    for (int q = lane; q < 2 * gm.nsamp_period; q += 32) {
-                        const int n = mean_n0 + q;
-                        s += (n >= nlo[f] && n < nhi[f]) ? (int)sm[sb[f] + n] : 0;
+                    if (nlo[f] <= mean_n0 && nhi[f] >= mean_n0 + 2 * gm.nsamp_period) {   // interior frame: no range checks
+                        const int16_t* ms = sm + sb[f] + mean_n0;
+                        for (int q = lane; q < 2 * gm.nsamp_period; q += 32) s += (int)ms[q];
+                    } else {
+                        for (int q = lane; q < 2 * gm.nsamp_period; q += 32) {
+                            const int n = mean_n0 + q;
+                            s += (n >= nlo[f] && n < nhi[f]) ? (int)sm[sb[f] + n] : 0;
+                        }
                     }
                     s = pb_warp_sum_i(s);
                     lmean[f] = (float)(((double)s / 32768.0) / (double)(2 * gm.nsamp_period));
@@ -371,20 +392,32 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
                 // ---- window both frames into the FFT buffer, z = a + i b (natural order, zero padded); a compact
                 //      rolled loop: the range checks live here once instead of in 32 unrolled copies
                 float mxA = 0.0f, mxB = 0.0f;
-                for (int n = g; n < N; n += GT) {
-                    float a = 0.0f, b = 0.0f;
-                    if (n < gm.nw) {
+                const float2 nmean = make_float2(-lmean[0], -lmean[1]), q15 = make_float2(1.0f / 32768.0f, 1.0f / 32768.0f);
+                const float hb = hasB ? 1.0f : 0.0f;
+                if (nlo[0] <= 0 && nhi[0] >= gm.nw && nlo[1] <= 0 && nhi[1] >= gm.nw) {
+                    // interior pair (all but the first / last frames of a unit): no range checks, packed-pair arithmetic
+                    const int16_t* pa = sm + sb[0]; const int16_t* pb = sm + sb[1];
+                    for (int n = g; n < gm.nw; n += GT) {
+                        const float w = __ldg(&gm.window[n]);
+                        const float2 ab = __fmul2_rn(__ffma2_rn(make_float2((float)pa[n], (float)pb[n]), q15, nmean), make_float2(w, w * hb));
+                        const float aa = fabsf(ab.x), bb = fabsf(ab.y);
+                        mxA = fmaxf(mxA, aa); mxB = fmaxf(mxB, bb);
+                        if (n >= pk_lo && n < pk_hi) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, bb); }
+                        buf[pb_pad5(n)] = ab;
+                    }
+                } else {
+                    for (int n = g; n < gm.nw; n += GT) {
                         const float w = __ldg(&gm.window[n]);
                         const int sa = (n >= nlo[0] && n < nhi[0]) ? (int)sm[sb[0] + n] : 0;
                         const int sbv = (n >= nlo[1] && n < nhi[1]) ? (int)sm[sb[1] + n] : 0;
-                        a = ((float)sa * (1.0f / 32768.0f) - lmean[0]) * w;
-                        b = hasB ? ((float)sbv * (1.0f / 32768.0f) - lmean[1]) * w : 0.0f;
-                        const float aa = fabsf(a), ab = fabsf(b);
-                        mxA = fmaxf(mxA, aa); mxB = fmaxf(mxB, ab);
-                        if (n >= pk_lo && n < pk_hi) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, ab); }
+                        const float2 ab = __fmul2_rn(__ffma2_rn(make_float2((float)sa, (float)sbv), q15, nmean), make_float2(w, w * hb));
+                        const float aa = fabsf(ab.x), bb = fabsf(ab.y);
+                        mxA = fmaxf(mxA, aa); mxB = fmaxf(mxB, bb);
+                        if (n >= pk_lo && n < pk_hi) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, bb); }
+                        buf[pb_pad5(n)] = ab;
                     }
-                    buf[pb_pad5(n)] = make_float2(a, b);
                 }
+                for (int n = g + ((gm.nw - g + GT - 1) / GT) * GT; n < N; n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);   // zero padding
                 mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB); pkA = pb_warp_max(pkA); pkB = pb_warp_max(pkB);
                 if (G > 1) {
                     if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; red[wg * 4 + 2] = pkA; red[wg * 4 + 3] = pkB; }
@@ -407,11 +440,11 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
         // ---- two FFTs x two passes through ONE copy of the butterfly code: FFT (step >> 1), pass (step & 1).  The step
         //      index is made opaque so the optimiser neither peels nor unswitches the loop (either duplicates ~450
         //      instructions of butterflies, and instruction fetch is what this kernel stalls on).
+        int n_steps = active ? 4 : 0;
+        asm volatile("" : "+r"(n_steps));
 #ifndef PB_SIMT_EMU
 #pragma unroll 1
 #endif
-        int n_steps = active ? 4 : 0;
-        asm volatile("" : "+r"(n_steps));
         for (int it = 0; it < n_steps; it++) {
             int step = it;
             asm volatile("" : "+r"(step));
@@ -507,6 +540,9 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
             }
             pb_group_sync<G>(bar_id);
         }
+#ifdef PB_MID_SYNC
+        if (gm.phase_sync) __syncthreads();
+#endif
         // ---- candidates: warp 0 of the group takes frame A, warp 1 (or warp 0 again) frame B
         {
             const float gpk = (float)ud.global_peak;

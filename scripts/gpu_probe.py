@@ -19,7 +19,8 @@ for i in range(n_utt):
     items.append((i * n, n, sr, 2.5, 4.5, float(sr)))
 units = pb.Units.from_list(items)
 p = pb.pitch_params(75.0, 600.0)
-ex = pb.Extractor(0)
+import os
+ex = pb.Extractor(0, lib=pb._native.load(os.environ["PB_LIB"])) if os.environ.get("PB_LIB") else pb.Extractor(0)
 print(ex.device_info())
 flat = pcm.reshape(-1)
 for it in range(4):
