@@ -339,7 +339,7 @@ template <int LOG2N>
 int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, const int32_t* d_pair_off, const PbPitchGeomDev& gm,
                   float* cand_f, float* cand_s, uint8_t* ncand, float* inten) {
     typedef PbFftCfg<LOG2N> C;
-    const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + 2 * (size_t)gm.pre_cap * sizeof(int16_t)) + 72 * sizeof(float);
+    const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + 72 * sizeof(float);
     const int threads = C::WARPS_PER_CTA * 32;
     auto kfn = pb_pitch_frames_kernel<LOG2N>;
     int per_sm = 2;

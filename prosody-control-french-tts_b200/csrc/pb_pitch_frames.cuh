@@ -296,12 +296,12 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
     const int group = warp / G, wg = warp % G;          // group in CTA, warp in group
     const int g = wg * 32 + lane;                       // thread in group = butterfly index
     const int bar_id = 1 + (G == 1 ? (group & 7) : group);   // one-warp groups may share an id: every arrival completes the barrier
-    // per-group shared memory: FFT buffer, a small reduction scratch, two sample staging buffers
-    const size_t group_bytes = (size_t)(C::BUF + 8 * G) * sizeof(float2) + 2 * (size_t)gm.pre_cap * sizeof(int16_t);
+    // per-group shared memory: FFT buffer, a small reduction scratch, the sample staging buffer
+    const size_t group_bytes = (size_t)(C::BUF + 8 * G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t);
     unsigned char* gbase = smem_raw + (size_t)group * group_bytes;
     float2* buf = (float2*)gbase;
     float* red = (float*)(buf + C::BUF);                // [G][4] floats
-    int16_t* pre = (int16_t*)(buf + C::BUF + 8 * G);    // [2][pre_cap]
+    int16_t* pre = (int16_t*)(buf + C::BUF + 8 * G);    // [pre_cap] staged samples of one pair
     // CTA-wide: the half-sample sinc coefficients (72 floats after the last group's region)
     float* half_tab = (float*)(smem_raw + (size_t)C::GROUPS_PER_CTA * group_bytes);
     if (threadIdx.x < 72) half_tab[threadIdx.x] = threadIdx.x < 70 ? __ldg(&gm.half_tab[threadIdx.x]) : 0.0f;
@@ -345,14 +345,9 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
         }
         const PbPairPos pos = pos_next;
         if (u != u_next) { u = u_next; ud = units[u]; }
-        const int16_t* sm = pre + (size_t)((item - item_begin) & 1) * gm.pre_cap;
-        if (item + 1 < item_end) {
-            if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); }
-            pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, item + 1, gm, span_lo, span_len,
-                                            pre + (size_t)((item + 1 - item_begin) & 1) * gm.pre_cap, g);
-            pb_cp_async_wait<1>();                      // everything but the copy just issued has landed
-        } else pb_cp_async_wait<0>();
-        pb_group_sync<G>(bar_id);                       // ... and is visible to every lane of the group
+        const int16_t* sm = pre;
+        pb_cp_async_wait<0>();                          // this pair's samples (requested during the previous pair) have landed
+        pb_group_sync<G>(bar_id);                       // ... and are visible to every lane of the group
         const int fA = 2 * (item - ud.pair_off);
         const bool hasB = fA + 1 < ud.n_frames;
         const bool global_silent = ud.global_peak == 0.0;
@@ -436,6 +431,11 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
                 sB = mxB > 0.0f ? __int_as_float((254 - ((__float_as_int(mxB) >> 23) & 0xff)) << 23) : 1.0f;
                 pb_group_sync<G>(bar_id);               // the windowed frames are in the buffer
             }
+        }
+        // the staged samples are consumed: request the next pair's now, they land while this pair is transformed
+        if (item + 1 < item_end) {
+            if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); }
+            pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, item + 1, gm, span_lo, span_len, pre, g);
         }
         // ---- two FFTs x two passes through ONE copy of the butterfly code: FFT (step >> 1), pass (step & 1).  The step
         //      index is made opaque so the optimiser neither peels nor unswitches the loop (either duplicates ~450
