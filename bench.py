@@ -228,7 +228,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        acc = dict(frames_ms=0.0, lufs_ms=0.0, path_ms=0.0, unit_stats_ms=0.0, h2d_ms=0.0, n_launches=0, n_frames=0)
+        acc = dict(frames_ms=0.0, lufs_ms=0.0, path_ms=0.0, unit_stats_ms=0.0, h2d_ms=0.0, total_ms=0.0, host_plan_ms=0.0, n_launches=0, n_frames=0)
         for _ in range(steps):
             out = step(src)
             for k in acc:
@@ -295,7 +295,7 @@ def main():
             e2e=dict(value=e2e, unit="audio-s/s", h2d_bytes_per_step=int(host_pcm.numel() * 2 + n_units * 120),
                      d2h_bytes_per_step=int(n_units * 20), ms_per_step=1e3 * dt_e2e / args.steps),
             gpu_launches=int(acc["n_launches"]),
-            kernels_ms_per_step={k: acc[k] / args.steps for k in ("unit_stats_ms", "frames_ms", "path_ms", "lufs_ms", "h2d_ms")},
+            kernels_ms_per_step={k: acc[k] / args.steps for k in ("unit_stats_ms", "frames_ms", "path_ms", "lufs_ms", "h2d_ms", "total_ms", "host_plan_ms")},
             roofline=dict(bound="fp32", kernel="pb_pitch_frames_kernel<10>", achieved=achieved_tflops, peak=fp32_peak, unit="TFLOP/s",
                           frac=achieved_tflops / fp32_peak, traffic=traffic,
                           note="non-tensor FP32 pipe: no stage is a dense contraction; peak = SMs x 128 FFMA lanes x 2 x max SM clock "

@@ -191,6 +191,12 @@ int pb_syntagme_deltas(int64_t n, const double* p_nat, const double* base_f0, co
                        const int32_t* word_count, const double* nat_total_s, const double* syn_total_s, const int32_t* pause_ms,
                        const PbDeltaParams* prm, double* raw_pitch, double* raw_volume, double* raw_rate);
 
+/* Per-segment baselines (Code/audioPipeline.py:401-424): np.median of the voiced p_nat (> 0), of l_nat and of rate_ratio
+ * over all segments (window < 0 for None, or window >= n) or over the sliding window [i - window/2, i + window/2 + 1).
+ * An empty voiced set gives NaN, as `float(np.median([])) or 1.0` does.  All arrays have n entries. */
+int pb_segment_baselines(int64_t n, const double* p_nat, const double* l_nat, const double* rate_ratio, int32_t window,
+                         double* f0, double* loud, double* rate);
+
 /* EMA over all rows then the forward jump clamp (Code/audioPipeline.py:593-602). out may alias x. */
 int pb_ema_clamp(const double* x, int64_t n, double alpha, double max_jump, double* out);
 

@@ -123,7 +123,7 @@ struct PbHandle {
     std::map<int, size_t> occ_last;                        // LOG2N -> footprint the function attributes were last set for
     BatchPlan plan;                                        // host plan of the call in progress (scratch reused across calls)
     int64_t cur_pcm_len = 0;                               // samples in the pcm buffer of the call in progress
-    size_t sil_smem = 0; int sil_per_sm = 2;               // K5: footprint its function attribute was set for, resident CTAs per SM
+    size_t sil_smem = 0; int sil_per_sm = 2, sil_nv = 0;               // K5: footprint its function attribute was set for, resident CTAs per SM
 };
 
 namespace {

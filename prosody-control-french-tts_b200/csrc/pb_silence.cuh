@@ -31,9 +31,21 @@ struct PbSilFileDev {
 #define PB_SIL_PADW(w) ((w) + ((w) >> 5))       // one pad word per 32: lane-strided bin reads stay (nearly) conflict-free
 
 // pydub frame_count(ms) = ms * (frame_rate / 1000.0), truncated by int(); files are < 2^31 - 2^16 samples (host check)
-#define PB_SIL_NV 6     // 16-byte vectors one lane keeps in flight per 32-bin group: 32 * 6 * 8 samples, i.e. rates up to 48 kHz
-
 __device__ __forceinline__ int pb_sil_frame32(int ms, double per_ms) { return __double2int_rz(__dmul_rn((double)ms, per_ms)); }
+
+// Sum of squares of the two s16 halves of wd, split as x * x = 256 * x * (x >> 8) + x * (x & 255) so that each half is one
+// dp2a (16-bit x 8-bit dot product with accumulate): acc_hi += x0 * hi0 + x1 * hi1, acc_lo += x0 * lo0 + x1 * lo1.
+__device__ __forceinline__ void pb_sil_sq2(uint32_t wd, int& acc_hi, int& acc_lo) {
+#ifdef PB_SIMT_EMU
+    const int x0 = (int)(short)(wd & 0xffff), x1 = (int)wd >> 16;
+    acc_hi += x0 * (x0 >> 8) + x1 * (x1 >> 8);
+    acc_lo += x0 * (x0 & 255) + x1 * (x1 & 255);
+#else
+    const uint32_t b = __byte_perm(wd, 0, 0x3120);            // bytes (lo0, lo1, hi0, hi1)
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(acc_lo) : "r"(wd), "r"(b));
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %0;" : "+r"(acc_hi) : "r"(wd), "r"(b));
+#endif
+}
 
 __device__ __forceinline__ int4 pb_sil_load_vec(const int16_t* __restrict__ pcm, const int4* __restrict__ pal, long long mis, long long pcm_len, long long v) {
     const long long s0 = (v << 3) - mis;
@@ -45,6 +57,8 @@ __device__ __forceinline__ int4 pb_sil_load_vec(const int16_t* __restrict__ pcm,
 
 // tile_windows: window starts per CTA tile; the tile needs tile_windows + win_ms + 1 bins (+1 window of halo each side).
 // smem layout: u64 bins[nb_cap + 1] | u64 warp_tot[PB_SIL_WARPS] | u8 flags[tile_windows + 2] | u32 stage[PB_SIL_WARPS][words_per_warp]
+// NV: 16-byte vectors one lane keeps in flight per 32-bin group (32 * NV * 8 samples cover 32 ms at the batch's highest rate)
+template <int NV>
 __global__ void __launch_bounds__(PB_SIL_WARPS * 32, 2)
 pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const PbSilFileDev* __restrict__ files, int n_files,
                        long long n_tiles, int tile_windows, int win_ms, int nb_cap, int words_per_warp, long long limit_per_sample,
@@ -83,9 +97,9 @@ pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const
                 gv0 = (F.pcm_off + fA + mis) >> 3;
                 gnvec = (int)(((F.pcm_off + fB + mis + 7) >> 3) - gv0);
             };
-            int4 q[PB_SIL_NV];
+            int4 q[NV];
             auto load = [&](long long gv0, int gnvec) {
-                PB_UNROLL for (int c = 0; c < PB_SIL_NV; c++) {
+                PB_UNROLL for (int c = 0; c < NV; c++) {
                     const int vi = c * 32 + lane;
                     if (vi < gnvec) q[c] = pb_sil_load_vec(pcm, pal, mis, pcm_len, gv0 + vi);
                 }
@@ -94,18 +108,17 @@ pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const
             long long v0 = 0;
             if (g * 32 < nb) { geom(g, a, b, v0, nvec); load(v0, nvec); }
             while (g * 32 < nb) {
-                PB_UNROLL for (int c = 0; c < PB_SIL_NV; c++) {
-                    const int vi = c * 32 + lane, w = vi * 4;
+                PB_UNROLL for (int c = 0; c < NV; c++) {
+                    const int vi = c * 32 + lane;
                     if (vi < nvec) {
-                        stage[PB_SIL_PADW(w)] = (uint32_t)q[c].x; stage[PB_SIL_PADW(w + 1)] = (uint32_t)q[c].y;
-                        stage[PB_SIL_PADW(w + 2)] = (uint32_t)q[c].z; stage[PB_SIL_PADW(w + 3)] = (uint32_t)q[c].w;
+                        uint32_t* d = stage + (vi * 4 + (vi >> 3));            // = PADW(4 vi): the four words never straddle a pad
+                        d[0] = (uint32_t)q[c].x; d[1] = (uint32_t)q[c].y; d[2] = (uint32_t)q[c].z; d[3] = (uint32_t)q[c].w;
                     }
                 }
-                for (int vi = PB_SIL_NV * 32 + lane; vi < nvec; vi += 32) {   // rates above 48 kHz: the rest, unpipelined
+                for (int vi = NV * 32 + lane; vi < nvec; vi += 32) {           // a rate above what NV covers: the rest, unpipelined
                     const int4 r = pb_sil_load_vec(pcm, pal, mis, pcm_len, v0 + vi);
-                    const int w = vi * 4;
-                    stage[PB_SIL_PADW(w)] = (uint32_t)r.x; stage[PB_SIL_PADW(w + 1)] = (uint32_t)r.y;
-                    stage[PB_SIL_PADW(w + 2)] = (uint32_t)r.z; stage[PB_SIL_PADW(w + 3)] = (uint32_t)r.w;
+                    uint32_t* d = stage + (vi * 4 + (vi >> 3));
+                    d[0] = (uint32_t)r.x; d[1] = (uint32_t)r.y; d[2] = (uint32_t)r.z; d[3] = (uint32_t)r.w;
                 }
                 __syncwarp();
                 const int gn = g + PB_SIL_WARPS;
@@ -118,13 +131,16 @@ pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const
                 if (k < e) {
                     if (k & 1) { const int x = (int)stage[PB_SIL_PADW(k >> 1)] >> 16; sum = (unsigned long long)((long long)x * x); k++; }
                     const int wl = e >> 1;
+                    int acc_hi = 0, acc_lo = 0;
+                    for (int w = k >> 1; w < wl;) {                              // runs of words between two pad slots
+                        const int w_end = min(wl, (w | 31) + 1);
+                        const uint32_t* sp = stage + (w + (w >> 5));
+                        const int n = w_end - w;
 #pragma unroll 4
-                    for (int w = k >> 1; w < wl; w++) {
-                        const uint32_t wd = stage[PB_SIL_PADW(w)];
-                        const int x0 = (int)(short)(wd & 0xffff), x1 = (int)wd >> 16;
-                        sum += (unsigned long long)((long long)x0 * x0);
-                        sum += (unsigned long long)((long long)x1 * x1);
+                        for (int c = 0; c < n; c++) pb_sil_sq2(sp[c], acc_hi, acc_lo);
+                        w = w_end;
                     }
+                    sum += (unsigned long long)((long long)acc_hi * 256 + (long long)acc_lo);
                     if (e & 1) { const int x = (int)(short)(stage[PB_SIL_PADW(wl)] & 0xffff); sum += (unsigned long long)((long long)x * x); }
                 }
                 if (g * 32 + lane < nb) bins[g * 32 + lane] = sum;

@@ -103,29 +103,20 @@ def plan(segments: Sequence[Segment], prosody: dict | None = None, pos_of: IV.Po
                 np.asarray(p_ms, np.int32), np.asarray(swc, np.int32), units, want_p, want_l, S, K)
 
 
-def _median_or_nan(v: np.ndarray) -> float:
-    return float(np.median(v)) if len(v) else float("nan")
-
-
-def baselines(p_nat, l_nat, rate_ratio, window: int | None):
-    """Global or sliding-window medians per segment (:401-424). -> (f0, loud, rate) arrays."""
-    S = len(p_nat)
-    f0 = np.empty(S); loud = np.empty(S); rate = np.empty(S)
-    if window is None or window >= S:
-        f0[:] = _median_or_nan(p_nat[p_nat > 0]) or 1.0
-        loud[:] = float(np.median(l_nat)); rate[:] = float(np.median(rate_ratio))
-        return f0, loud, rate
-    half = window // 2
-    for i in range(S):
-        lo, hi = max(0, i - half), min(S, i + half + 1)
-        w = p_nat[lo:hi]
-        f0[i] = _median_or_nan(w[w > 0]) or 1.0
-        loud[i] = float(np.median(l_nat[lo:hi])); rate[i] = float(np.median(rate_ratio[lo:hi]))
-    return f0, loud, rate
-
-
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def baselines(p_nat, l_nat, rate_ratio, window: int | None, lib=None):
+    """Global or sliding-window medians per segment (:401-424), np.median semantics, in C (pb_segment_baselines).
+    -> (f0, loud, rate) arrays."""
+    lib = lib if lib is not None else N.load()
+    S = len(p_nat)
+    p = np.ascontiguousarray(p_nat, np.float64); l = np.ascontiguousarray(l_nat, np.float64); r = np.ascontiguousarray(rate_ratio, np.float64)
+    f0 = np.empty(S); loud = np.empty(S); rate = np.empty(S)
+    N.check(lib, None, lib.pb_segment_baselines(S, _dp(p), _dp(l), _dp(r), -1 if window is None else int(window), _dp(f0), _dp(loud), _dp(rate)),
+            "pb_segment_baselines")
+    return f0, loud, rate
 
 
 def _ip(a):
@@ -155,7 +146,7 @@ def measure(ex: Extractor, pcm, pl: Plan, prosody: dict | None = None, pitch: di
     wc = pl.word_counts.astype(np.float64)
     with np.errstate(divide="ignore", invalid="ignore"):
         rate_ratio = np.where((pl.word_counts > 0) & (d_syn > 0), (wc / d_nat) / (wc / d_syn), 1.0)
-    b_f0, b_loud, b_rate = baselines(p_nat, l_nat, rate_ratio, prm["baseline_window"])
+    b_f0, b_loud, b_rate = baselines(p_nat, l_nat, rate_ratio, prm["baseline_window"], ex._lib)
     # ---- pass 2 (:495-589)
     a = slice(2 * S, 2 * S + 2 * K, 2); b = slice(2 * S + 1, 2 * S + 2 * K, 2)
     sp_nat = np.ascontiguousarray(med[a]); sl_syn = np.ascontiguousarray(lufs[b])

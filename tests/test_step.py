@@ -100,3 +100,30 @@ def test_delta_and_smoothing_helpers_match_python_arithmetic(native_lib):
     x = rng.normal(0, 6, 3000); out = np.empty(3000)
     assert native_lib.pb_ema_clamp(d(x), 3000, 0.4, 5.0, d(out)) == 0
     assert list(out) == F.smooth(list(x), 0.4, 5.0)
+
+
+def test_segment_baselines_match_numpy_medians():
+    """pb_segment_baselines against the reference's own expression (np.median over list comprehensions, :401-424)."""
+    import warnings
+    from prosody_b200 import step as S
+    rng = np.random.default_rng(5)
+    for n, win in ((1, None), (7, None), (7, 10), (40, 10), (41, 3), (200, 11), (64, 0), (30, 1)):
+        p = rng.uniform(80, 300, n); p[rng.random(n) < 0.3] = 0.0
+        if n >= 40:
+            p[10:22] = 0.0                                         # a window without any voiced segment -> NaN baseline
+        l = rng.uniform(-35, -12, n); r = rng.uniform(0.7, 1.3, n)
+        if n > 5:
+            l[3] = -np.inf
+            l[5] = np.nan
+        f0, loud, rate = S.baselines(p, l, r, win)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in range(n):
+                if win is None or win >= n:
+                    lo, hi = 0, n
+                else:
+                    lo, hi = max(0, i - win // 2), min(n, i + win // 2 + 1)
+                ef = float(np.median([x for x in p[lo:hi] if x > 0])) or 1.0
+                el = float(np.median(list(l[lo:hi]))); er = float(np.median(list(r[lo:hi])))
+                for got, exp in ((f0[i], ef), (loud[i], el), (rate[i], er)):
+                    assert (np.isnan(got) and np.isnan(exp)) or got == exp, (n, win, i, got, exp)
