@@ -76,6 +76,8 @@ struct LufsKeyHash {
 struct PitchClass { PbGeomHost g; int gstatus = 0; double rate = 0.0; };
 
 // everything the host decides about a batch before any GPU work
+struct LufsResolved { int64_t a, b, npad; int st; };
+
 struct BatchPlan {
     // pitch
     std::vector<PbUnitPlan> pplan;            // per caller unit
@@ -93,6 +95,7 @@ struct BatchPlan {
     std::vector<LufsKey> seen_key;            // key of every compact unit
     // per-call scratch kept here so its capacity (and its pages) survive from call to call
     std::vector<int32_t> pstat, lflags;
+    std::vector<LufsResolved> lres;           // slice arithmetic of every unit (filled in parallel)
     std::vector<std::vector<int64_t>> pids, lids, by_class;
     void reset() {
         pplan.clear(); pclass.clear(); classes.clear(); max_cand = 0; total_frames = 0;
@@ -230,6 +233,20 @@ int get_tables(PbHandle* h, const PbGeomHost& g, PitchTables** out) {
 }
 
 // ------------------------------------------------------------------------------------------------ planning (host only)
+// fn(i0, i1) over [0, n) on a few host threads (the per-unit planning is independent float64 arithmetic)
+template <class F> void pb_parallel_for(int64_t n, int64_t grain, F fn) {
+    const int64_t want = grain > 0 ? n / grain : 1;
+    const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())), want));
+    if (nt <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    const int64_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        const int64_t i0 = (int64_t)t * per, i1 = std::min<int64_t>(n, i0 + per);
+        if (i0 < i1) pool.emplace_back(fn, i0, i1);
+    }
+    for (auto& th : pool) th.join();
+}
+
 int validate_units(PbHandle* h, const PbUnits* u, int64_t pcm_len) {
     if (!u || u->n_units < 0) return fail(h, PB_EINVAL, "%s", "units is null or n_units < 0");
     if (u->n_units && (!u->file_off || !u->file_nx || !u->rate || !u->has_t1 || !u->t0 || !u->t1))
@@ -247,6 +264,8 @@ int validate_units(PbHandle* h, const PbUnits* u, int64_t pcm_len) {
 int plan_pitch(PbHandle* h, const PbUnits* u, const PbPitchParams* p, const uint8_t* want, int32_t* status, int32_t* n_frames, BatchPlan& bp) {
     const int64_t n = u->n_units;
     bp.pplan.resize((size_t)n); bp.pclass.assign((size_t)n, -1);
+    // geometry class of every wanted unit (sequential: a handful of distinct rates), then the float64 planning of the
+    // units themselves split over a few host threads, then the totals
     double last_rate = -1.0; int last_cls = -1;
     for (int64_t i = 0; i < n; i++) {
         if (want && !want[i]) continue;
@@ -260,11 +279,22 @@ int plan_pitch(PbHandle* h, const PbUnits* u, const PbPitchParams* p, const uint
             }
             last_rate = u->rate[i]; last_cls = ci;
         }
-        PitchClass& pc = bp.classes[(size_t)ci];
-        PbUnitPlan& pl = bp.pplan[(size_t)i];
-        pb_plan_pitch_unit(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], *p, pc.g, pc.gstatus, pl);
-        status[i] = pl.status; n_frames[i] = pl.n_frames;
-        if (pl.status == PB_UNIT_OK) { bp.pclass[(size_t)i] = ci; bp.total_frames += pl.n_frames; bp.max_cand = pc.g.max_cand; }
+        bp.pclass[(size_t)i] = ci;
+    }
+    pb_parallel_for(n, 16384, [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; i++) {
+            const int ci = bp.pclass[(size_t)i];
+            if (ci < 0) continue;
+            const PitchClass& pc = bp.classes[(size_t)ci];
+            PbUnitPlan& pl = bp.pplan[(size_t)i];
+            pb_plan_pitch_unit(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], *p, pc.g, pc.gstatus, pl);
+            status[i] = pl.status; n_frames[i] = pl.n_frames;
+            if (pl.status != PB_UNIT_OK) bp.pclass[(size_t)i] = -1;
+        }
+    });
+    for (int64_t i = 0; i < n; i++) {
+        const int ci = bp.pclass[(size_t)i];
+        if (ci >= 0) { bp.total_frames += bp.pplan[(size_t)i].n_frames; bp.max_cand = bp.classes[(size_t)ci].g.max_cand; }
     }
     if (bp.max_cand > PB_MAXC) return fail(h, PB_EUNSUPPORTED, "%s", "pitch_ceiling / pitch_floor exceeds 32 candidates per frame");
     return PB_OK;
@@ -282,11 +312,22 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
     bp.seen.assign(cap, 0);
     bp.seen_key.clear();
     const LufsKeyHash hasher;
+    // the slice arithmetic of every unit in parallel, the de-duplication below in order
+    bp.lres.resize((size_t)n);
+    pb_parallel_for(n, 16384, [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; i++) {
+            if (want && !want[i]) continue;
+            const double mr = u->meter_rate ? u->meter_rate[i] : u->rate[i];
+            LufsResolved& r = bp.lres[(size_t)i];
+            r.st = pb_lufs_resolve(u->file_nx[i], u->rate[i], mr, u->has_t1[i], u->t0[i], u->t1[i], &r.a, &r.b, &r.npad);
+        }
+    });
     for (int64_t i = 0; i < n; i++) {
         if (want && !want[i]) continue;
         const double mr = u->meter_rate ? u->meter_rate[i] : u->rate[i];
-        int64_t a, b, npad;
-        const int st = pb_lufs_resolve(u->file_nx[i], u->rate[i], mr, u->has_t1[i], u->t0[i], u->t1[i], &a, &b, &npad);
+        const LufsResolved& rs = bp.lres[(size_t)i];
+        const int64_t a = rs.a, b = rs.b, npad = rs.npad;
+        const int st = rs.st;
         flags[i] = st;
         if (st & (PB_UNIT_LUFS_ERROR | PB_UNIT_SLICE_ERROR)) continue;
         const LufsKey key{u->file_off[i] + a, b - a, npad, mr};
