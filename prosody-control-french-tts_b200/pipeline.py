@@ -132,3 +132,11 @@ def measure_prosody_and_build_ssml(self, extractor: Extractor | None = None, pos
                                              out["raw_volume"], self.azure_voice, self.inter_syntagme_pause_factor)
     SSML.write_csvs(final, syn_rows, synth_rows, self.bdd_ssml_csv, self.bdd_syntagme_ssml_csv, self.bdd_syntagme_synth_csv)
     return out
+
+
+def export_training_json(self):
+    """Drop-in for AudioPipeline.export_training_json (/root/reference/Code/audioPipeline.py:840-854): the syntagme-level
+    CSV of this voice -> training_data_<name>.json, then bdd.json over every voice folder under <out_dir>/results."""
+    from . import training_export as TE
+    TE.create_training_data(str(self.bdd_syntagme_ssml_csv), str(self.results_dir / f"training_data_{self.name}.json"))
+    TE.combine_training_jsons(str(self.out_dir / "results"), str(self.out_dir / "results" / "bdd.json"))
