@@ -200,6 +200,19 @@ int pb_segment_baselines(int64_t n, const double* p_nat, const double* l_nat, co
 /* EMA over all rows then the forward jump clamp (Code/audioPipeline.py:593-602). out may alias x. */
 int pb_ema_clamp(const double* x, int64_t n, double alpha, double max_jump, double* out);
 
+/* ---- TextGrid input at corpus scale (host only, no handle): one tier of many files, parsed on host threads.
+ * Replaces per-file `textgrid.TextGrid.fromFile(path)[0]` (Code/Preprocessing/gen_break_ssml.py:19-26).
+ * status per file: 0 ok, 1 unreadable, 2 not a TextGrid / truncated, 3 no such tier.  pb_textgrid_copy fills caller
+ * arrays: status/xmin/xmax [n_files], iv_off [n_files+1], tmin/tmax [n_intervals], mark_off [n_intervals+1] into the
+ * UTF-8 `marks` pool [mark_bytes].  Times are rounded to 5 decimals and intervals with min >= max dropped, as the
+ * textgrid package does.  n_threads <= 0: all host cores. */
+typedef struct PbTextGridBatch PbTextGridBatch;
+int pb_textgrid_parse_files(const char* const* paths, int64_t n_files, int tier_index, int n_threads, PbTextGridBatch** out);
+int pb_textgrid_sizes(const PbTextGridBatch* b, int64_t* n_files, int64_t* n_intervals, int64_t* mark_bytes);
+int pb_textgrid_copy(const PbTextGridBatch* b, int32_t* status, double* xmin, double* xmax, int64_t* iv_off,
+                     double* tmin, double* tmax, int64_t* mark_off, char* marks);
+void pb_textgrid_free(PbTextGridBatch* b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,7 +50,8 @@ class PbDeltaParams(C.Structure):
 EXPORTS = ["pb_syntagme_deltas", "pb_ema_clamp", "pb_abi_version", "pb_create", "pb_destroy", "pb_last_error", "pb_set_stream", "pb_get_timings",
            "pb_device_info", "pb_pitch_params_default", "pb_pitch_plan", "pb_median_pitch_batch", "pb_lufs_batch",
            "pb_part_duration_batch", "pb_extract_batch", "pb_intensity_plan", "pb_intensity_batch", "pb_legacy_loudness_batch", "pb_split_on_silence_bound",
-           "pb_split_on_silence_batch", "pb_segment_baselines"]
+           "pb_split_on_silence_batch", "pb_segment_baselines", "pb_textgrid_parse_files",
+           "pb_textgrid_sizes", "pb_textgrid_copy", "pb_textgrid_free"]
 
 
 def bind(lib: C.CDLL) -> C.CDLL:
@@ -76,9 +77,13 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.pb_split_on_silence_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, C.c_int, C.c_double, C.c_int, C.c_int64, i64p, i32p, i32p, i64p, i32p, i32p]
     lib.pb_syntagme_deltas.argtypes = [C.c_int64, dp, dp, dp, dp, i32p, dp, dp, i32p, C.POINTER(PbDeltaParams), dp, dp, dp]
     lib.pb_segment_baselines.argtypes = [C.c_int64, dp, dp, dp, C.c_int32, dp, dp, dp]
+    lib.pb_textgrid_parse_files.argtypes = [C.POINTER(C.c_char_p), C.c_int64, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.pb_textgrid_sizes.argtypes = [vp, i64p, i64p, i64p]
+    lib.pb_textgrid_copy.argtypes = [vp, i32p, dp, dp, i64p, dp, dp, i64p, C.c_char_p]
+    lib.pb_textgrid_free.argtypes = [vp]; lib.pb_textgrid_free.restype = None
     lib.pb_ema_clamp.argtypes = [dp, C.c_int64, C.c_double, C.c_double, dp]
     for name in EXPORTS:
-        if name not in ("pb_destroy", "pb_last_error", "pb_pitch_params_default", "pb_split_on_silence_bound"):
+        if name not in ("pb_destroy", "pb_last_error", "pb_pitch_params_default", "pb_split_on_silence_bound", "pb_textgrid_free"):
             getattr(lib, name).restype = C.c_int
     return lib
 

@@ -16,6 +16,7 @@
 #include "pb_silence.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -808,5 +809,6 @@ int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_o
 #include "pb_api_host.inc"
 #include "pb_api_next.inc"
 #include "pb_api_silence.inc"
+#include "pb_textgrid.inc"
 
 }  // extern "C"

@@ -91,9 +91,13 @@ def load_voice(audio_dir, raw_audio_dir, textgrid_dir):
     """Reads segment_ph*.wav (sorted by number, :364-367), the raw-synth twins and the TextGrids into one PCM buffer."""
     seg_files = sorted(Path(audio_dir).glob("*.wav"), key=lambda p: int(re.search(r"segment_ph(\d+)", p.stem).group(1)))
     bufs, segs, off = [], [], 0
-    for wav in seg_files:
+    # all alignments in one native call (host threads); a file it refuses goes through the Python reader for its error
+    tg_paths = [Path(textgrid_dir) / f"{wav.stem}.TextGrid" for wav in seg_files]
+    tg_status, tg_words = TG.read_tier_batch(tg_paths, tier=0) if seg_files else ([], [])
+    for k, wav in enumerate(seg_files):
         pcm, sr = read_wav(wav)
-        seg = S.Segment(wav.stem, off, len(pcm), sr, TG.word_intervals(Path(textgrid_dir) / f"{wav.stem}.TextGrid"))
+        words = tg_words[k] if tg_status[k] == TG.STATUS_OK else TG.word_intervals(tg_paths[k])
+        seg = S.Segment(wav.stem, off, len(pcm), sr, words)
         bufs.append(pcm); off += len(pcm)
         try:
             spcm, ssr = read_wav(Path(raw_audio_dir) / f"{wav.stem}.wav")

@@ -113,3 +113,38 @@ def write(path, tiers: dict, xmin: float = 0.0, xmax: float | None = None) -> No
         for j, (a, b, mark) in enumerate(ivs, 1):
             out += [f"        intervals [{j}]:", f"            xmin = {a}", f"            xmax = {b}", f'            text = "{esc(mark)}"']
     Path(path).write_text("\n".join(out) + "\n", encoding="utf-8")
+
+
+STATUS_OK, STATUS_UNREADABLE, STATUS_NOT_TEXTGRID, STATUS_NO_TIER = 0, 1, 2, 3
+
+
+def read_tier_batch(paths, tier: int = 0, threads: int = 0, lib=None):
+    """One tier of many TextGrid files through the native batch parser (pb_textgrid_parse_files, host threads).
+    -> (status per file, [[(tmin, tmax, mark), ...] per file]); a file with status != 0 has an empty list."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _native as N
+    lib = lib if lib is not None else N.load()
+    enc = [str(p).encode() for p in paths]
+    arr = (C.c_char_p * len(enc))(*enc)
+    h = C.c_void_p()
+    N.check(lib, None, lib.pb_textgrid_parse_files(arr, len(enc), int(tier), int(threads), C.byref(h)), "pb_textgrid_parse_files")
+    try:
+        nf, ni, mb = C.c_int64(), C.c_int64(), C.c_int64()
+        lib.pb_textgrid_sizes(h, C.byref(nf), C.byref(ni), C.byref(mb))
+        st = np.zeros(nf.value, np.int32); off = np.zeros(nf.value + 1, np.int64)
+        t0 = np.zeros(ni.value); t1 = np.zeros(ni.value); mo = np.zeros(ni.value + 1, np.int64)
+        pool = C.create_string_buffer(max(1, mb.value))
+        dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        N.check(lib, None, lib.pb_textgrid_copy(h, st.ctypes.data_as(ip), None, None, off.ctypes.data_as(lp), t0.ctypes.data_as(dp),
+                                                t1.ctypes.data_as(dp), mo.ctypes.data_as(lp), pool), "pb_textgrid_copy")
+    finally:
+        lib.pb_textgrid_free(h)
+    raw = pool.raw
+    out = []
+    for f in range(nf.value):
+        a, b = int(off[f]), int(off[f + 1])
+        out.append([(float(t0[k]), float(t1[k]), raw[mo[k]:mo[k + 1]].decode("utf-8")) for k in range(a, b)])
+    return st, out
