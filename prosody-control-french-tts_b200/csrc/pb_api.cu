@@ -405,6 +405,7 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
     } else per_sm = oc->second;
 #endif
     long long need = ((long long)gm.n_pairs + C::GROUPS_PER_CTA - 1) / C::GROUPS_PER_CTA;
+    { const char* e = getenv("PB_FRAMES_CTAS"); if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e); }   // experiments: fewer resident CTAs
     long long cap = (long long)h->sm_count * per_sm;
     int grid = (int)std::max(1LL, std::min(need, cap));
     PB_LAUNCH(kfn, dim3(grid), dim3(threads), smem, h->stream, d_pcm, d_units, d_pair_off, gm, cand_f, cand_s, ncand, inten);
