@@ -15,12 +15,18 @@
 #include "pb_lufs.cuh"
 #include "pb_silence.cuh"
 
+// descriptors: pinned host staging -> device, read by the SMs over PCIe (does not queue behind the PCM in the copy engine)
+__global__ void pb_copy16_kernel(const int4* __restrict__ src, int4* __restrict__ dst, long long n16) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -313,6 +319,8 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
     bp.seen.assign(cap, 0);
     bp.seen_key.clear();
     const LufsKeyHash hasher;
+    double last_mr = -1.0; int last_meter = -1;
+    bp.lunits.reserve((size_t)n); bp.lneed.reserve((size_t)n); bp.seen_key.reserve((size_t)n);
     // the slice arithmetic of every unit in parallel, the de-duplication below in order
     bp.lres.resize((size_t)n);
     pb_parallel_for(n, 16384, [&](int64_t i0, int64_t i1) {
@@ -342,6 +350,17 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
         if (dup) continue;
         bp.seen[slot] = (int32_t)bp.lunits.size() + 1;
         bp.seen_key.push_back(key);
+        if (mr == last_mr) {                                    // nearly every unit of a voice uses the same meter
+            PbLufsUnitDev d;
+            d.pcm_off = u->file_off[i]; d.a = a; d.b = b; d.npad = npad; d.chunk_off = 0;
+            const int64_t len = b - a + npad;
+            d.n_blocks = (int32_t)pb_lufs_num_blocks(len, mr); d.n_chunks = d.n_blocks + 3;
+            d.meter = last_meter; d.out_index = (int)i; d.inv_peak = 1.0;
+            bp.lunits.push_back(d);
+            bp.lneed.push_back(u->file_off[i] + b);
+            bp.lufs_samples += len;
+            continue;
+        }
         auto it = meter_ix.find(mr);
         if (it == meter_ix.end()) {
             PbMeterDev md; memset(&md, 0, sizeof md);
@@ -369,6 +388,7 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
         const int64_t len = b - a + npad;
         d.n_blocks = (int32_t)pb_lufs_num_blocks(len, mr); d.n_chunks = d.n_blocks + 3;
         d.meter = it->second; d.out_index = (int)i; d.inv_peak = 1.0;
+        last_mr = mr; last_meter = it->second;
         bp.lunits.push_back(d);
         bp.lneed.push_back(u->file_off[i] + b);
         bp.lufs_samples += len;
@@ -590,101 +610,132 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     std::vector<int32_t>& pstat = bp.pstat; std::vector<int32_t>& lflags = bp.lflags;
     pstat.assign((size_t)n, 0); lflags.assign((size_t)n, 0);
     const auto t_plan0 = std::chrono::steady_clock::now();
-    if (do_pitch) {
-        memset(o.n_frames, 0, (size_t)n * 4);
-        rc = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp);
-        if (rc != PB_OK) return rc;
-    }
-    if (do_lufs) { rc = plan_lufs(h, u, want_lufs, lflags.data(), bp); if (rc != PB_OK) return rc; }
-    h->last.n_frames = bp.total_frames; h->last.n_lufs_samples = bp.lufs_samples;
-
-    // ---- segments of the PCM buffer: one when it is already resident, several when it is uploaded here
+    static const bool plan_profile = getenv("PB_PLAN_PROFILE") != nullptr;      // development aid: host planning laps on stderr
+    auto t_lap = t_plan0;
+    auto lap = [&](const char* what) {
+        if (!plan_profile) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pb plan] %-14s %.3f ms\n", what, std::chrono::duration<float, std::milli>(now - t_lap).count());
+        t_lap = now;
+    };
+    // Order of the call (everything the host computes overlaps something the GPU or the copy engine does):
+    //   1. host PCM: its upload starts NOW, in segments, on the copy stream;
+    //   2. the pitch units are planned and their descriptors staged; descriptors reach the device through a small copy
+    //      kernel on the compute stream that reads the pinned staging buffer directly (a DMA copy would queue behind the
+    //      PCM segments: the copy engine is FIFO);
+    //   3. resident PCM (one segment): the pitch kernels are launched before the loudness units are even planned;
+    //   4. the loudness units are planned and staged; then the remaining launches, segment by segment.
     const size_t pcm_bytes = (size_t)pcm_len * 2;
     int n_seg = 1;
     if (!on_device && !want_frames && pcm_bytes >= ((size_t)64 << 20)) n_seg = 8;
     const int64_t seg_samples = n_seg > 1 ? (((pcm_len + n_seg - 1) / n_seg + 127) & ~(int64_t)127) : (pcm_len > 0 ? pcm_len : 1);
     auto seg_of = [&](int64_t need_end) { int64_t s = need_end > 0 ? (need_end - 1) / seg_samples : 0; return (int)(s >= n_seg ? n_seg - 1 : s); };
+    PB_CKMEM(h->med.ensure((size_t)n * 8 + 8) || h->nvoiced.ensure((size_t)n * 4 + 4) || h->lufs.ensure((size_t)n * 8 + 8) ||
+             h->stage_out.ensure((size_t)n * 20 + 64), "unit results");
+    if (!on_device) PB_CKMEM(h->pcm.ensure(pcm_bytes + 64), "pcm staging");
+    const int16_t* d_pcm = on_device ? pcm : (const int16_t*)h->pcm.p;
+    std::unique_ptr<ScopedEv> evt(new ScopedEv(h, EV_TOTAL));       // closed once the result download is enqueued
+    std::vector<pbEvent_t> seg_done((size_t)n_seg);
+    if (!on_device) {
+        ScopedEv ev(h, EV_H2D, h->copy_stream);
+        for (int s = 0; s < n_seg; s++) {
+            const int64_t a = (int64_t)s * seg_samples, b = std::min<int64_t>(pcm_len, a + seg_samples);
+            if (b > a) PB_CK(pbrt_h2d((char*)h->pcm.p + a * 2, pcm + a, (size_t)(b - a) * 2, h->copy_stream), "pcm upload");
+            seg_done[(size_t)s] = *next_event(h);
+            pbrt_event_record(&seg_done[(size_t)s], h->copy_stream);
+        }
+    }
+    if (do_pitch) PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
+    if (do_lufs) PB_CK(pbrt_memset(h->lufs.p, 0xff, (size_t)n * 8, h->stream), "memset");      // all-ones = NaN
+    // pinned staging -> device, by the SMs (16-byte words; the staging buffers are allocated with slack)
+    auto upload = [&](void* dst, const void* src_pinned, size_t bytes) {
+        if (!bytes) return;
+        const long long n16 = (long long)((bytes + 15) / 16);
+        const int grid = (int)std::max<long long>(1, std::min<long long>((n16 + 255) / 256, (long long)h->sm_count * 4));
+        PB_LAUNCH(pb_copy16_kernel, dim3(grid), dim3(256), 0, h->stream, (const int4*)pbrt_host_device_ptr(src_pinned), (int4*)dst, n16);
+        h->last.n_launches++;
+    };
+
+    // ---- pitch: plan, stage, upload descriptors
     std::vector<std::vector<int64_t>>& pids = bp.pids; std::vector<std::vector<int64_t>>& lids = bp.lids;
     if (pids.size() < (size_t)n_seg) pids.resize((size_t)n_seg);
     if (lids.size() < (size_t)n_seg) lids.resize((size_t)n_seg);
     for (auto& v : pids) v.clear();
     for (auto& v : lids) v.clear();
     std::vector<int64_t> seg_frames((size_t)n_seg, 0), seg_chunks((size_t)n_seg, 0);
-    size_t n_pok = 0;
-    if (do_pitch) for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0) {
-        const int s = seg_of(u->file_off[i] + u->file_nx[i]);
-        pids[(size_t)s].push_back(i); seg_frames[(size_t)s] += bp.pplan[(size_t)i].n_frames; n_pok++;
-    }
-    for (size_t k = 0; k < bp.lunits.size(); k++) {
-        const int s = seg_of(bp.lneed[k]);
-        lids[(size_t)s].push_back((int64_t)k); seg_chunks[(size_t)s] += bp.lunits[k].n_chunks;
-    }
-    // per-frame outputs follow the caller's unit order (the layout pb_pitch_plan reports)
-    std::vector<int64_t> frame_off;
-    if (want_frames) {
-        frame_off.assign((size_t)n + 1, 0);
-        int64_t acc = 0;
-        for (int64_t i = 0; i < n; i++) { frame_off[(size_t)i] = acc; if (bp.pclass[(size_t)i] >= 0) acc += bp.pplan[(size_t)i].n_frames; }
-        frame_off[(size_t)n] = acc;
-    }
-    // ---- size every buffer once, before anything is in flight
-    const size_t T = (size_t)*std::max_element(seg_frames.begin(), seg_frames.end());
-    const size_t CH = (size_t)*std::max_element(seg_chunks.begin(), seg_chunks.end());
-    const size_t mc = (size_t)(bp.max_cand > 0 ? bp.max_cand : 1);
-    PB_CKMEM(h->med.ensure((size_t)n * 8 + 8) || h->nvoiced.ensure((size_t)n * 4 + 4) || h->lufs.ensure((size_t)n * 8 + 8) ||
-             h->stage_out.ensure((size_t)n * 20 + 64), "unit results");
-    if (n_pok) PB_CKMEM(h->cand_f.ensure(T * mc * 4) || h->cand_s.ensure(T * mc * 4) || h->ncand.ensure(T) || h->inten.ensure(T * 4) ||
-                        h->psi.ensure(T * mc) || h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4) ||
-                        h->stage_units.ensure(n_pok * sizeof(PbUnitDev)) || h->units.ensure(n_pok * sizeof(PbUnitDev)) ||
-                        h->stage_pairs.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4) ||
-                        h->pair_off.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4), "pitch buffers");
-    if (!bp.lunits.empty()) {
-        PB_CKMEM(h->stage_lunits.ensure(bp.lunits.size() * sizeof(PbLufsUnitDev)) || h->lunits.ensure(bp.lunits.size() * sizeof(PbLufsUnitDev)) ||
-                 h->meters.ensure(bp.meters.size() * sizeof(PbMeterDev)) || h->stage_meters.ensure(bp.meters.size() * sizeof(PbMeterDev)) ||
-                 h->lstate.ensure(CH * 32) || h->lenergy.ensure(CH * 8), "loudness buffers");
-        memcpy(h->stage_meters.p, bp.meters.data(), bp.meters.size() * sizeof(PbMeterDev));
-    }
-    if (!on_device) PB_CKMEM(h->pcm.ensure(pcm_bytes + 64), "pcm staging");
-    const int16_t* d_pcm = on_device ? pcm : (const int16_t*)h->pcm.p;
-    // ---- descriptors of every segment into pinned staging (host work only)
     std::vector<std::vector<PitchLaunch>> pl((size_t)n_seg);
     std::vector<LufsLaunch> ll((size_t)n_seg);
-    for (int s = 0; s < n_seg; s++) {
-        if (do_pitch) { rc = stage_pitch(h, u, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr, pl[(size_t)s]); if (rc != PB_OK) return rc; }
-        ll[(size_t)s].off = 0; ll[(size_t)s].m = 0; ll[(size_t)s].chunks = 0;
-        if (do_lufs && !lids[(size_t)s].empty()) stage_lufs(h, bp, lids[(size_t)s], ll[(size_t)s]);
+    std::vector<int64_t> frame_off;
+    bool pitch_launched = false;
+    if (do_pitch) {
+        memset(o.n_frames, 0, (size_t)n * 4);
+        rc = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp);
+        if (rc != PB_OK) return rc;
+        lap("plan_pitch");
+        size_t n_pok = 0;
+        for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0) {
+            const int s = seg_of(u->file_off[i] + u->file_nx[i]);
+            pids[(size_t)s].push_back(i); seg_frames[(size_t)s] += bp.pplan[(size_t)i].n_frames; n_pok++;
+        }
+        // per-frame outputs follow the caller's unit order (the layout pb_pitch_plan reports)
+        if (want_frames) {
+            frame_off.assign((size_t)n + 1, 0);
+            int64_t acc = 0;
+            for (int64_t i = 0; i < n; i++) { frame_off[(size_t)i] = acc; if (bp.pclass[(size_t)i] >= 0) acc += bp.pplan[(size_t)i].n_frames; }
+            frame_off[(size_t)n] = acc;
+        }
+        const size_t T = (size_t)*std::max_element(seg_frames.begin(), seg_frames.end());
+        const size_t mc = (size_t)(bp.max_cand > 0 ? bp.max_cand : 1);
+        if (n_pok) PB_CKMEM(h->cand_f.ensure(T * mc * 4) || h->cand_s.ensure(T * mc * 4) || h->ncand.ensure(T) || h->inten.ensure(T * 4) ||
+                            h->psi.ensure(T * mc) || h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4) ||
+                            h->stage_units.ensure(n_pok * sizeof(PbUnitDev) + 16) || h->units.ensure(n_pok * sizeof(PbUnitDev) + 16) ||
+                            h->stage_pairs.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4 + 16) ||
+                            h->pair_off.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4 + 16), "pitch buffers");
+        for (int s = 0; s < n_seg; s++) {
+            rc = stage_pitch(h, u, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr, pl[(size_t)s]);
+            if (rc != PB_OK) return rc;
+        }
+        lap("stage_pitch");
+        upload(h->units.p, h->stage_units.p, h->su_off * sizeof(PbUnitDev));
+        upload(h->pair_off.p, h->stage_pairs.p, h->sp_off * 4);
+        if (n_seg == 1) {
+            if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
+            for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
+            pitch_launched = true;
+        }
     }
+    // ---- loudness: plan, stage, upload descriptors (with resident PCM the pitch kernels are already running)
+    if (do_lufs) {
+        rc = plan_lufs(h, u, want_lufs, lflags.data(), bp);
+        if (rc != PB_OK) return rc;
+        lap("plan_lufs");
+        for (size_t k = 0; k < bp.lunits.size(); k++) {
+            const int s = seg_of(bp.lneed[k]);
+            lids[(size_t)s].push_back((int64_t)k); seg_chunks[(size_t)s] += bp.lunits[k].n_chunks;
+        }
+        const size_t CH = (size_t)*std::max_element(seg_chunks.begin(), seg_chunks.end());
+        if (!bp.lunits.empty()) {
+            PB_CKMEM(h->stage_lunits.ensure(bp.lunits.size() * sizeof(PbLufsUnitDev) + 16) || h->lunits.ensure(bp.lunits.size() * sizeof(PbLufsUnitDev) + 16) ||
+                     h->meters.ensure(bp.meters.size() * sizeof(PbMeterDev) + 16) || h->stage_meters.ensure(bp.meters.size() * sizeof(PbMeterDev) + 16) ||
+                     h->lstate.ensure(CH * 32) || h->lenergy.ensure(CH * 8), "loudness buffers");
+            memcpy(h->stage_meters.p, bp.meters.data(), bp.meters.size() * sizeof(PbMeterDev));
+        }
+        for (int s = 0; s < n_seg; s++) {
+            ll[(size_t)s].off = 0; ll[(size_t)s].m = 0; ll[(size_t)s].chunks = 0;
+            if (!lids[(size_t)s].empty()) stage_lufs(h, bp, lids[(size_t)s], ll[(size_t)s]);
+        }
+        lap("stage_lufs");
+        upload(h->lunits.p, h->stage_lunits.p, h->sl_off * sizeof(PbLufsUnitDev));
+        upload(h->meters.p, h->stage_meters.p, bp.meters.size() * sizeof(PbMeterDev));
+    }
+    h->last.n_frames = bp.total_frames; h->last.n_lufs_samples = bp.lufs_samples;
     h->last.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
 
     {
-        ScopedEv evt(h, EV_TOTAL);
-        if (do_pitch) PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
-        if (do_lufs) PB_CK(pbrt_memset(h->lufs.p, 0xff, (size_t)n * 8, h->stream), "memset");      // all-ones = NaN
-        // All host->device traffic goes through the copy stream, descriptors FIRST: H2D copies are served in FIFO order
-        // by the copy engine, so a small descriptor upload queued behind the PCM would hold every kernel back until
-        // the whole PCM has landed.  The compute stream itself never issues an H2D copy.
-        pbEvent_t desc_done = *next_event(h);
-        std::vector<pbEvent_t> seg_done((size_t)n_seg);
-        {
-            ScopedEv ev(h, EV_H2D, h->copy_stream);
-            if (h->su_off) PB_CK(pbrt_h2d(h->units.p, h->stage_units.p, h->su_off * sizeof(PbUnitDev), h->copy_stream) ||
-                                 pbrt_h2d(h->pair_off.p, h->stage_pairs.p, h->sp_off * 4, h->copy_stream), "descriptor upload");
-            if (h->sl_off) PB_CK(pbrt_h2d(h->lunits.p, h->stage_lunits.p, h->sl_off * sizeof(PbLufsUnitDev), h->copy_stream) ||
-                                 pbrt_h2d(h->meters.p, h->stage_meters.p, bp.meters.size() * sizeof(PbMeterDev), h->copy_stream), "descriptor upload");
-            pbrt_event_record(&desc_done, h->copy_stream);
-            if (!on_device) for (int s = 0; s < n_seg; s++) {
-                const int64_t a = (int64_t)s * seg_samples, b = std::min<int64_t>(pcm_len, a + seg_samples);
-                if (b > a) PB_CK(pbrt_h2d((char*)h->pcm.p + a * 2, pcm + a, (size_t)(b - a) * 2, h->copy_stream), "pcm upload");
-                seg_done[(size_t)s] = *next_event(h);
-                pbrt_event_record(&seg_done[(size_t)s], h->copy_stream);
-            }
-        }
-        PB_CK(pbrt_stream_wait_event(h->stream, desc_done), "stream wait");
         for (int s = 0; s < n_seg; s++) {
-            if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[(size_t)s]), "stream wait");
-            for (const PitchLaunch& L : pl[(size_t)s]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
-            rc = launch_lufs_group(h, d_pcm, ll[(size_t)s]);
-            if (rc != PB_OK) return rc;
+            if (!on_device && !(pitch_launched && s == 0)) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[(size_t)s]), "stream wait");
+            if (!pitch_launched) for (const PitchLaunch& L : pl[(size_t)s]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
+            if (do_lufs) { rc = launch_lufs_group(h, d_pcm, ll[(size_t)s]); if (rc != PB_OK) return rc; }
         }
         ScopedEv evd(h, EV_D2H);
         char* so = (char*)h->stage_out.p;
@@ -697,6 +748,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
             if (o.frame_intensity) PB_CK(pbrt_d2h(o.frame_intensity, h->inten.p, fb, h->stream), "frame download");
         }
     }
+    evt.reset();
     // host arithmetic overlaps the GPU work
     if (o.duration_s) for (int64_t i = 0; i < n; i++) {
         int st; o.duration_s[i] = pb_part_duration(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], &st);

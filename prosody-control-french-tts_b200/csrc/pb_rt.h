@@ -37,6 +37,7 @@ static inline int pbrt_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); retu
 static inline int pbrt_free(void* p) { free(p); return 0; }
 static inline int pbrt_malloc_host(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
 static inline int pbrt_free_host(void* p) { free(p); return 0; }
+static inline const void* pbrt_host_device_ptr(const void* p) { return p; }
 static inline int pbrt_h2d(void* d, const void* s, size_t n, pbStream_t) { memcpy(d, s, n); return 0; }
 static inline int pbrt_d2h(void* d, const void* s, size_t n, pbStream_t) { memcpy(d, s, n); return 0; }
 static inline int pbrt_memset(void* d, int v, size_t n, pbStream_t) { memset(d, v, n); return 0; }
@@ -61,6 +62,12 @@ static inline int pbrt_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n :
 static inline int pbrt_free(void* p) { return cudaFree(p) != cudaSuccess; }
 static inline int pbrt_malloc_host(void** p, size_t n) { return cudaMallocHost(p, n ? n : 1) != cudaSuccess; }
 static inline int pbrt_free_host(void* p) { return cudaFreeHost(p) != cudaSuccess; }
+// device-side address of pinned host memory (identical under unified addressing)
+static inline const void* pbrt_host_device_ptr(const void* p) {
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return p; }
+    return d;
+}
 static inline int pbrt_h2d(void* d, const void* s, size_t n, pbStream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st) != cudaSuccess; }
 static inline int pbrt_d2h(void* d, const void* s, size_t n, pbStream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st) != cudaSuccess; }
 static inline int pbrt_memset(void* d, int v, size_t n, pbStream_t st) { return cudaMemsetAsync(d, v, n, st) != cudaSuccess; }
