@@ -103,9 +103,10 @@ struct BatchPlan {
     // per-call scratch kept here so its capacity (and its pages) survive from call to call
     std::vector<int32_t> pstat, lflags;
     std::vector<LufsResolved> lres;           // slice arithmetic of every unit (filled in parallel)
+    std::vector<int64_t> fbase;               // first frame of every staged pitch unit
     std::vector<std::vector<int64_t>> pids, lids, by_class;
     void reset() {
-        pplan.clear(); pclass.clear(); classes.clear(); max_cand = 0; total_frames = 0;
+        classes.clear(); max_cand = 0; total_frames = 0;       // pplan / pclass keep their size: plan_pitch rewrites them
         lunits.clear(); lneed.clear(); meters.clear(); dups.clear(); lufs_samples = 0;
         seen_key.clear();
     }
@@ -270,12 +271,13 @@ int validate_units(PbHandle* h, const PbUnits* u, int64_t pcm_len) {
 // status / n_frames must be zero-initialised by the caller; only wanted units are touched
 int plan_pitch(PbHandle* h, const PbUnits* u, const PbPitchParams* p, const uint8_t* want, int32_t* status, int32_t* n_frames, BatchPlan& bp) {
     const int64_t n = u->n_units;
-    bp.pplan.resize((size_t)n); bp.pclass.assign((size_t)n, -1);
+    if (bp.pplan.size() != (size_t)n) bp.pplan.resize((size_t)n);     // every wanted entry is rewritten below: no re-zeroing per call
+    bp.pclass.resize((size_t)n);
     // geometry class of every wanted unit (sequential: a handful of distinct rates), then the float64 planning of the
     // units themselves split over a few host threads, then the totals
     double last_rate = -1.0; int last_cls = -1;
     for (int64_t i = 0; i < n; i++) {
-        if (want && !want[i]) continue;
+        if (want && !want[i]) { bp.pclass[(size_t)i] = -1; continue; }
         int ci = last_cls;
         if (u->rate[i] != last_rate) {
             ci = -1;
@@ -458,21 +460,29 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
         if (rc != PB_OK) return rc;
         PbUnitDev* su = (PbUnitDev*)h->stage_units.p + h->su_off;
         int32_t* sp = (int32_t*)h->stage_pairs.p + h->sp_off;
+        // running pair / frame offsets first (sequential, two adds per unit), then the 80-byte descriptors in parallel
         int64_t pairs = 0;
+        std::vector<int64_t>& fbase = h->plan.fbase;
+        fbase.resize(m);
         for (size_t k = 0; k < m; k++) {
-            const int64_t i = cid[k];
-            const PbUnitPlan& pl = bp.pplan[(size_t)i];
-            PbUnitDev& d = su[k];
-            d.pcm_off = u->file_off[i]; d.ix1 = pl.ix1; d.nx = pl.nx;
-            d.frame_off = frame_off_by_unit ? (*frame_off_by_unit)[(size_t)i] : frame_base;
-            d.x1 = pl.x1; d.t1 = pl.t1; d.mean = 0.0; d.global_peak = 0.0;
-            d.file_nx = (int32_t)u->file_nx[i]; d.n_frames = pl.n_frames; d.pair_off = (int32_t)pairs; d.out_index = (int32_t)i;
-            sp[k] = (int32_t)pairs;
+            const PbUnitPlan& pl = bp.pplan[(size_t)cid[k]];
+            sp[k] = (int32_t)pairs; fbase[k] = frame_base;
             pairs += (pl.n_frames + 1) / 2;
             frame_base += pl.n_frames;
             if (pairs > 0x7ffffff0LL) return fail(h, PB_EUNSUPPORTED, "%s", "more than 2^31 frame pairs in one launch; split the batch");
         }
         sp[m] = (int32_t)pairs;
+        pb_parallel_for((int64_t)m, 16384, [&](int64_t k0, int64_t k1) {
+            for (int64_t k = k0; k < k1; k++) {
+                const int64_t i = cid[(size_t)k];
+                const PbUnitPlan& pl = bp.pplan[(size_t)i];
+                PbUnitDev& d = su[k];
+                d.pcm_off = u->file_off[i]; d.ix1 = pl.ix1; d.nx = pl.nx;
+                d.frame_off = frame_off_by_unit ? (*frame_off_by_unit)[(size_t)i] : fbase[(size_t)k];
+                d.x1 = pl.x1; d.t1 = pl.t1; d.mean = 0.0; d.global_peak = 0.0;
+                d.file_nx = (int32_t)u->file_nx[i]; d.n_frames = pl.n_frames; d.pair_off = sp[k]; d.out_index = (int32_t)i;
+            }
+        });
         PitchLaunch L; L.cls = (int)ci; L.uoff = h->su_off; L.poff = h->sp_off; L.m = m; L.pairs = pairs;
         out.push_back(L);
         h->su_off += m; h->sp_off += m + 1;
@@ -626,10 +636,16 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     //   3. resident PCM (one segment): the pitch kernels are launched before the loudness units are even planned;
     //   4. the loudness units are planned and staged; then the remaining launches, segment by segment.
     const size_t pcm_bytes = (size_t)pcm_len * 2;
-    int n_seg = 1;
-    if (!on_device && !want_frames && pcm_bytes >= ((size_t)64 << 20)) n_seg = 8;
-    const int64_t seg_samples = n_seg > 1 ? (((pcm_len + n_seg - 1) / n_seg + 127) & ~(int64_t)127) : (pcm_len > 0 ? pcm_len : 1);
-    auto seg_of = [&](int64_t need_end) { int64_t s = need_end > 0 ? (need_end - 1) / seg_samples : 0; return (int)(s >= n_seg ? n_seg - 1 : s); };
+    // Host PCM is uploaded in segments so that kernels start as soon as the first one has landed.  Small segments first
+    // (the wait before the first kernel is one segment), larger ones later (fewer launches and kernel tails).
+    std::vector<int64_t> seg_end;                              // exclusive end sample of every segment
+    if (!on_device && !want_frames && pcm_bytes >= ((size_t)64 << 20)) {
+        static const int parts[] = {1, 1, 1, 1, 2, 2, 4, 4, 8, 8};          // in 32nds of the buffer
+        int64_t acc = 0;
+        for (int k = 0; k < 10; k++) { acc += parts[k]; seg_end.push_back(k == 9 ? pcm_len : (((pcm_len * acc) / 32 + 127) & ~(int64_t)127)); }
+    } else seg_end.push_back(pcm_len);
+    const int n_seg = (int)seg_end.size();
+    auto seg_of = [&](int64_t need_end) { int s = 0; while (s + 1 < n_seg && need_end > seg_end[(size_t)s]) s++; return s; };
     PB_CKMEM(h->med.ensure((size_t)n * 8 + 8) || h->nvoiced.ensure((size_t)n * 4 + 4) || h->lufs.ensure((size_t)n * 8 + 8) ||
              h->stage_out.ensure((size_t)n * 20 + 64), "unit results");
     if (!on_device) PB_CKMEM(h->pcm.ensure(pcm_bytes + 64), "pcm staging");
@@ -639,7 +655,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     if (!on_device) {
         ScopedEv ev(h, EV_H2D, h->copy_stream);
         for (int s = 0; s < n_seg; s++) {
-            const int64_t a = (int64_t)s * seg_samples, b = std::min<int64_t>(pcm_len, a + seg_samples);
+            const int64_t a = s ? seg_end[(size_t)s - 1] : 0, b = seg_end[(size_t)s];
             if (b > a) PB_CK(pbrt_h2d((char*)h->pcm.p + a * 2, pcm + a, (size_t)(b - a) * 2, h->copy_stream), "pcm upload");
             seg_done[(size_t)s] = *next_event(h);
             pbrt_event_record(&seg_done[(size_t)s], h->copy_stream);
