@@ -629,38 +629,33 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         t_lap = now;
     };
     // Order of the call (everything the host computes overlaps something the GPU or the copy engine does):
-    //   1. host PCM: its upload starts NOW, in segments, on the copy stream;
-    //   2. the pitch units are planned and their descriptors staged; descriptors reach the device through a small copy
-    //      kernel on the compute stream that reads the pinned staging buffer directly (a DMA copy would queue behind the
-    //      PCM segments: the copy engine is FIFO);
-    //   3. resident PCM (one segment): the pitch kernels are launched before the loudness units are even planned;
-    //   4. the loudness units are planned and staged; then the remaining launches, segment by segment.
+    //   * host PCM: the upload of a first segment starts NOW on the copy stream; both plans are made while it is in flight,
+    //     then the rest of the buffer is cut where the PLANNED work says (below) and queued behind it;
+    //   * resident PCM: the pitch kernels are launched before the loudness units are even planned;
+    //   * descriptors reach the device through a small copy kernel on the compute stream that reads the pinned staging
+    //     buffer directly (a DMA copy would queue behind the PCM: the copy engine is FIFO).
     const size_t pcm_bytes = (size_t)pcm_len * 2;
-    // Host PCM is uploaded in segments so that kernels start as soon as the first one has landed.  Small segments first
-    // (the wait before the first kernel is one segment), larger ones later (fewer launches and kernel tails).
-    std::vector<int64_t> seg_end;                              // exclusive end sample of every segment
-    if (!on_device && !want_frames && pcm_bytes >= ((size_t)64 << 20)) {
-        static const int parts[] = {1, 1, 1, 1, 2, 2, 4, 4, 8, 8};          // in 32nds of the buffer
-        int64_t acc = 0;
-        for (int k = 0; k < 10; k++) { acc += parts[k]; seg_end.push_back(k == 9 ? pcm_len : (((pcm_len * acc) / 32 + 127) & ~(int64_t)127)); }
-    } else seg_end.push_back(pcm_len);
-    const int n_seg = (int)seg_end.size();
-    auto seg_of = [&](int64_t need_end) { int s = 0; while (s + 1 < n_seg && need_end > seg_end[(size_t)s]) s++; return s; };
+    const bool segmented = !on_device && !want_frames && pcm_bytes >= ((size_t)64 << 20);
     PB_CKMEM(h->med.ensure((size_t)n * 8 + 8) || h->nvoiced.ensure((size_t)n * 4 + 4) || h->lufs.ensure((size_t)n * 8 + 8) ||
              h->stage_out.ensure((size_t)n * 20 + 64), "unit results");
     if (!on_device) PB_CKMEM(h->pcm.ensure(pcm_bytes + 64), "pcm staging");
     const int16_t* d_pcm = on_device ? pcm : (const int16_t*)h->pcm.p;
     std::unique_ptr<ScopedEv> evt(new ScopedEv(h, EV_TOTAL));       // closed once the result download is enqueued
-    std::vector<pbEvent_t> seg_done((size_t)n_seg);
-    if (!on_device) {
+    std::vector<int64_t> seg_end;                                    // exclusive end sample of every PCM segment
+    std::vector<pbEvent_t> seg_done;
+    constexpr int NB = 512;                                          // planning histogram: work per 1/512 of the buffer
+    auto bin_edge = [&](int b) { return b >= NB ? pcm_len : std::min<int64_t>(pcm_len, (((pcm_len * b) / NB + 127) & ~(int64_t)127)); };
+    auto enqueue_upload = [&](int64_t a, int64_t b) -> int {
         ScopedEv ev(h, EV_H2D, h->copy_stream);
-        for (int s = 0; s < n_seg; s++) {
-            const int64_t a = s ? seg_end[(size_t)s - 1] : 0, b = seg_end[(size_t)s];
-            if (b > a) PB_CK(pbrt_h2d((char*)h->pcm.p + a * 2, pcm + a, (size_t)(b - a) * 2, h->copy_stream), "pcm upload");
-            seg_done[(size_t)s] = *next_event(h);
-            pbrt_event_record(&seg_done[(size_t)s], h->copy_stream);
-        }
-    }
+        if (b > a) PB_CK(pbrt_h2d((char*)h->pcm.p + a * 2, pcm + a, (size_t)(b - a) * 2, h->copy_stream), "pcm upload");
+        seg_end.push_back(b);
+        seg_done.push_back(*next_event(h));
+        pbrt_event_record(&seg_done.back(), h->copy_stream);
+        return PB_OK;
+    };
+    const int first_bins = 5 * NB / 32;                              // ~ what uploads while the host plans
+    if (on_device) seg_end.push_back(pcm_len);
+    else { rc = enqueue_upload(0, segmented ? bin_edge(first_bins) : pcm_len); if (rc != PB_OK) return rc; }
     if (do_pitch) PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
     if (do_lufs) PB_CK(pbrt_memset(h->lufs.p, 0xff, (size_t)n * 8, h->stream), "memset");      // all-ones = NaN
     // pinned staging -> device, by the SMs (16-byte words; the staging buffers are allocated with slack)
@@ -671,23 +666,32 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         PB_LAUNCH(pb_copy16_kernel, dim3(grid), dim3(256), 0, h->stream, (const int4*)pbrt_host_device_ptr(src_pinned), (int4*)dst, n16);
         h->last.n_launches++;
     };
+    auto seg_of = [&](int64_t need_end) { int s = 0; const int ns = (int)seg_end.size(); while (s + 1 < ns && need_end > seg_end[(size_t)s]) s++; return s; };
 
-    // ---- pitch: plan, stage, upload descriptors
     std::vector<std::vector<int64_t>>& pids = bp.pids; std::vector<std::vector<int64_t>>& lids = bp.lids;
-    if (pids.size() < (size_t)n_seg) pids.resize((size_t)n_seg);
-    if (lids.size() < (size_t)n_seg) lids.resize((size_t)n_seg);
-    for (auto& v : pids) v.clear();
-    for (auto& v : lids) v.clear();
-    std::vector<int64_t> seg_frames((size_t)n_seg, 0), seg_chunks((size_t)n_seg, 0);
-    std::vector<std::vector<PitchLaunch>> pl((size_t)n_seg);
-    std::vector<LufsLaunch> ll((size_t)n_seg);
+    std::vector<std::vector<PitchLaunch>> pl;
+    std::vector<LufsLaunch> ll;
     std::vector<int64_t> frame_off;
     bool pitch_launched = false;
-    if (do_pitch) {
+
+    auto plan_pitch_units = [&]() -> int {
         memset(o.n_frames, 0, (size_t)n * 4);
-        rc = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp);
-        if (rc != PB_OK) return rc;
+        int r = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp);
         lap("plan_pitch");
+        return r;
+    };
+    auto plan_lufs_units = [&]() -> int {
+        int r = plan_lufs(h, u, want_lufs, lflags.data(), bp);
+        lap("plan_lufs");
+        return r;
+    };
+    // units -> segments, descriptors into pinned staging, descriptors to the device (the segments are final by now)
+    auto stage_upload_pitch = [&]() -> int {
+        const int n_seg = (int)seg_end.size();
+        if (pids.size() < (size_t)n_seg) pids.resize((size_t)n_seg);
+        for (auto& v : pids) v.clear();
+        pl.assign((size_t)n_seg, std::vector<PitchLaunch>());
+        std::vector<int64_t> seg_frames((size_t)n_seg, 0);
         size_t n_pok = 0;
         for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0) {
             const int s = seg_of(u->file_off[i] + u->file_nx[i]);
@@ -708,23 +712,20 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
                             h->stage_pairs.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4 + 16) ||
                             h->pair_off.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4 + 16), "pitch buffers");
         for (int s = 0; s < n_seg; s++) {
-            rc = stage_pitch(h, u, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr, pl[(size_t)s]);
-            if (rc != PB_OK) return rc;
+            int r = stage_pitch(h, u, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr, pl[(size_t)s]);
+            if (r != PB_OK) return r;
         }
         lap("stage_pitch");
         upload(h->units.p, h->stage_units.p, h->su_off * sizeof(PbUnitDev));
         upload(h->pair_off.p, h->stage_pairs.p, h->sp_off * 4);
-        if (n_seg == 1) {
-            if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
-            for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
-            pitch_launched = true;
-        }
-    }
-    // ---- loudness: plan, stage, upload descriptors (with resident PCM the pitch kernels are already running)
-    if (do_lufs) {
-        rc = plan_lufs(h, u, want_lufs, lflags.data(), bp);
-        if (rc != PB_OK) return rc;
-        lap("plan_lufs");
+        return PB_OK;
+    };
+    auto stage_upload_lufs = [&]() -> int {
+        const int n_seg = (int)seg_end.size();
+        if (lids.size() < (size_t)n_seg) lids.resize((size_t)n_seg);
+        for (auto& v : lids) v.clear();
+        ll.assign((size_t)n_seg, LufsLaunch());
+        std::vector<int64_t> seg_chunks((size_t)n_seg, 0);
         for (size_t k = 0; k < bp.lunits.size(); k++) {
             const int s = seg_of(bp.lneed[k]);
             lids[(size_t)s].push_back((int64_t)k); seg_chunks[(size_t)s] += bp.lunits[k].n_chunks;
@@ -743,7 +744,55 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         lap("stage_lufs");
         upload(h->lunits.p, h->stage_lunits.p, h->sl_off * sizeof(PbLufsUnitDev));
         upload(h->meters.p, h->stage_meters.p, bp.meters.size() * sizeof(PbMeterDev));
+        return PB_OK;
+    };
+
+    if (!segmented) {
+        // one segment: pitch descriptors up and pitch kernels running before the loudness units are planned
+        if (do_pitch) {
+            if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch()) != PB_OK) return rc;
+            if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
+            for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
+            pitch_launched = true;
+        }
+        if (do_lufs && ((rc = plan_lufs_units()) != PB_OK || (rc = stage_upload_lufs()) != PB_OK)) return rc;
+    } else {
+        // Both plans first (the first segment is uploading meanwhile), then cut the rest of the buffer by PLANNED work:
+        // a kernel can only start when its segment has landed, so the last segment should carry little work (it lands
+        // when the upload ends) and the ones before it similar amounts (fewer, fuller launches than a fixed grid of cuts).
+        if (do_pitch && (rc = plan_pitch_units()) != PB_OK) return rc;
+        if (do_lufs && (rc = plan_lufs_units()) != PB_OK) return rc;
+        std::vector<double> work((size_t)NB, 0.0);               // estimated GPU milliseconds per bin (measured rates)
+        auto bin_of = [&](int64_t need_end) { int64_t b = need_end > 0 ? ((need_end - 1) * NB) / pcm_len : 0; return (size_t)(b >= NB ? NB - 1 : b); };
+        if (do_pitch) for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0)
+            work[bin_of(u->file_off[i] + u->file_nx[i])] += 5.2e-6 * (double)bp.pplan[(size_t)i].n_frames;
+        for (size_t k = 0; k < bp.lunits.size(); k++)
+            work[bin_of(bp.lneed[k])] += 2.6e-9 * (double)(bp.lunits[k].b - bp.lunits[k].a + bp.lunits[k].npad);
+        double total = 0.0; for (double w : work) total += w;
+        int tail = NB;                                           // the last segment: the longest suffix with little work
+        { double sfx = 0.0; const double budget = std::max(3.0, 0.05 * total);
+          while (tail > first_bins + 1 && sfx + work[(size_t)tail - 1] <= budget) { sfx += work[(size_t)tail - 1]; tail--; } }
+        const double ms_per_bin = (double)pcm_bytes / NB / 55e6;     // ~55 GB/s pinned host -> device
+        int pieces = (int)std::ceil((tail - first_bins) * ms_per_bin / 14.0);
+        pieces = std::max(1, std::min(4, pieces));
+        double mid = 0.0; for (int b = first_bins; b < tail; b++) mid += work[(size_t)b];
+        { double acc = 0.0; int cut = 1, last = first_bins;
+          for (int b = first_bins; b < tail; b++) {
+              acc += work[(size_t)b];
+              if (cut < pieces && acc >= mid * cut / pieces && b + 1 > last && b + 1 < tail) {
+                  rc = enqueue_upload(bin_edge(last), bin_edge(b + 1)); if (rc != PB_OK) return rc;
+                  last = b + 1; cut++;
+              }
+          }
+          if (tail > last) { rc = enqueue_upload(bin_edge(last), bin_edge(tail)); if (rc != PB_OK) return rc; }
+          if (tail < NB) { rc = enqueue_upload(bin_edge(tail), pcm_len); if (rc != PB_OK) return rc; } }
+        lap("segments");
+        if (do_pitch && (rc = stage_upload_pitch()) != PB_OK) return rc;
+        if (do_lufs && (rc = stage_upload_lufs()) != PB_OK) return rc;
     }
+    const int n_seg = (int)seg_end.size();
+    if (pl.size() < (size_t)n_seg) pl.resize((size_t)n_seg);
+    if (ll.size() < (size_t)n_seg) ll.resize((size_t)n_seg, LufsLaunch());
     h->last.n_frames = bp.total_frames; h->last.n_lufs_samples = bp.lufs_samples;
     h->last.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
 
