@@ -244,7 +244,7 @@ int get_tables(PbHandle* h, const PbGeomHost& g, PitchTables** out) {
 // fn(i0, i1) over [0, n) on a few host threads (the per-unit planning is independent float64 arithmetic)
 template <class F> void pb_parallel_for(int64_t n, int64_t grain, F fn) {
     const int64_t want = grain > 0 ? n / grain : 1;
-    const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())), want));
+    const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), want));
     if (nt <= 1) { fn((int64_t)0, n); return; }
     std::vector<std::thread> pool;
     const int64_t per = (n + nt - 1) / nt;
@@ -316,9 +316,6 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
     // Units that resolve to the same samples and meter have the same loudness (the reference's < 0.4 s / empty-slice
     // fallbacks send every short syntagme of a file to that file's whole-file value): measure once, copy on the host.
     // flat open-addressing table (slot = 1 + index into bp.lunits, 0 = empty), kept in the plan scratch across calls
-    size_t cap = 1024;
-    while (cap < (size_t)n * 2 + 16) cap <<= 1;
-    bp.seen.assign(cap, 0);
     bp.seen_key.clear();
     const LufsKeyHash hasher;
     double last_mr = -1.0; int last_meter = -1;
@@ -333,6 +330,15 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
             r.st = pb_lufs_resolve(u->file_nx[i], u->rate[i], mr, u->has_t1[i], u->t0[i], u->t1[i], &r.a, &r.b, &r.npad);
         }
     });
+    size_t n_whole = 0;                                          // units that resolve to a whole file: the table's load
+    for (int64_t i = 0; i < n; i++) {
+        if (want && !want[i]) continue;
+        const LufsResolved& rs = bp.lres[(size_t)i];
+        n_whole += (rs.a == 0 && rs.b == u->file_nx[i] && rs.npad == 0);
+    }
+    size_t cap = 1024;
+    while (cap < n_whole * 2 + 16) cap <<= 1;
+    bp.seen.assign(cap, 0);
     for (int64_t i = 0; i < n; i++) {
         if (want && !want[i]) continue;
         const double mr = u->meter_rate ? u->meter_rate[i] : u->rate[i];
@@ -342,15 +348,19 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
         flags[i] = st;
         if (st & (PB_UNIT_LUFS_ERROR | PB_UNIT_SLICE_ERROR)) continue;
         const LufsKey key{u->file_off[i] + a, b - a, npad, mr};
-        size_t slot = hasher(key) & (cap - 1);
-        bool dup = false;
-        while (bp.seen[slot]) {
-            const size_t k = (size_t)bp.seen[slot] - 1;
-            if (bp.seen_key[k] == key) { bp.dups.push_back(std::make_pair(i, (int64_t)bp.lunits[k].out_index)); dup = true; break; }
-            slot = (slot + 1) & (cap - 1);
+        // only units that resolve to a WHOLE file are looked up (that is where the reference's fallbacks pile up, and
+        // it keeps the table small enough to stay in cache); two identical slices are simply measured twice
+        if (a == 0 && b == u->file_nx[i] && npad == 0) {
+            size_t slot = hasher(key) & (cap - 1);
+            bool dup = false;
+            while (bp.seen[slot]) {
+                const size_t k = (size_t)bp.seen[slot] - 1;
+                if (bp.seen_key[k] == key) { bp.dups.push_back(std::make_pair(i, (int64_t)bp.lunits[k].out_index)); dup = true; break; }
+                slot = (slot + 1) & (cap - 1);
+            }
+            if (dup) continue;
+            bp.seen[slot] = (int32_t)bp.lunits.size() + 1;
         }
-        if (dup) continue;
-        bp.seen[slot] = (int32_t)bp.lunits.size() + 1;
         bp.seen_key.push_back(key);
         if (mr == last_mr) {                                    // nearly every unit of a voice uses the same meter
             PbLufsUnitDev d;
@@ -653,7 +663,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         pbrt_event_record(&seg_done.back(), h->copy_stream);
         return PB_OK;
     };
-    const int first_bins = 5 * NB / 32;                              // ~ what uploads while the host plans
+    const int first_bins = 4 * NB / 32;                              // ~ what uploads while the host plans
     if (on_device) seg_end.push_back(pcm_len);
     else { rc = enqueue_upload(0, segmented ? bin_edge(first_bins) : pcm_len); if (rc != PB_OK) return rc; }
     if (do_pitch) PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
