@@ -663,7 +663,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         pbrt_event_record(&seg_done.back(), h->copy_stream);
         return PB_OK;
     };
-    const int first_bins = 4 * NB / 32;                              // ~ what uploads while the host plans
+    const int first_bins = 2 * NB / 32;                              // ~ what uploads while the host plans
     if (on_device) seg_end.push_back(pcm_len);
     else { rc = enqueue_upload(0, segmented ? bin_edge(first_bins) : pcm_len); if (rc != PB_OK) return rc; }
     if (do_pitch) PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
@@ -696,16 +696,24 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         return r;
     };
     // units -> segments, descriptors into pinned staging, descriptors to the device (the segments are final by now)
-    auto stage_upload_pitch = [&]() -> int {
+    // round 0: every unit (one segment or all segments known); round 1: only the units of the first segment (the others
+    // are not cut yet); round 2: the rest.  Descriptors already on the device are not uploaded again.
+    size_t su_sent = 0, sp_sent = 0;
+    auto stage_upload_pitch = [&](int round) -> int {
         const int n_seg = (int)seg_end.size();
         if (pids.size() < (size_t)n_seg) pids.resize((size_t)n_seg);
-        for (auto& v : pids) v.clear();
-        pl.assign((size_t)n_seg, std::vector<PitchLaunch>());
+        if (pl.size() < (size_t)n_seg) pl.resize((size_t)n_seg);
+        for (int s = (round == 2 ? 1 : 0); s < n_seg; s++) pids[(size_t)s].clear();
         std::vector<int64_t> seg_frames((size_t)n_seg, 0);
         size_t n_pok = 0;
         for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0) {
-            const int s = seg_of(u->file_off[i] + u->file_nx[i]);
-            pids[(size_t)s].push_back(i); seg_frames[(size_t)s] += bp.pplan[(size_t)i].n_frames; n_pok++;
+            n_pok++;
+            const int64_t need = u->file_off[i] + u->file_nx[i];
+            const bool in_first = need <= seg_end[0];
+            if (round == 1 && !in_first) continue;
+            if (round == 2 && in_first) continue;
+            const int s = seg_of(need);
+            pids[(size_t)s].push_back(i); seg_frames[(size_t)s] += bp.pplan[(size_t)i].n_frames;
         }
         // per-frame outputs follow the caller's unit order (the layout pb_pitch_plan reports)
         if (want_frames) {
@@ -714,20 +722,24 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
             for (int64_t i = 0; i < n; i++) { frame_off[(size_t)i] = acc; if (bp.pclass[(size_t)i] >= 0) acc += bp.pplan[(size_t)i].n_frames; }
             frame_off[(size_t)n] = acc;
         }
-        const size_t T = (size_t)*std::max_element(seg_frames.begin(), seg_frames.end());
+        // frame arrays are shared by the segments (stream order); when the cuts are not known yet, size them for everything
+        const size_t T = round == 0 ? (size_t)*std::max_element(seg_frames.begin(), seg_frames.end()) : (size_t)bp.total_frames;
         const size_t mc = (size_t)(bp.max_cand > 0 ? bp.max_cand : 1);
-        if (n_pok) PB_CKMEM(h->cand_f.ensure(T * mc * 4) || h->cand_s.ensure(T * mc * 4) || h->ncand.ensure(T) || h->inten.ensure(T * 4) ||
-                            h->psi.ensure(T * mc) || h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4) ||
-                            h->stage_units.ensure(n_pok * sizeof(PbUnitDev) + 16) || h->units.ensure(n_pok * sizeof(PbUnitDev) + 16) ||
-                            h->stage_pairs.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4 + 16) ||
-                            h->pair_off.ensure((n_pok + (size_t)n_seg * bp.classes.size() + 1) * 4 + 16), "pitch buffers");
-        for (int s = 0; s < n_seg; s++) {
+        const size_t n_groups = 16 * bp.classes.size() + 4;           // launch groups (segments x classes) + alignment slack
+        if (n_pok && round != 2)
+            PB_CKMEM(h->cand_f.ensure(T * mc * 4) || h->cand_s.ensure(T * mc * 4) || h->ncand.ensure(T) || h->inten.ensure(T * 4) ||
+                     h->psi.ensure(T * mc) || h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4) ||
+                     h->stage_units.ensure(n_pok * sizeof(PbUnitDev) + 16) || h->units.ensure(n_pok * sizeof(PbUnitDev) + 16) ||
+                     h->stage_pairs.ensure((n_pok + n_groups) * 4 + 16) || h->pair_off.ensure((n_pok + n_groups) * 4 + 16), "pitch buffers");
+        for (int s = (round == 2 ? 1 : 0); s < (round == 1 ? 1 : n_seg); s++) {
             int r = stage_pitch(h, u, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr, pl[(size_t)s]);
             if (r != PB_OK) return r;
         }
+        h->sp_off = (h->sp_off + 3) & ~(size_t)3;                     // keep the next round's upload 16-byte aligned
         lap("stage_pitch");
-        upload(h->units.p, h->stage_units.p, h->su_off * sizeof(PbUnitDev));
-        upload(h->pair_off.p, h->stage_pairs.p, h->sp_off * 4);
+        upload((char*)h->units.p + su_sent * sizeof(PbUnitDev), (const char*)h->stage_units.p + su_sent * sizeof(PbUnitDev), (h->su_off - su_sent) * sizeof(PbUnitDev));
+        upload((char*)h->pair_off.p + sp_sent * 4, (const char*)h->stage_pairs.p + sp_sent * 4, (h->sp_off - sp_sent) * 4);
+        su_sent = h->su_off; sp_sent = h->sp_off;
         return PB_OK;
     };
     auto stage_upload_lufs = [&]() -> int {
@@ -760,21 +772,27 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     if (!segmented) {
         // one segment: pitch descriptors up and pitch kernels running before the loudness units are planned
         if (do_pitch) {
-            if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch()) != PB_OK) return rc;
+            if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch(0)) != PB_OK) return rc;
             if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
             for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
             pitch_launched = true;
         }
         if (do_lufs && ((rc = plan_lufs_units()) != PB_OK || (rc = stage_upload_lufs()) != PB_OK)) return rc;
     } else {
-        // Both plans first (the first segment is uploading meanwhile), then cut the rest of the buffer by PLANNED work:
+        // The pitch units of the first segment are planned, staged and launched as soon as that segment has landed; the
+        // loudness plan and everything below happen while they run.  The rest of the buffer is then cut by PLANNED work:
         // a kernel can only start when its segment has landed, so the last segment should carry little work (it lands
         // when the upload ends) and the ones before it similar amounts (fewer, fuller launches than a fixed grid of cuts).
-        if (do_pitch && (rc = plan_pitch_units()) != PB_OK) return rc;
+        if (do_pitch) {
+            if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch(1)) != PB_OK) return rc;
+            PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
+            for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
+            pl[0].clear();
+        }
         if (do_lufs && (rc = plan_lufs_units()) != PB_OK) return rc;
         std::vector<double> work((size_t)NB, 0.0);               // estimated GPU milliseconds per bin (measured rates)
         auto bin_of = [&](int64_t need_end) { int64_t b = need_end > 0 ? ((need_end - 1) * NB) / pcm_len : 0; return (size_t)(b >= NB ? NB - 1 : b); };
-        if (do_pitch) for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0)
+        if (do_pitch) for (int64_t i = 0; i < n; i++) if (bp.pclass[(size_t)i] >= 0 && u->file_off[i] + u->file_nx[i] > seg_end[0])
             work[bin_of(u->file_off[i] + u->file_nx[i])] += 5.2e-6 * (double)bp.pplan[(size_t)i].n_frames;
         for (size_t k = 0; k < bp.lunits.size(); k++)
             work[bin_of(bp.lneed[k])] += 2.6e-9 * (double)(bp.lunits[k].b - bp.lunits[k].a + bp.lunits[k].npad);
@@ -797,7 +815,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
           if (tail > last) { rc = enqueue_upload(bin_edge(last), bin_edge(tail)); if (rc != PB_OK) return rc; }
           if (tail < NB) { rc = enqueue_upload(bin_edge(tail), pcm_len); if (rc != PB_OK) return rc; } }
         lap("segments");
-        if (do_pitch && (rc = stage_upload_pitch()) != PB_OK) return rc;
+        if (do_pitch && (rc = stage_upload_pitch(2)) != PB_OK) return rc;
         if (do_lufs && (rc = stage_upload_lufs()) != PB_OK) return rc;
     }
     const int n_seg = (int)seg_end.size();
