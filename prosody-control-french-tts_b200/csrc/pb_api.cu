@@ -783,11 +783,14 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         // loudness plan and everything below happen while they run.  The rest of the buffer is then cut by PLANNED work:
         // a kernel can only start when its segment has landed, so the last segment should carry little work (it lands
         // when the upload ends) and the ones before it similar amounts (fewer, fuller launches than a fixed grid of cuts).
+        double t_first_launch_ms = 0.0, work_first_ms = 0.0;
         if (do_pitch) {
             if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch(1)) != PB_OK) return rc;
             PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
             for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
             pl[0].clear();
+            t_first_launch_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
+            for (int64_t i : pids[0]) work_first_ms += 5.2e-6 * (double)bp.pplan[(size_t)i].n_frames;
         }
         if (do_lufs && (rc = plan_lufs_units()) != PB_OK) return rc;
         std::vector<double> work((size_t)NB, 0.0);               // estimated GPU milliseconds per bin (measured rates)
@@ -800,20 +803,21 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         int tail = NB;                                           // the last segment: the longest suffix with little work
         { double sfx = 0.0; const double budget = std::max(3.0, 0.05 * total);
           while (tail > first_bins + 1 && sfx + work[(size_t)tail - 1] <= budget) { sfx += work[(size_t)tail - 1]; tail--; } }
+        // Between the first and the last segment: every cut goes as far as the upload will have got by the time the GPU
+        // runs out of the work it already has (a simulation with the measured rates), at least 1/16 of the buffer each.
         const double ms_per_bin = (double)pcm_bytes / NB / 55e6;     // ~55 GB/s pinned host -> device
-        int pieces = (int)std::ceil((tail - first_bins) * ms_per_bin / 14.0);
-        pieces = std::max(1, std::min(4, pieces));
-        double mid = 0.0; for (int b = first_bins; b < tail; b++) mid += work[(size_t)b];
-        { double acc = 0.0; int cut = 1, last = first_bins;
-          for (int b = first_bins; b < tail; b++) {
-              acc += work[(size_t)b];
-              if (cut < pieces && acc >= mid * cut / pieces && b + 1 > last && b + 1 < tail) {
-                  rc = enqueue_upload(bin_edge(last), bin_edge(b + 1)); if (rc != PB_OK) return rc;
-                  last = b + 1; cut++;
-              }
-          }
-          if (tail > last) { rc = enqueue_upload(bin_edge(last), bin_edge(tail)); if (rc != PB_OK) return rc; }
-          if (tail < NB) { rc = enqueue_upload(bin_edge(tail), pcm_len); if (rc != PB_OK) return rc; } }
+        const int min_bins = NB / 16;
+        double t_free = std::max(t_first_launch_ms, first_bins * ms_per_bin) + work_first_ms;   // when the GPU has drained segment 0
+        for (int last = first_bins; last < tail;) {
+            int e = std::min(tail, last + min_bins);
+            while (e < tail && (e + 1) * ms_per_bin <= t_free) e++;
+            if (tail - e < min_bins) e = tail;
+            rc = enqueue_upload(bin_edge(last), bin_edge(e)); if (rc != PB_OK) return rc;
+            double w = 0.0; for (int b = last; b < e; b++) w += work[(size_t)b];
+            t_free = std::max(t_free, e * ms_per_bin) + w;
+            last = e;
+        }
+        if (tail < NB) { rc = enqueue_upload(bin_edge(tail), pcm_len); if (rc != PB_OK) return rc; }
         lap("segments");
         if (do_pitch && (rc = stage_upload_pitch(2)) != PB_OK) return rc;
         if (do_lufs && (rc = stage_upload_lufs()) != PB_OK) return rc;
