@@ -61,7 +61,9 @@ pb_pitch_path_kernel(const PbUnitDev* __restrict__ units, PbPitchGeomDev gm, con
             const int voiced = fr_d > 0.0 && fr_d < gm.ceiling;
             double us = gm.silence_threshold <= 0.0 ? 0.0 : 2.0 - (double)inten * us_scale;
             us = gm.voicing_threshold + (us > 0.0 ? us : 0.0);
-            const double l2 = voiced ? log2(fr_d) : 0.0;
+            // the candidate frequencies are float32 (relative error ~1e-4 against Praat's): a float32 log2 (error ~1e-7) costs
+            // a tenth of the software float64 one and changes no decision
+            const double l2 = voiced ? (double)log2f(cf) : 0.0;
             const double local = voiced ? (double)cs - gm.octave_cost_d * (l2_ceiling - l2) : us;
             double best = local; int place = 0;
             if (f > 0) {

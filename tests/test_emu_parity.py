@@ -118,3 +118,28 @@ def test_emulated_silence_split_matches_oracle(emu, oracle):
                 assert r["n_samples"][lo + k] + r["n_pad"][lo + k] == len(seg)
                 a = r["first_sample"][lo + k]
                 assert np.array_equal(x[a:a + r["n_samples"][lo + k]], seg[:r["n_samples"][lo + k]])
+
+
+def test_emulated_empty_and_degenerate_batches(emu):
+    """Every batched entry point with nothing to do, with empty files and with units it must refuse."""
+    import prosody_b200 as pb
+    from prosody_b200 import legacy
+    none = pb.Units.from_list([])
+    pcm = np.zeros(16, np.int16)
+    r = emu.extract(pcm, none)
+    assert len(r["median_f0"]) == 0 and len(r["lufs"]) == 0
+    assert len(emu.intensity(pcm, none)["intensity_db"]) == 0
+    assert len(legacy.loudness_segments(emu, pcm, none)) == 0 and len(legacy.pitch_segments(emu, pcm, none)) == 0
+    s = emu.split_on_silence(pcm, none)
+    assert list(s["seg_off"]) == [0] and len(s["start_ms"]) == 0
+    empty_file = pb.Units.from_list([(0, 0, 16000, 0.0, None), (0, 16, 16000, 0.0, None)])
+    s = emu.split_on_silence(pcm, empty_file, 1000, -50, 300)
+    assert list(s["seg_off"]) == [0, 1, 2]                   # shorter than the window: one (possibly empty) segment per file
+    assert list(zip(s["start_ms"], s["end_ms"])) == [(0, 0), (0, 1)]
+    r = emu.extract(pcm, empty_file)
+    assert list(r["status"] & 3) == [1, 1] and list(r["n_frames"]) == [0, 0]      # Praat refuses both (too short)
+    sliced = pb.Units.from_list([(0, 16, 16000, 0.0, 0.001)])
+    import pytest
+    with pytest.raises(pb._native.NativeError):
+        emu.split_on_silence(pcm, sliced)                     # whole files only
+    assert list(emu.intensity(pcm, sliced)["status"]) == [64]
