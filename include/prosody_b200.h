@@ -200,6 +200,21 @@ int pb_segment_baselines(int64_t n, const double* p_nat, const double* l_nat, co
 /* EMA over all rows then the forward jump clamp (Code/audioPipeline.py:593-602). out may alias x. */
 int pb_ema_clamp(const double* x, int64_t n, double alpha, double max_jump, double* out);
 
+/* ---- aggregation of per-frame tracks over word / syntagme intervals (the "interval reduction" of the path) */
+
+/* Frame times of the pitch analysis of every unit: frame k of unit i sits at t_first[i] + k * dt[i] (host only). */
+int pb_pitch_frame_times(const PbPitchParams* p, const PbUnits* u, double* t_first, double* dt);
+
+/* Segmented reduction on the GPU.  Series s (e.g. the per-frame f0 of unit s from pb_median_pitch_batch) occupies
+ * [frame_off[s], frame_off[s+1]) of f0 / track2; interval j takes the frames of series iv_series[j] whose time lies in
+ * [iv_tmin[j], iv_tmax[j]] (Praat's Sampled_getWindowSamples rule, float64).  Outputs per interval: n_frames, n_voiced
+ * (f0 > 0), np.median and mean of the voiced f0 (0.0 when none, like get_median_pitch), mean of track2 (intensity; may be
+ * NULL together with mean_track2).  tracks_on_device: f0 / track2 are device pointers. */
+int pb_reduce_intervals(PbHandle* h, int64_t n_series, const int64_t* frame_off, const double* t_first, const double* dt,
+                        const float* f0, const float* track2, int tracks_on_device,
+                        int64_t n_intervals, const int64_t* iv_series, const double* iv_tmin, const double* iv_tmax,
+                        int32_t* n_frames, int32_t* n_voiced, double* median_f0, double* mean_f0, double* mean_track2);
+
 /* ---- TextGrid input at corpus scale (host only, no handle): one tier of many files, parsed on host threads.
  * Replaces per-file `textgrid.TextGrid.fromFile(path)[0]` (Code/Preprocessing/gen_break_ssml.py:19-26).
  * status per file: 0 ok, 1 unreadable, 2 not a TextGrid / truncated, 3 no such tier.  pb_textgrid_copy fills caller

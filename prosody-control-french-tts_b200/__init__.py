@@ -7,6 +7,6 @@ hi-paris/Prosody-Control-French-TTS (AudioPipeline.measure_prosody_and_build_ssm
     build      nvcc build of the library (in-tree)
 """
 from . import _native
-from .batch import Extractor, Units, intensity_plan, part_durations, pitch_params, pitch_plan
+from .batch import Extractor, Units, intensity_plan, part_durations, pitch_frame_times, pitch_params, pitch_plan
 
-__all__ = ["Extractor", "Units", "pitch_params", "pitch_plan", "part_durations", "intensity_plan", "_native"]
+__all__ = ["Extractor", "Units", "pitch_params", "pitch_plan", "part_durations", "intensity_plan", "pitch_frame_times", "_native"]

@@ -51,7 +51,7 @@ EXPORTS = ["pb_syntagme_deltas", "pb_ema_clamp", "pb_abi_version", "pb_create", 
            "pb_device_info", "pb_pitch_params_default", "pb_pitch_plan", "pb_median_pitch_batch", "pb_lufs_batch",
            "pb_part_duration_batch", "pb_extract_batch", "pb_intensity_plan", "pb_intensity_batch", "pb_legacy_loudness_batch", "pb_split_on_silence_bound",
            "pb_split_on_silence_batch", "pb_segment_baselines", "pb_textgrid_parse_files",
-           "pb_textgrid_sizes", "pb_textgrid_copy", "pb_textgrid_free"]
+           "pb_textgrid_sizes", "pb_textgrid_copy", "pb_textgrid_free", "pb_pitch_frame_times", "pb_reduce_intervals"]
 
 
 def bind(lib: C.CDLL) -> C.CDLL:
@@ -81,6 +81,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.pb_textgrid_sizes.argtypes = [vp, i64p, i64p, i64p]
     lib.pb_textgrid_copy.argtypes = [vp, i32p, dp, dp, i64p, dp, dp, i64p, C.c_char_p]
     lib.pb_textgrid_free.argtypes = [vp]; lib.pb_textgrid_free.restype = None
+    lib.pb_pitch_frame_times.argtypes = [P, U, dp, dp]
+    lib.pb_reduce_intervals.argtypes = [vp, C.c_int64, i64p, dp, dp, vp, vp, C.c_int, C.c_int64, i64p, dp, dp, i32p, i32p, dp, dp, dp]
     lib.pb_ema_clamp.argtypes = [dp, C.c_int64, C.c_double, C.c_double, dp]
     for name in EXPORTS:
         if name not in ("pb_destroy", "pb_last_error", "pb_pitch_params_default", "pb_split_on_silence_bound", "pb_textgrid_free"):

@@ -251,6 +251,55 @@ class Extractor:
         return dict(seg_off=so, start_ms=s_ms[:m], end_ms=e_ms[:m], first_sample=first[:m], n_samples=ns[:m], n_pad=npad[:m])
 
 
+    def reduce_intervals(self, frame_off, t_first, dt, f0, intervals, track2=None) -> dict:
+        """Per-frame tracks -> per-interval statistics on the GPU (pb_reduce_intervals).
+        frame_off / t_first / dt describe the series (e.g. from median_pitch(frames=True) and pitch_frame_times);
+        intervals = (series index, tmin, tmax) arrays or a list of such triples; f0 / track2 numpy float32 or CUDA tensors."""
+        if isinstance(intervals, (list, tuple)) and len(intervals) and not isinstance(intervals[0], np.ndarray):
+            intervals = tuple(np.asarray(c) for c in zip(*intervals)) if len(intervals) else (np.zeros(0, np.int64),) * 3
+        ser = np.ascontiguousarray(intervals[0], np.int64); tmin = np.ascontiguousarray(intervals[1], np.float64)
+        tmax = np.ascontiguousarray(intervals[2], np.float64)
+        fo = np.ascontiguousarray(frame_off, np.int64); tf = np.ascontiguousarray(t_first, np.float64); dd = np.ascontiguousarray(dt, np.float64)
+        on_dev = 0
+        keep = []
+
+        def ptr(a):
+            nonlocal on_dev
+            if a is None:
+                return None
+            if isinstance(a, np.ndarray):
+                a = np.ascontiguousarray(a, np.float32); keep.append(a)
+                return C.c_void_p(a.ctypes.data)
+            import torch
+            a = a.contiguous()
+            if a.dtype != torch.float32:
+                raise TypeError("tracks must be float32")
+            if a.is_cuda:
+                torch.cuda.current_stream(a.device).synchronize(); on_dev = 1
+            keep.append(a)
+            return C.c_void_p(a.data_ptr())
+
+        p_f0, p_t2 = ptr(f0), ptr(track2)
+        m = len(ser)
+        nf = np.zeros(m, np.int32); nv = np.zeros(m, np.int32); med = np.zeros(m); mean = np.zeros(m); m2 = np.zeros(m)
+        rc = self._lib.pb_reduce_intervals(self._h, len(fo) - 1, _ptr(fo, C.c_int64), _ptr(tf, C.c_double), _ptr(dd, C.c_double), p_f0, p_t2, on_dev,
+                                           m, _ptr(ser, C.c_int64), _ptr(tmin, C.c_double), _ptr(tmax, C.c_double), _ptr(nf, C.c_int32),
+                                           _ptr(nv, C.c_int32), _ptr(med, C.c_double), _ptr(mean, C.c_double), _ptr(m2, C.c_double) if track2 is not None else None)
+        N.check(self._lib, self._h, rc, "pb_reduce_intervals")
+        return dict(n_frames=nf, n_voiced=nv, median_f0=med, mean_f0=mean, mean_track2=m2 if track2 is not None else None)
+
+
+def pitch_frame_times(units: Units, params: N.PbPitchParams | None = None, lib=None):
+    """Host-only: (t_first, dt) of the pitch frames of every unit."""
+    lib = lib if lib is not None else N.load()
+    params = params or pitch_params()
+    n = len(units)
+    t1 = np.zeros(n); dt = np.zeros(n)
+    cu = units.c_struct()
+    N.check(lib, None, lib.pb_pitch_frame_times(C.byref(params), C.byref(cu), _ptr(t1, C.c_double), _ptr(dt, C.c_double)), "pb_pitch_frame_times")
+    return t1, dt
+
+
 def intensity_plan(units: Units, minimum_pitch: float = 100.0, time_step: float = 0.0, lib=None):
     """Host-only: (status, n_frames, frame_off, t_first, dt) of Praat's Sound_to_Intensity per whole-file unit."""
     lib = lib if lib is not None else N.load()

@@ -14,6 +14,7 @@
 #include "pb_pitch_path.cuh"
 #include "pb_lufs.cuh"
 #include "pb_silence.cuh"
+#include "pb_intervals.cuh"
 
 // descriptors: pinned host staging -> device, read by the SMs over PCIe (does not queue behind the PCM in the copy engine)
 __global__ void pb_copy16_kernel(const int4* __restrict__ src, int4* __restrict__ dst, long long n16) {

@@ -143,3 +143,45 @@ def test_emulated_empty_and_degenerate_batches(emu):
     with pytest.raises(pb._native.NativeError):
         emu.split_on_silence(pcm, sliced)                     # whole files only
     assert list(emu.intensity(pcm, sliced)["status"]) == [64]
+
+
+def _reduce_ref(frame_off, t_first, dt, f0, t2, intervals):
+    """numpy restatement of pb_reduce_intervals (Praat window rule, np.median / np.mean of the voiced frames)."""
+    out = []
+    for s, a, b in intervals:
+        v = f0[frame_off[s]:frame_off[s + 1]]; w = t2[frame_off[s]:frame_off[s + 1]]
+        nf = len(v)
+        k0 = int(min(max(math.ceil((a - t_first[s]) / dt[s]), 0), nf)) if nf else 0
+        k1 = int(min(max(math.floor((b - t_first[s]) / dt[s]), -1), nf - 1)) if nf else -1
+        if b < a or k1 < k0:
+            out.append((0, 0, 0.0, 0.0, 0.0)); continue
+        seg = v[k0:k1 + 1].astype(np.float64); voiced = seg[seg > 0]
+        out.append((len(seg), len(voiced), float(np.median(voiced)) if len(voiced) else 0.0,
+                    float(np.mean(voiced)) if len(voiced) else 0.0, float(np.mean(w[k0:k1 + 1].astype(np.float64)))))
+    return out
+
+
+def test_emulated_interval_reduction_matches_numpy(emu, oracle):
+    import prosody_b200 as pb
+    sr = 16000
+    x = speechlike(3, 1.0, sr, seed=12)
+    n = x.shape[1]
+    units = pb.Units.from_list([(i * n, n, sr, 0.0, None) for i in range(3)] + [(0, n, sr, 0.2, 0.9)])
+    p = pb.pitch_params(75.0, 600.0)
+    r = emu.median_pitch(x.reshape(-1), units, p, frames=True)
+    t_first, dt = pb.pitch_frame_times(units, p)
+    for i, (t0, t1) in enumerate(((0.0, None), (0.0, None), (0.0, None), (0.2, 0.9))):
+        g = oracle.pitch_track(x[i % 3 if i < 3 else 0], sr, t0, t1, params=oracle.pitch_params(75.0, 600.0))
+        assert abs(t_first[i] - g["t1"]) < 1e-12 and abs(dt[i] - g["dt"]) < 1e-15
+    rng = np.random.default_rng(2)
+    ivs = [(int(rng.integers(0, 4)), float(a), float(a + rng.uniform(0.0, 0.5))) for a in rng.uniform(-0.1, 1.0, 60)]
+    ivs += [(0, 0.0, 1.0), (1, 0.5, 0.4), (2, 5.0, 6.0), (3, 0.2, 0.9), (0, t_first[0], t_first[0])]
+    got = emu.reduce_intervals(r["frame_off"], t_first, dt, r["frame_f0"], ivs, track2=r["frame_intensity"])
+    ref = _reduce_ref(r["frame_off"], t_first, dt, r["frame_f0"], r["frame_intensity"], ivs)
+    for j, (nf, nv, med, mean, m2) in enumerate(ref):
+        assert got["n_frames"][j] == nf and got["n_voiced"][j] == nv, (j, ivs[j])
+        assert got["median_f0"][j] == med
+        assert abs(got["mean_f0"][j] - mean) <= 1e-12 * max(1.0, abs(mean)) and abs(got["mean_track2"][j] - m2) <= 1e-12
+    # the whole-unit interval reproduces get_median_pitch
+    whole = emu.reduce_intervals(r["frame_off"], t_first, dt, r["frame_f0"], [(i, -1.0, 99.0) for i in range(4)])
+    assert np.array_equal(whole["median_f0"], r["median_f0"]) and np.array_equal(whole["n_voiced"], r["n_voiced"])

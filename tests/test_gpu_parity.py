@@ -420,3 +420,33 @@ def test_segmented_host_upload_matches_resident_pcm(gpu_extractor):
         assert np.array_equal(r_dev[k], r_host[k], equal_nan=True), k
         assert np.array_equal(r_dev[k], r_np[k], equal_nan=True), k
     assert (r_dev["n_voiced"] > 0).mean() > 0.5
+
+
+def test_interval_reduction_on_word_grids(gpu_extractor):
+    """K6: per-frame F0 / intensity reduced over word intervals (device-resident tracks and host tracks), against numpy;
+    whole-unit intervals must reproduce the units' own medians."""
+    import torch
+    import prosody_b200 as pb
+    from prosody_b200 import synth
+    from test_emu_parity import _reduce_ref
+    sr, dur, n_utt = 16000, 5.0, 64
+    pcm = synth.make_corpus(n_utt, dur, sr, seed=31, device="cuda")
+    n = pcm.shape[1]
+    units = pb.Units.from_list([(i * n, n, sr, 0.0, None) for i in range(n_utt)])
+    p = pb.pitch_params(75.0, 600.0)
+    r = gpu_extractor.median_pitch(pcm.reshape(-1), units, p, frames=True)
+    t_first, dt = pb.pitch_frame_times(units, p)
+    grids = synth.make_word_grid(n_utt, dur, seed=31)
+    ivs = [(i, a, b) for i, g in enumerate(grids) for (a, b, mark) in g if mark.strip()]
+    ivs += [(i, -1.0, 99.0) for i in range(n_utt)]
+    got = gpu_extractor.reduce_intervals(r["frame_off"], t_first, dt, r["frame_f0"], ivs, track2=r["frame_intensity"])
+    dev = gpu_extractor.reduce_intervals(r["frame_off"], t_first, dt, torch.from_numpy(r["frame_f0"]).cuda(), ivs,
+                                         track2=torch.from_numpy(r["frame_intensity"]).cuda())
+    for k in ("n_frames", "n_voiced", "median_f0", "mean_f0", "mean_track2"):
+        assert np.array_equal(got[k], dev[k]), k
+    ref = _reduce_ref(r["frame_off"], t_first, dt, r["frame_f0"], r["frame_intensity"], ivs)
+    for j, (nf, nv, med, mean, m2) in enumerate(ref):
+        assert got["n_frames"][j] == nf and got["n_voiced"][j] == nv and got["median_f0"][j] == med
+        assert abs(got["mean_f0"][j] - mean) <= 1e-12 * max(1.0, abs(mean)) and abs(got["mean_track2"][j] - m2) <= 1e-12
+    assert np.array_equal(got["median_f0"][-n_utt:], r["median_f0"]) and np.array_equal(got["n_voiced"][-n_utt:], r["n_voiced"])
+    assert len(ivs) > 500 and (got["n_voiced"][:-n_utt] > 0).mean() > 0.3
