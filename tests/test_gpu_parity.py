@@ -450,3 +450,43 @@ def test_interval_reduction_on_word_grids(gpu_extractor):
         assert abs(got["mean_f0"][j] - mean) <= 1e-12 * max(1.0, abs(mean)) and abs(got["mean_track2"][j] - m2) <= 1e-12
     assert np.array_equal(got["median_f0"][-n_utt:], r["median_f0"]) and np.array_equal(got["n_voiced"][-n_utt:], r["n_voiced"])
     assert len(ivs) > 500 and (got["n_voiced"][:-n_utt] > 0).mean() > 0.3
+
+
+def test_config4_one_hour_recording(gpu_extractor, oracle):
+    """BASELINE config 4: a 1-hour 22.05 kHz recording (a) unsegmented through the path finder — 359 997 frames in one
+    Viterbi chain — and (b) segmented on the GPU (split_on_silence 1000 / -50 / 300), every segment analysed as its own file
+    exactly as the reference does after writing segment_ph{i}.wav; checked against the oracle."""
+    import prosody_b200 as pb
+    from prosody_b200 import synth
+    sr = 22050
+    pcm = synth.make_corpus(720, 5.0, sr, seed=3456, device="cuda")            # 720 x 5 s = 1 h
+    x = pcm.reshape(-1).clone()
+    n = x.numel()
+    t = np.arange(0, 3600, 19.0)
+    for k, a in enumerate(t[1:]):                                              # a pause every 19 s, 1.1 .. 2.3 s long
+        i0 = int(a * sr); i1 = i0 + int((1.1 + 0.1 * (k % 13)) * sr)
+        x[i0:i1] = (x[i0:i1].float() * 0.004).to(x.dtype)
+    host = x.cpu().numpy()
+    whole = pb.Units.from_list([(0, n, sr, 0.0, None, float(sr))])
+    p = pb.pitch_params(75.0, 600.0)
+    r = gpu_extractor.median_pitch(x, whole, p, frames=True)
+    o = oracle.pitch_track(host, sr, params=oracle.pitch_params(75.0, 600.0))
+    assert r["n_frames"][0] == o["n_frames"] == 359997
+    agree, rel = compare_tracks(r["frame_f0"], o["frequency"])
+    assert agree >= VOICING_AGREE and rel < F0_TOL, (agree, rel)
+    assert abs(r["median_f0"][0] - o["median"]) / o["median"] < F0_TOL
+    # (b) segmentation, then per-segment analysis
+    s = gpu_extractor.split_on_silence(x, whole, 1000, -50, 300)
+    ref = oracle.split_on_silence(host, sr, 1000, -50, 300)
+    got = list(zip(s["start_ms"].tolist(), s["end_ms"].tolist()))
+    assert got == ref and len(ref) == len(t)
+    seg_units = pb.Units.from_list([(int(a), int(m), sr, 0.0, None, float(sr)) for a, m in zip(s["first_sample"], s["n_samples"])])
+    e = gpu_extractor.extract(x, seg_units, p)
+    assert np.all(e["status"] == 0) and e["n_frames"].sum() > 300000
+    for k in (0, 7, len(ref) // 2, len(ref) - 1):
+        a, m = int(s["first_sample"][k]), int(s["n_samples"][k])
+        seg = host[a:a + m]
+        med = oracle.median_pitch(seg, sr, 0.0, None, 75.0, 600.0)
+        assert abs(e["median_f0"][k] - med) <= F0_TOL * max(med, 1.0)
+        assert abs(e["lufs"][k] - oracle.lufs(seg, sr, float(sr))) < 1e-9
+        assert e["duration_s"][k] == oracle.part_duration(m, sr, 0.0, None)
