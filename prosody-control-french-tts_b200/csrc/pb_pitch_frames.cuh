@@ -113,29 +113,24 @@ __device__ PB_NOINLINE int pb_candidates_overflow(const float* __restrict__ r, f
 // [i-1, i+1] and the four evaluations may sit on another bump than the one Praat's Brent search ends on (measured on a
 // 1-hour recording: 4 of 250 000 voiced frames, F0 off by up to 0.6 %).  Those candidates — about 0.5 % — get the real
 // thing: golden-section / parabolic minimisation of -y(x) over [i-1, i+1] (Brent 1973, the routine Praat calls), to a
-// lag tolerance of 2e-4 samples, one sinc evaluation per step by the candidate's lane group.  `active` selects the
-// groups that take part; the others ride along with depth 0.
-__device__ PB_NOINLINE void pb_brent_refine(const float* __restrict__ r, int B, float fi, int depth, bool active, int sl, int nl,
-                                            float* bx, float* by) {
-    const float golden = 0.38196601125f, tol = 2.0e-4f;
+// lag tolerance of 1e-3 samples (4e-5 relative at the shortest refined lag), one candidate at a time with all 32 lanes on
+// each sinc evaluation.
+__device__ PB_NOINLINE void pb_brent_refine(const float* __restrict__ r, int B, float fi, int depth, int lane, float* bx, float* by) {
+    const float golden = 0.38196601125f, tol = 1.0e-3f;
     float a = fi - 1.0f, b = fi + 1.0f;
     float t = a + golden * (b - a);
     float x = t, v = t, w = t, fx = 0.0f, fv = 0.0f, fw = 0.0f;
-    bool done = !active, first = true;
-    for (int iter = 0; iter < 48; iter++) {
-        const float ft = -pb_sinc8(r, B, t, done ? 0 : depth, sl, nl);
-        if (first) { fx = fv = fw = ft; first = false; }
-        else if (!done) {
-            if (ft <= fx) { if (t < x) b = x; else a = x; v = w; w = x; x = t; fv = fw; fw = fx; fx = ft; }
-            else {
-                if (t < x) a = t; else b = t;
-                if (ft <= fw || w == x) { v = w; w = t; fv = fw; fw = ft; }
-                else if (ft <= fv || v == x || v == w) { v = t; fv = ft; }
-            }
+    for (int iter = 0; iter < 32; iter++) {                   // every lane carries the same state: the loop is warp-uniform
+        const float ft = -pb_sinc8(r, B, t, depth, lane, 32);
+        if (iter == 0) { fx = fv = fw = ft; }
+        else if (ft <= fx) { if (t < x) b = x; else a = x; v = w; w = x; x = t; fv = fw; fw = fx; fx = ft; }
+        else {
+            if (t < x) a = t; else b = t;
+            if (ft <= fw || w == x) { v = w; w = t; fv = fw; fw = ft; }
+            else if (ft <= fv || v == x || v == w) { v = t; fv = ft; }
         }
         const float range = b - a, mid = 0.5f * (a + b);
-        if (fabsf(x - mid) + 0.5f * range <= 2.0f * tol) done = true;
-        if (__all_sync(PB_FULL_MASK, done)) break;
+        if (fabsf(x - mid) + 0.5f * range <= 2.0f * tol) break;
         float step = golden * (x < mid ? b - x : a - x);
         if (fabsf(x - w) >= tol) {
             const float tt = (x - w) * (fx - fv);
@@ -148,7 +143,7 @@ __device__ PB_NOINLINE void pb_brent_refine(const float* __restrict__ r, int B, 
         if (fabsf(step) < tol) step = step > 0.0f ? tol : -tol;
         t = x + step;
     }
-    if (active) { *bx = x; *by = -fx; }
+    *bx = x; *by = -fx;
 }
 
 // ------------------------------------------------------------------------------------------------ candidates of one frame
@@ -257,7 +252,12 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
         if (y1 > by) { bx = x1; by = y1; }
         const bool flat = have && depth > 0 && !(by > yc);      // no vertex beat the best grid point: not a parabola-shaped peak
         if (yc > by) { bx = xc; by = yc; }
-        if (__any_sync(PB_FULL_MASK, flat)) pb_brent_refine(r, B, fi, depth, flat, sl, nl, &bx, &by);
+        for (unsigned todo = __ballot_sync(PB_FULL_MASK, flat && sl == 0); todo; todo &= todo - 1) {
+            const int src = __ffs(todo) - 1;                    // first lane of the flagged candidate's group
+            float rx, ry;
+            pb_brent_refine(r, B, __shfl_sync(PB_FULL_MASK, fi, src), __shfl_sync(PB_FULL_MASK, depth, src), lane, &rx, &ry);
+            if (lane / nl == src / nl) { bx = rx; by = ry; }
+        }
         if (by > 1.0f) by = __fdividef(1.0f, by);
         if (have && sl == 0) { out_f[c] = __fdividef(gm.sr, bx); out_s[c] = by; }
     }

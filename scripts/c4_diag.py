@@ -33,3 +33,12 @@ in_gap = [any(a <= ti <= a + 2.4 for a in t[1:]) for ti in tt]
 print("bad frames in attenuated gaps:", sum(in_gap), "of", len(bad))
 for b in bad[:12]:
     print(b, round(float(o["t1"] + b * o["dt"]), 3), fg[b], fo[b], rel[b], "strength", r["frame_strength"][b], o["strength"][b])
+s = ex.split_on_silence(x, whole, 1000, -50, 300)
+ref = oracle.split_on_silence(host, sr, 1000, -50, 300)
+got = list(zip(s["start_ms"].tolist(), s["end_ms"].tolist()))
+print("segments gpu", len(got), "oracle", len(ref), "pauses", len(t) - 1, "equal", got == ref)
+if got != ref:
+    for k, (g_, r_) in enumerate(zip(got, ref)):
+        if g_ != r_:
+            print("first diff at", k, g_, r_); break
+print(got[:3], ref[:3])

@@ -479,7 +479,7 @@ def test_config4_one_hour_recording(gpu_extractor, oracle):
     s = gpu_extractor.split_on_silence(x, whole, 1000, -50, 300)
     ref = oracle.split_on_silence(host, sr, 1000, -50, 300)
     got = list(zip(s["start_ms"].tolist(), s["end_ms"].tolist()))
-    assert got == ref and len(ref) == len(t)
+    assert got == ref and len(ref) >= len(t)          # the inserted pauses plus the corpus' own long silences
     seg_units = pb.Units.from_list([(int(a), int(m), sr, 0.0, None, float(sr)) for a, m in zip(s["first_sample"], s["n_samples"])])
     e = gpu_extractor.extract(x, seg_units, p)
     assert np.all(e["status"] == 0) and e["n_frames"].sum() > 300000
