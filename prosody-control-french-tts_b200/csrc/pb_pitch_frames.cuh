@@ -194,6 +194,8 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
     }
     // ---- refine the others on the sinc curve; the lanes are split evenly over the candidates of a round:
     //      32 lanes for a single candidate, 16 each for two, otherwise 8 each and 4 candidates per round
+    int* flagged = (int*)scratch;                       // candidates whose peak is not parabola-shaped (see pb_brent_refine)
+    int n_flagged = 0;
     const int nref = ncf - c_first;
     const int nl = nref <= 1 ? 32 : nref == 2 ? 16 : 8;
     const int per_round = 32 / nl;
@@ -252,14 +254,25 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
         if (y1 > by) { bx = x1; by = y1; }
         const bool flat = have && depth > 0 && !(by > yc);      // no vertex beat the best grid point: not a parabola-shaped peak
         if (yc > by) { bx = xc; by = yc; }
-        for (unsigned todo = __ballot_sync(PB_FULL_MASK, flat && sl == 0); todo; todo &= todo - 1) {
-            const int src = __ffs(todo) - 1;                    // first lane of the flagged candidate's group
-            float rx, ry;
-            pb_brent_refine(r, B, __shfl_sync(PB_FULL_MASK, fi, src), __shfl_sync(PB_FULL_MASK, depth, src), lane, &rx, &ry);
-            if (lane / nl == src / nl) { bx = rx; by = ry; }
+        // remember the flagged candidates (scratch words [0, PB_MAXC) are free here); they are redone after the loop, where
+        // nothing of this iteration is live across the out-of-line call
+        const unsigned fm = __ballot_sync(PB_FULL_MASK, flat && sl == 0);
+        if (fm) {
+            if (flat && sl == 0) flagged[n_flagged + __popc(fm & ((1u << lane) - 1u))] = c | (depth == 700 ? 0x100 : 0);
+            n_flagged += __popc(fm);
         }
         if (by > 1.0f) by = __fdividef(1.0f, by);
         if (have && sl == 0) { out_f[c] = __fdividef(gm.sr, bx); out_s[c] = by; }
+    }
+    if (n_flagged) {
+        __syncwarp();
+        for (int k = 0; k < n_flagged; k++) {
+            const int code = flagged[k], c = code & 0xff;
+            float bx, by;
+            pb_brent_refine(r, B, (float)imax[c], (code & 0x100) ? 700 : 70, lane, &bx, &by);
+            if (by > 1.0f) by = __fdividef(1.0f, by);
+            if (lane == 0) { out_f[c] = __fdividef(gm.sr, bx); out_s[c] = by; }
+        }
     }
 }
 
