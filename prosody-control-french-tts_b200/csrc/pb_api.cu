@@ -245,7 +245,10 @@ int get_tables(PbHandle* h, const PbGeomHost& g, PitchTables** out) {
 // fn(i0, i1) over [0, n) on a few host threads (the per-unit planning is independent float64 arithmetic)
 template <class F> void pb_parallel_for(int64_t n, int64_t grain, F fn) {
     const int64_t want = grain > 0 ? n / grain : 1;
-    const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())), want));
+    // one process per GPU shares the host with its siblings (torchrun exports LOCAL_WORLD_SIZE): split the cores
+    static const unsigned share = [] { const char* e = getenv("LOCAL_WORLD_SIZE"); const int v = e ? atoi(e) : 1; return (unsigned)(v > 1 ? v : 1); }();
+    const unsigned cores = std::max(1u, std::thread::hardware_concurrency() / share);
+    const unsigned nt = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min(16u, cores), want));
     if (nt <= 1) { fn((int64_t)0, n); return; }
     std::vector<std::thread> pool;
     const int64_t per = (n + nt - 1) / nt;

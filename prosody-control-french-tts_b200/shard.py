@@ -48,6 +48,10 @@ def gather_rows(rows, index, dst: int = 0):
     dist.gather(pad, bufs, dst=dst)
     if rank != dst:
         return None
-    allr = torch.cat([b[:n] for b, n in zip(bufs, sizes)], 0).cpu()
-    order = torch.argsort(allr[:, k].to(torch.int64), stable=True)
-    return allr[order, :k]
+    allr = torch.cat([b[:n] for b, n in zip(bufs, sizes)], 0)
+    ids = allr[:, k].to(torch.int64)
+    # rows come sorted per rank; only an interleaved partition needs the global sort (done where the data lives: on the GPU
+    # for NCCL, where a 5e5-row argsort is microseconds instead of the tens of milliseconds of a single host thread)
+    if ids.numel() > 1 and not bool((ids[1:] >= ids[:-1]).all()):
+        allr = allr[torch.argsort(ids, stable=True)]
+    return allr[:, :k].cpu()
