@@ -1,11 +1,10 @@
 // pb_silence.cuh — K5: silence detection with pydub.silence semantics.
 //
 // pydub's detect_silence slides a min_silence_len window over the audio at a 1 ms step and calls audioop.rms on every
-// slice: O(samples x window) on the CPU.  Here one CTA owns a tile of window starts: its threads square-sum the PCM into
+// slice: O(samples x window) on the CPU.  Here one CTA owns a tile of window starts: its warps square-sum the PCM into
 // one integer energy per millisecond bin (bin i = frames [int(i*rate/1000), int((i+1)*rate/1000)), pydub's own frame
-// arithmetic; 16-byte loads, dp2a squares, shared-memory atomics), a block scan turns the bins into prefix sums, and
-// every window is then one subtraction and one integer comparison.  PCM is read once (plus the window-length halo
-// between tiles): the kernel is HBM-bound.
+// arithmetic), a block scan turns the bins into prefix sums, and every window is then one subtraction and one integer
+// comparison.  PCM is read once (plus the window-length halo between tiles): the kernel is HBM-bound.
 //
 //   rms <= thresh   <=>   (unsigned) sqrt(S / n) <= floor(thresh)   <=>   S < (floor(thresh) + 1)^2 * n
 //
@@ -29,6 +28,7 @@ struct PbSilFileDev {
 };
 
 #define PB_SIL_WARPS 16
+#define PB_SIL_PADW(w) ((w) + ((w) >> 5))       // one pad word per 32: lane-strided bin reads stay (nearly) conflict-free
 
 // pydub frame_count(ms) = ms * (frame_rate / 1000.0), truncated by int(); files are < 2^31 - 2^16 samples (host check)
 __device__ __forceinline__ int pb_sil_frame32(int ms, double per_ms) { return __double2int_rz(__dmul_rn((double)ms, per_ms)); }
@@ -56,16 +56,20 @@ __device__ __forceinline__ int4 pb_sil_load_vec(const int16_t* __restrict__ pcm,
 }
 
 // tile_windows: window starts per CTA tile; the tile needs tile_windows + win_ms + 1 bins (+1 window of halo each side).
-// smem layout: u64 bins[nb_cap + 1] | u64 warp_tot[PB_SIL_WARPS] | u8 flags[tile_windows + 2]
+// smem layout: u64 bins[nb_cap + 1] | u64 warp_tot[PB_SIL_WARPS] | u8 flags[tile_windows + 2] | u32 stage[PB_SIL_WARPS][words_per_warp]
+// NV: 16-byte vectors one lane keeps in flight per 32-bin group (32 * NV * 8 samples cover 32 ms at the batch's highest rate)
+template <int NV>
 __global__ void __launch_bounds__(PB_SIL_WARPS * 32, 2)
 pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const PbSilFileDev* __restrict__ files, int n_files,
-                       long long n_tiles, int tile_windows, int win_ms, int nb_cap, long long limit_per_sample,
+                       long long n_tiles, int tile_windows, int win_ms, int nb_cap, int words_per_warp, long long limit_per_sample,
                        unsigned long long* __restrict__ run_keys, unsigned long long run_cap, unsigned long long* __restrict__ run_count) {
     PB_DYN_SMEM(smem);
     unsigned long long* bins = reinterpret_cast<unsigned long long*>(smem);
     unsigned long long* warp_tot = bins + nb_cap + 1;
     unsigned char* flags = reinterpret_cast<unsigned char*>(warp_tot + PB_SIL_WARPS);
+    uint32_t* stage_all = reinterpret_cast<uint32_t*>(flags + ((tile_windows + 2 + 15) & ~15));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* stage = stage_all + (size_t)warp * words_per_warp;
     const long long mis = (long long)((((size_t)pcm) & 15) >> 1);            // samples between the last 16-byte boundary and pcm
     const int4* __restrict__ pal = reinterpret_cast<const int4*>(pcm - mis);
 
@@ -78,61 +82,72 @@ pb_silence_runs_kernel(const int16_t* __restrict__ pcm, long long pcm_len, const
         const int base = max(j0 - 1, 0);                                      // first bin (one window of halo to the left)
         const int wend = min(j0 + jn + 1, F.n_win);                           // one past the last window whose flag we need
         const int nb = (wend - 1 + win_ms) - base;                            // bins [base, base + nb)
-        // ---- 1. per-millisecond energies.  Every thread takes 16-byte vectors (8 samples) of the tile's sample range,
-        // strided over the CTA so that a warp reads 512 contiguous bytes.  A vector lies in one bin or straddles one bin
-        // edge (bins hold >= 8 samples): its squares are summed with dp2a, whole and up to the edge, and the one or two
-        // partial sums go to the bins with shared-memory atomics on (hi, lo) int pairs.
-        int2* acc = reinterpret_cast<int2*>(bins);                            // {lo, hi} per bin while accumulating
-        for (int k = threadIdx.x; k <= nb; k += blockDim.x) acc[k] = make_int2(0, 0);
-        __syncthreads();
+        // ---- 1. per-millisecond energies: each warp stages the samples of 32 consecutive bins, each lane sums one bin.
+        // The 16-byte loads of the warp's NEXT group are issued before the current group is summed (registers q).
         {
-            const int fA = min(pb_sil_frame32(base, F.per_ms), F.nx), fB = min(pb_sil_frame32(base + nb, F.per_ms), F.nx);
-            const long long v0 = (F.pcm_off + fA + mis) >> 3, v1 = (F.pcm_off + fB + mis + 7) >> 3;
-            const double inv_per_ms = 1.0 / F.per_ms;
-            auto word_mask = [](int m2) -> uint32_t {                         // 2 sample bits -> 32-bit mask of their halves
-                return ((0u - (uint32_t)(m2 & 1)) & 0xffffu) | ((0u - (uint32_t)((m2 >> 1) & 1)) & 0xffff0000u);
+            // frames [a, b) of this lane's bin, first vector and vector count of the group
+            auto geom = [&](int gg, int& ga, int& gb, long long& gv0, int& gnvec) {
+                const int i0 = base + gg * 32, iend = min(i0 + 32, base + nb);
+                const int fa = min(pb_sil_frame32(min(i0 + lane, iend), F.per_ms), F.nx);
+                const int fB = min(pb_sil_frame32(iend, F.per_ms), F.nx);
+                int fb = __shfl_down_sync(PB_FULL_MASK, fa, 1);
+                if (lane == 31) fb = fB;
+                const int fA = __shfl_sync(PB_FULL_MASK, fa, 0);
+                ga = fa; gb = fb;
+                gv0 = (F.pcm_off + fA + mis) >> 3;
+                gnvec = (int)(((F.pcm_off + fB + mis + 7) >> 3) - gv0);
             };
-            auto masked_sum = [&](const int4& q, int m8, int& hi, int& lo) {   // squares of the samples selected by the 8 bits of m8
-                hi = 0; lo = 0;
-                if (m8 == 0xff) { pb_sil_sq2((uint32_t)q.x, hi, lo); pb_sil_sq2((uint32_t)q.y, hi, lo); pb_sil_sq2((uint32_t)q.z, hi, lo); pb_sil_sq2((uint32_t)q.w, hi, lo); }
-                else {
-                    pb_sil_sq2((uint32_t)q.x & word_mask(m8), hi, lo); pb_sil_sq2((uint32_t)q.y & word_mask(m8 >> 2), hi, lo);
-                    pb_sil_sq2((uint32_t)q.z & word_mask(m8 >> 4), hi, lo); pb_sil_sq2((uint32_t)q.w & word_mask(m8 >> 6), hi, lo);
+            int4 q[NV];
+            auto load = [&](long long gv0, int gnvec) {
+                PB_UNROLL for (int c = 0; c < NV; c++) {
+                    const int vi = c * 32 + lane;
+                    if (vi < gnvec) q[c] = pb_sil_load_vec(pcm, pal, mis, pcm_len, gv0 + vi);
                 }
             };
-            auto scatter = [&](const int4& q, long long v) {
-                const long long s = (v << 3) - mis - F.pcm_off;               // file sample index of the vector's first sample
-                const int k_lo = s < fA ? (int)(fA - s) : 0, k_hi = s + 8 > fB ? (int)(fB - s) : 8;
-                if (k_hi <= k_lo) return;
-                const int x = (int)s + k_lo;                                  // first live sample: find its bin b, fc(b) <= x < fc(b+1)
-                int b = __double2int_rz(__dmul_rn((double)x + 1.0, inv_per_ms));
-                int nxt = pb_sil_frame32(b + 1, F.per_ms);
-                if (nxt <= x) { b++; nxt = pb_sil_frame32(b + 1, F.per_ms); }
-                else if (pb_sil_frame32(b, F.per_ms) > x) { nxt = pb_sil_frame32(b, F.per_ms); b--; }
-                const int cut = min(max(nxt - (int)s, k_lo), k_hi);          // samples [k_lo, cut) -> bin b, [cut, k_hi) -> bin b + 1
-                const int m_all = ((1 << k_hi) - 1) & ~((1 << k_lo) - 1), m_one = ((1 << cut) - 1) & ~((1 << k_lo) - 1);
-                int th, tl, oh, ol;
-                masked_sum(q, m_all, th, tl);
-                const int kb = b - base;
-                if (cut == k_hi) { if (kb >= 0 && kb < nb) { atomicAdd(&acc[kb].x, tl); atomicAdd(&acc[kb].y, th); } return; }
-                masked_sum(q, m_one, oh, ol);
-                if (kb >= 0 && kb < nb && cut > k_lo) { atomicAdd(&acc[kb].x, ol); atomicAdd(&acc[kb].y, oh); }
-                if (kb + 1 >= 0 && kb + 1 < nb) { atomicAdd(&acc[kb + 1].x, tl - ol); atomicAdd(&acc[kb + 1].y, th - oh); }
-            };
-            long long v = v0 + threadIdx.x;
-            const int stride = PB_SIL_WARPS * 32;
-            for (; v + stride < v1; v += 2 * stride) {                        // two loads in flight per thread
-                const int4 q0 = pb_sil_load_vec(pcm, pal, mis, pcm_len, v), q1 = pb_sil_load_vec(pcm, pal, mis, pcm_len, v + stride);
-                scatter(q0, v); scatter(q1, v + stride);
+            int g = warp, a = 0, b = 0, nvec = 0;
+            long long v0 = 0;
+            if (g * 32 < nb) { geom(g, a, b, v0, nvec); load(v0, nvec); }
+            while (g * 32 < nb) {
+                PB_UNROLL for (int c = 0; c < NV; c++) {
+                    const int vi = c * 32 + lane;
+                    if (vi < nvec) {
+                        uint32_t* d = stage + (vi * 4 + (vi >> 3));            // = PADW(4 vi): the four words never straddle a pad
+                        d[0] = (uint32_t)q[c].x; d[1] = (uint32_t)q[c].y; d[2] = (uint32_t)q[c].z; d[3] = (uint32_t)q[c].w;
+                    }
+                }
+                for (int vi = NV * 32 + lane; vi < nvec; vi += 32) {           // a rate above what NV covers: the rest, unpipelined
+                    const int4 r = pb_sil_load_vec(pcm, pal, mis, pcm_len, v0 + vi);
+                    uint32_t* d = stage + (vi * 4 + (vi >> 3));
+                    d[0] = (uint32_t)r.x; d[1] = (uint32_t)r.y; d[2] = (uint32_t)r.z; d[3] = (uint32_t)r.w;
+                }
+                __syncwarp();
+                const int gn = g + PB_SIL_WARPS;
+                int an = 0, bn = 0, nvecn = 0;
+                long long v0n = 0;
+                if (gn * 32 < nb) { geom(gn, an, bn, v0n, nvecn); load(v0n, nvecn); }
+                int k = (int)(F.pcm_off + a + mis - (v0 << 3));
+                const int e = k + (b - a);
+                unsigned long long sum = 0;
+                if (k < e) {
+                    if (k & 1) { const int x = (int)stage[PB_SIL_PADW(k >> 1)] >> 16; sum = (unsigned long long)((long long)x * x); k++; }
+                    const int wl = e >> 1;
+                    int acc_hi = 0, acc_lo = 0;
+                    for (int w = k >> 1; w < wl;) {                              // runs of words between two pad slots
+                        const int w_end = min(wl, (w | 31) + 1);
+                        const uint32_t* sp = stage + (w + (w >> 5));
+                        const int n = w_end - w;
+#pragma unroll 4
+                        for (int c = 0; c < n; c++) pb_sil_sq2(sp[c], acc_hi, acc_lo);
+                        w = w_end;
+                    }
+                    sum += (unsigned long long)((long long)acc_hi * 256 + (long long)acc_lo);
+                    if (e & 1) { const int x = (int)(short)(stage[PB_SIL_PADW(wl)] & 0xffff); sum += (unsigned long long)((long long)x * x); }
+                }
+                if (g * 32 + lane < nb) bins[g * 32 + lane] = sum;
+                __syncwarp();
+                g = gn; a = an; b = bn; v0 = v0n; nvec = nvecn;
             }
-            if (v < v1) scatter(pb_sil_load_vec(pcm, pal, mis, pcm_len, v), v);
         }
-        __syncthreads();
-        for (int k = threadIdx.x; k < nb; k += blockDim.x) {                  // (hi, lo) -> the integer energy of the bin
-            const int2 a = acc[k];
-            bins[k] = (unsigned long long)((long long)a.y * 256 + (long long)a.x);
-        }
-        __syncthreads();
         if (threadIdx.x == 0) bins[nb] = 0;
         __syncthreads();
         // ---- 2. exclusive prefix sums over bins[0 .. nb]: every warp owns one contiguous segment (total first, then scan)
