@@ -119,7 +119,7 @@ struct PbHandle {
     int device = 0;
     int sm_count = 1, cc_major = 0, cc_minor = 0;
     long long total_mem = 0;
-    pbStream_t own_stream = 0, stream = 0, copy_stream = 0;
+    pbStream_t own_stream = 0, stream = 0, copy_stream = 0, lufs_stream = 0;   // lufs_stream: loudness kernels run beside the path finder
     std::string err;
     // device buffers (grow on demand)
     DevBuf pcm, units, pair_off, cand_f, cand_s, ncand, inten, psi, sel_f, sel_s, med, nvoiced;
@@ -165,6 +165,7 @@ struct ScopedEv {     // records an event pair around a section of a stream
 enum { EV_TOTAL = 0, EV_H2D, EV_STATS, EV_FRAMES, EV_PATH, EV_LUFS, EV_INTENSITY, EV_D2H };
 
 void begin_call(PbHandle* h) {
+    pbrt_stream_sync(h->lufs_stream);          // a call that failed half-way may have left work there
     h->evs.clear(); h->ev_used = 0;
     h->su_off = h->sp_off = h->sl_off = 0;
     memset(&h->last, 0, sizeof h->last);
@@ -587,25 +588,25 @@ void stage_lufs(PbHandle* h, const BatchPlan& bp, const std::vector<int64_t>& id
     h->sl_off += m;
 }
 
-int launch_lufs_group(PbHandle* h, const int16_t* d_pcm, const LufsLaunch& L) {
+int launch_lufs_group(PbHandle* h, const int16_t* d_pcm, const LufsLaunch& L, pbStream_t stream) {
     const size_t m = L.m;
     if (!m) return PB_OK;
     PbLufsUnitDev* du = (PbLufsUnitDev*)h->lunits.p + L.off;
     const int64_t chunks = L.chunks;
     {
-        ScopedEv ev(h, EV_LUFS);
+        ScopedEv ev(h, EV_LUFS, stream);
         const PbMeterDev* dm = (const PbMeterDev*)h->meters.p;
         double* st = (double*)h->lstate.p; double* en = (double*)h->lenergy.p;
         int g1 = (int)std::max<size_t>(1, std::min<size_t>((m + 7) / 8, (size_t)h->sm_count * 8));           // one warp per unit
-        PB_LAUNCH(pb_lufs_peak_kernel, dim3(g1), dim3(256), 0, h->stream, d_pcm, du, (int)m);
+        PB_LAUNCH(pb_lufs_peak_kernel, dim3(g1), dim3(256), 0, stream, d_pcm, du, (int)m);
         int gc = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 127) / 128, (int64_t)h->sm_count * 16));
         auto k_state = pb_lufs_chunk_kernel<false>; auto k_energy = pb_lufs_chunk_kernel<true>;
-        PB_LAUNCH(k_state, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
+        PB_LAUNCH(k_state, dim3(gc), dim3(128), 0, stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
         int gu = (int)std::max<size_t>(1, std::min<size_t>((m + 127) / 128, (size_t)h->sm_count * 16));
         int gs = (int)std::max<size_t>(1, std::min<size_t>((m + 31) / 32, (size_t)h->sm_count * 16));         // 8 units per warp
-        PB_LAUNCH(pb_lufs_scan_kernel, dim3(gs), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, st);
-        PB_LAUNCH(k_energy, dim3(gc), dim3(128), 0, h->stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
-        PB_LAUNCH(pb_lufs_gate_kernel, dim3(gu), dim3(128), 0, h->stream, (const PbLufsUnitDev*)du, (int)m, dm, (const double*)en, (double*)h->lufs.p);
+        PB_LAUNCH(pb_lufs_scan_kernel, dim3(gs), dim3(128), 0, stream, (const PbLufsUnitDev*)du, (int)m, dm, st);
+        PB_LAUNCH(k_energy, dim3(gc), dim3(128), 0, stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
+        PB_LAUNCH(pb_lufs_gate_kernel, dim3(gu), dim3(128), 0, stream, (const PbLufsUnitDev*)du, (int)m, dm, (const double*)en, (double*)h->lufs.p);
         h->last.n_launches += 5;
     }
     PB_CK(pbrt_last_error(), "lufs kernels");
@@ -673,13 +674,20 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     if (do_pitch) PB_CK(pbrt_memset(h->med.p, 0, (size_t)n * 8, h->stream) || pbrt_memset(h->nvoiced.p, 0, (size_t)n * 4, h->stream), "memset");
     if (do_lufs) PB_CK(pbrt_memset(h->lufs.p, 0xff, (size_t)n * 8, h->stream), "memset");      // all-ones = NaN
     // pinned staging -> device, by the SMs (16-byte words; the staging buffers are allocated with slack)
-    auto upload = [&](void* dst, const void* src_pinned, size_t bytes) {
+    auto upload = [&](void* dst, const void* src_pinned, size_t bytes, pbStream_t stream) {
         if (!bytes) return;
         const long long n16 = (long long)((bytes + 15) / 16);
         const int grid = (int)std::max<long long>(1, std::min<long long>((n16 + 255) / 256, (long long)h->sm_count * 4));
-        PB_LAUNCH(pb_copy16_kernel, dim3(grid), dim3(256), 0, h->stream, (const int4*)pbrt_host_device_ptr(src_pinned), (int4*)dst, n16);
+        PB_LAUNCH(pb_copy16_kernel, dim3(grid), dim3(256), 0, stream, (const int4*)pbrt_host_device_ptr(src_pinned), (int4*)dst, n16);
         h->last.n_launches++;
     };
+    // the loudness stream starts behind the result memsets; its descriptors and kernels then depend on nothing the pitch
+    // kernels do (same-stream order would park them behind the frames kernel)
+    if (do_lufs) {
+        pbEvent_t cleared = *next_event(h);
+        pbrt_event_record(&cleared, h->stream);
+        PB_CK(pbrt_stream_wait_event(h->lufs_stream, cleared), "stream wait");
+    }
     auto seg_of = [&](int64_t need_end) { int s = 0; const int ns = (int)seg_end.size(); while (s + 1 < ns && need_end > seg_end[(size_t)s]) s++; return s; };
 
     std::vector<std::vector<int64_t>>& pids = bp.pids; std::vector<std::vector<int64_t>>& lids = bp.lids;
@@ -741,8 +749,8 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         }
         h->sp_off = (h->sp_off + 3) & ~(size_t)3;                     // keep the next round's upload 16-byte aligned
         lap("stage_pitch");
-        upload((char*)h->units.p + su_sent * sizeof(PbUnitDev), (const char*)h->stage_units.p + su_sent * sizeof(PbUnitDev), (h->su_off - su_sent) * sizeof(PbUnitDev));
-        upload((char*)h->pair_off.p + sp_sent * 4, (const char*)h->stage_pairs.p + sp_sent * 4, (h->sp_off - sp_sent) * 4);
+        upload((char*)h->units.p + su_sent * sizeof(PbUnitDev), (const char*)h->stage_units.p + su_sent * sizeof(PbUnitDev), (h->su_off - su_sent) * sizeof(PbUnitDev), h->stream);
+        upload((char*)h->pair_off.p + sp_sent * 4, (const char*)h->stage_pairs.p + sp_sent * 4, (h->sp_off - sp_sent) * 4, h->stream);
         su_sent = h->su_off; sp_sent = h->sp_off;
         return PB_OK;
     };
@@ -768,8 +776,8 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
             if (!lids[(size_t)s].empty()) stage_lufs(h, bp, lids[(size_t)s], ll[(size_t)s]);
         }
         lap("stage_lufs");
-        upload(h->lunits.p, h->stage_lunits.p, h->sl_off * sizeof(PbLufsUnitDev));
-        upload(h->meters.p, h->stage_meters.p, bp.meters.size() * sizeof(PbMeterDev));
+        upload(h->lunits.p, h->stage_lunits.p, h->sl_off * sizeof(PbLufsUnitDev), h->lufs_stream);
+        upload(h->meters.p, h->stage_meters.p, bp.meters.size() * sizeof(PbMeterDev), h->lufs_stream);
         return PB_OK;
     };
 
@@ -833,10 +841,21 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     h->last.host_plan_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
 
     {
+        // The loudness kernels go to their own stream: they depend only on their descriptors (uploaded on that same
+        // stream) and on their PCM segment, and they share the SMs with the latency-bound path finder and
+        // the tails of the frames kernel instead of queueing behind them.
         for (int s = 0; s < n_seg; s++) {
             if (!on_device && !(pitch_launched && s == 0)) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[(size_t)s]), "stream wait");
             if (!pitch_launched) for (const PitchLaunch& L : pl[(size_t)s]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
-            if (do_lufs) { rc = launch_lufs_group(h, d_pcm, ll[(size_t)s]); if (rc != PB_OK) return rc; }
+            if (do_lufs) {
+                if (!on_device) PB_CK(pbrt_stream_wait_event(h->lufs_stream, seg_done[(size_t)s]), "stream wait");
+                rc = launch_lufs_group(h, d_pcm, ll[(size_t)s], h->lufs_stream); if (rc != PB_OK) return rc;
+            }
+        }
+        if (do_lufs) {
+            pbEvent_t lufs_done = *next_event(h);
+            pbrt_event_record(&lufs_done, h->lufs_stream);
+            PB_CK(pbrt_stream_wait_event(h->stream, lufs_done), "stream wait");
         }
         ScopedEv evd(h, EV_D2H);
         char* so = (char*)h->stage_out.p;
@@ -856,6 +875,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     }
     PB_CK(pbrt_stream_sync(h->stream), "stream sync");
     PB_CK(pbrt_stream_sync(h->copy_stream), "stream sync");
+    PB_CK(pbrt_stream_sync(h->lufs_stream), "stream sync");
     end_call(h);
     const char* so = (const char*)h->stage_out.p;
     if (do_pitch) { memcpy(o.median_f0, so, (size_t)n * 8); memcpy(o.n_voiced, so + (size_t)n * 8, (size_t)n * 4); }
@@ -883,7 +903,7 @@ int pb_create(int device, PbHandle** out) {
     PbHandle* h = new PbHandle();
     h->device = device;
     if (pbrt_props(device, &h->sm_count, &h->cc_major, &h->cc_minor, &h->total_mem)) { delete h; return PB_ENODEVICE; }
-    if (pbrt_stream_create(&h->own_stream) || pbrt_stream_create(&h->copy_stream)) { delete h; return PB_ECUDA; }
+    if (pbrt_stream_create(&h->own_stream) || pbrt_stream_create(&h->copy_stream) || pbrt_stream_create(&h->lufs_stream)) { delete h; return PB_ECUDA; }
     h->stream = h->own_stream;
     memset(&h->last, 0, sizeof h->last);
     *out = h;
@@ -895,6 +915,7 @@ void pb_destroy(PbHandle* h) {
     pbrt_set_device(h->device);
     pbrt_stream_sync(h->stream);
     pbrt_stream_sync(h->copy_stream);
+    pbrt_stream_sync(h->lufs_stream);
     DevBuf* dbs[] = {&h->pcm, &h->units, &h->pair_off, &h->cand_f, &h->cand_s, &h->ncand, &h->inten, &h->psi, &h->sel_f, &h->sel_s,
                      &h->med, &h->nvoiced, &h->lunits, &h->meters, &h->lstate, &h->lenergy, &h->lufs};
     for (auto* b : dbs) b->release();
@@ -904,6 +925,7 @@ void pb_destroy(PbHandle* h) {
     for (auto& e : h->ev_pool) pbrt_event_destroy(e);
     pbrt_stream_destroy(h->own_stream);
     pbrt_stream_destroy(h->copy_stream);
+    pbrt_stream_destroy(h->lufs_stream);
     delete h;
 }
 
