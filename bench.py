@@ -265,6 +265,13 @@ def main():
         frames_per_launch = acc["n_frames"] / args.steps
         kernel_ms = acc["frames_ms"] / args.steps
         achieved_tflops = fpf * frames_per_launch / (kernel_ms * 1e-3) / 1e12
+        # context only: the same launch with nothing beside it (inside the step the loudness kernels share the SMs with it)
+        alone = []
+        for _ in range(2):
+            ex.extract(pcm, pl.units, pb.pitch_params(FLOOR, CEILING), want_pitch=pl.want_pitch, want_lufs=np.zeros(n_units, np.uint8),
+                       lufs=False, durations=False)
+            alone.append(ex.timings()["frames_ms"])
+        kernel_ms_alone = min(alone)
         peaks = {}
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -300,8 +307,10 @@ def main():
                           frac=achieved_tflops / fp32_peak, traffic=traffic,
                           note="non-tensor FP32 pipe: no stage is a dense contraction; peak = SMs x 128 FFMA lanes x 2 x max SM clock "
                                "(nominal; MEASURED_PEAKS.json has no FP32 figure). achieved = the REFERENCE algorithm's flops per frame "
-                               f"({fpf:.0f}, oracle-counted on this input) x frames per launch / CUDA-event kernel time",
+                               f"({fpf:.0f}, oracle-counted on this input) x frames per launch / CUDA-event kernel time inside the step, where the "
+                               "loudness kernels run beside it on another stream (kernel_ms_alone / frac_alone: the same launch by itself)",
                           flops_per_frame=fpf, frames_per_launch=int(frames_per_launch), kernel_ms=kernel_ms,
+                          kernel_ms_alone=kernel_ms_alone, frac_alone=fpf * frames_per_launch / (kernel_ms_alone * 1e-3) / 1e12 / fp32_peak,
                           hbm=dict(achieved=hbm_gbs, peak=peaks.get("hbm_gbs"), unit="GB/s",
                                    frac=(hbm_gbs / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None, bytes_per_frame=alg_bytes,
                                    peak_source="MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "absent")),
