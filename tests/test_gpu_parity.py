@@ -490,29 +490,3 @@ def test_config4_one_hour_recording(gpu_extractor, oracle):
         assert abs(e["median_f0"][k] - med) <= F0_TOL * max(med, 1.0)
         assert abs(e["lufs"][k] - oracle.lufs(seg, sr, float(sr))) < 1e-9
         assert e["duration_s"][k] == oracle.part_duration(m, sr, 0.0, None)
-
-
-def test_two_phase_planning_matches_single_phase(gpu_extractor):
-    """Resident PCM with >= 32768 units: the units of the first 1/16 of the buffer are launched while the rest is planned.
-    The records must equal those of the same units sent in smaller (single-phase) calls."""
-    import prosody_b200 as pb
-    from prosody_b200 import synth
-    sr, dur, n_utt = 16000, 5.0, 640
-    pcm = synth.make_corpus(n_utt, dur, sr, seed=91, device="cuda")
-    n = pcm.shape[1]
-    rng = np.random.default_rng(8)
-    items = []
-    for i in range(n_utt):
-        for a in rng.uniform(0.0, 4.4, 56):
-            items.append((i * n, n, sr, float(a), float(a + rng.uniform(0.05, 0.6)), float(sr)))
-    order = rng.permutation(len(items))                                  # units in arbitrary order, not by file
-    items = [items[k] for k in order]
-    units = pb.Units.from_list(items)
-    assert len(units) >= 32768
-    p = pb.pitch_params(75.0, 600.0)
-    flat = pcm.reshape(-1)
-    big = gpu_extractor.extract(flat, units, p)
-    parts = [gpu_extractor.extract(flat, units.select(slice(a, a + 12000)), p) for a in range(0, len(units), 12000)]
-    for k in ("median_f0", "n_voiced", "n_frames", "lufs", "duration_s", "status"):
-        assert np.array_equal(big[k], np.concatenate([q[k] for q in parts]), equal_nan=True), k
-    assert (big["status"] & 3 != 0).any() and (big["n_voiced"] > 0).any()     # refused (too short) and voiced units both occur
