@@ -490,3 +490,32 @@ def test_config4_one_hour_recording(gpu_extractor, oracle):
         assert abs(e["median_f0"][k] - med) <= F0_TOL * max(med, 1.0)
         assert abs(e["lufs"][k] - oracle.lufs(seg, sr, float(sr))) < 1e-9
         assert e["duration_s"][k] == oracle.part_duration(m, sr, 0.0, None)
+
+
+def test_non_default_pitch_parameters(gpu_extractor, oracle):
+    """Every Praat parameter the ABI exposes is honoured: explicit time step, other floor / ceiling, thresholds and costs,
+    fewer candidates (the legacy callers and other users of to_pitch_ac pass these)."""
+    import prosody_b200 as pb
+    sr = 24000
+    x = speechlike(4, 1.5, sr, seed=55)
+    units = _units_whole(pb, x, sr)
+    cases = [dict(time_step=0.01, pitch_floor=100.0, pitch_ceiling=500.0),
+             dict(time_step=0.004, pitch_floor=60.0, pitch_ceiling=400.0, voicing_threshold=0.6, silence_threshold=0.09),
+             dict(time_step=0.0, pitch_floor=120.0, pitch_ceiling=800.0, octave_cost=0.03, octave_jump_cost=0.8, voiced_unvoiced_cost=0.3),
+             dict(time_step=0.0, pitch_floor=75.0, pitch_ceiling=600.0, max_candidates=4)]
+    for kw in cases:
+        p = pb.pitch_params(**kw)
+        r = gpu_extractor.median_pitch(x.reshape(-1), units, p, frames=True)
+        op = oracle.pitch_params(kw["pitch_floor"], kw["pitch_ceiling"], kw["time_step"])
+        op.voicingThreshold = kw.get("voicing_threshold", 0.45); op.silenceThreshold = kw.get("silence_threshold", 0.03)
+        op.octaveCost = kw.get("octave_cost", 0.01); op.octaveJumpCost = kw.get("octave_jump_cost", 0.35)
+        op.voicedUnvoicedCost = kw.get("voiced_unvoiced_cost", 0.14); op.maxnCandidates = kw.get("max_candidates", 15)
+        tot = ok = 0
+        for i in range(x.shape[0]):
+            o = oracle.pitch_track(x[i], sr, params=op)
+            a, b = r["frame_off"][i], r["frame_off"][i + 1]
+            assert b - a == o["n_frames"], kw
+            agree, rel = compare_tracks(r["frame_f0"][a:b], o["frequency"])
+            assert rel < F0_TOL, (kw, rel)
+            tot += b - a; ok += agree * (b - a)
+        assert ok / tot >= VOICING_AGREE, (kw, ok / tot)
