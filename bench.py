@@ -211,7 +211,8 @@ def main():
     torch.cuda.synchronize()
     ex = pb.Extractor(local)
     audio_s = n_utt * DUR
-    gather_buf = None
+    # the shards are fixed for the whole run: their row counts are exchanged once, not in every step
+    row_sizes = shard.row_counts(pl.n_syn, dev) if world > 1 else None
 
     def step(src):
         out = S.measure(ex, src, pl, prosody, pitch)
@@ -219,7 +220,7 @@ def main():
             # final gather of the per-syntagme results on rank 0 (the path's only exchange)
             rows = torch.from_numpy(np.stack([out["raw_pitch"], out["raw_volume"], out["raw_rate"], out["sm_pitch"], out["sm_rate"]], 1)).to(dev)
             ids = torch.arange(rows.shape[0], device=dev, dtype=torch.int64) + rank * (1 << 32)
-            gathered = shard.gather_rows(rows, ids, dst=0)
+            gathered = shard.gather_rows(rows, ids, dst=0, sizes=row_sizes)
             assert rank != 0 or gathered.shape[1] == 5
         return out
 

@@ -28,7 +28,19 @@ def partition_by_cost(costs: Sequence[float], world: int) -> list[list[int]]:
     return [sorted(np.nonzero(owner == r)[0].tolist()) for r in range(world)]
 
 
-def gather_rows(rows, index, dst: int = 0):
+def row_counts(n_local: int, device) -> list[int]:
+    """Row count of every rank (one all_gather).  A caller whose shards do not change from step to step exchanges them
+    once and passes them to gather_rows, which then needs no host synchronisation on the sending ranks."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    mine = torch.tensor([n_local], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, mine)
+    return [int(s.item()) for s in sizes]
+
+
+def gather_rows(rows, index, dst: int = 0, sizes: list[int] | None = None):
     """Gather [n_r, k] float64 rows and their global row ids [n_r] from every rank onto `dst`; returns the rows in
     global order on dst (None elsewhere).  Works for gloo (CPU tensors) and NCCL (CUDA tensors)."""
     import torch
@@ -36,10 +48,8 @@ def gather_rows(rows, index, dst: int = 0):
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = rows.device
     k = rows.shape[1]
-    n_local = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, n_local)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        sizes = row_counts(rows.shape[0], dev)
     mx = max(sizes + [1])
     pad = torch.zeros(mx, k + 1, dtype=torch.float64, device=dev)
     pad[:rows.shape[0], :k] = rows
