@@ -13,6 +13,12 @@
  *   pb_extract_batch        <- the four above for one list of units, host PCM in, host records out
  *                              (what one pass of the step's loops :375-400 / :495-521 needs per unit)
  *   pb_intensity_batch      <- Sound.to_intensity()               Code/visualisation/Compare_speech_noenhanced.py:19-26
+ *   pb_legacy_loudness_batch<- _calculate_loudness(path, s, e)    Code/Pipeline/compute_loudness_adjustments.py:8-25
+ *   (has_t1 = 2 units)      <- calculate_pitch_segment            Code/Pipeline/compute_pitch_adjustments.py:167-208
+ *   pb_split_on_silence_*   <- pydub.silence.split_on_silence     Code/Preprocessing/preprocess_audio.py:41-46
+ *   pb_reduce_intervals     <- per-word aggregation of the frame tracks (BASELINE.json north_star)
+ *   pb_segment_baselines, pb_syntagme_deltas, pb_ema_clamp <- the step's host arithmetic  Code/audioPipeline.py:401-424, 515-602
+ *   pb_textgrid_*           <- textgrid.TextGrid.fromFile(p)[0]   Code/Preprocessing/gen_break_ssml.py:19-26
  *
  * Conventions
  *   - All functions return PB_OK (0) or a PB_E* code; pb_last_error(h) gives the message.
