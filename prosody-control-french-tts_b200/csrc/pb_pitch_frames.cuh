@@ -396,9 +396,6 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
         const int item = item_begin + it;
         if (item >= item_end) {
             if (!gm.phase_sync) break;
-#ifdef PB_MID_SYNC
-            __syncthreads();
-#endif
             continue;
         }
         const PbPairPos pos = pos_next;
@@ -598,9 +595,6 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
             }
             pb_group_sync<G>(bar_id);
         }
-#ifdef PB_MID_SYNC
-        if (gm.phase_sync) __syncthreads();
-#endif
         // ---- candidates: warp 0 of the group takes frame A, warp 1 (or warp 0 again) frame B
         {
             const float gpk = (float)ud.global_peak;
