@@ -148,3 +148,34 @@ def read_tier_batch(paths, tier: int = 0, threads: int = 0, lib=None):
         a, b = int(off[f]), int(off[f + 1])
         out.append([(float(t0[k]), float(t1[k]), raw[mo[k]:mo[k + 1]].decode("utf-8")) for k in range(a, b)])
     return st, out
+
+
+def whisper_json_to_intervals(data: dict) -> tuple[list, float]:
+    """The word tier that `json_to_textgrid` builds from a whisper-timestamped result
+    (/root/reference/Code/Aligners/use_whisper_timestamped.py:330-395): a word whose start >= end gets end = start + 0.01,
+    a " " interval fills every gap before a word, "[*]" inside a word becomes " ", and a result without any word yields a
+    single "..." interval up to the last segment's end (1.0 s if unknown).  -> ([(tmin, tmax, mark)], maxTime)."""
+    out, current, n_words = [], 0.0, 0
+    for segment in data["segments"]:
+        for word in segment["words"]:
+            n_words += 1
+            start, end = word["start"], word["end"]
+            if start >= end:
+                end = start + 0.01
+            if start > current:
+                out.append((current, start, " "))
+            out.append((start, end, word["text"].replace("[*]", " ")))
+            current = end
+    if n_words == 0:
+        xmax = 1.0
+        if data["segments"] and "end" in data["segments"][-1]:
+            xmax = data["segments"][-1]["end"]
+        out.append((0.0, xmax, "..."))
+        current = xmax
+    return out, current
+
+
+def write_whisper_textgrid(path, data: dict) -> None:
+    """whisper-timestamped JSON -> TextGrid with the single tier `words` (what the Whisper aligner step leaves on disk)."""
+    ivs, xmax = whisper_json_to_intervals(data)
+    write(path, {"words": ivs}, 0.0, xmax)

@@ -59,3 +59,24 @@ def test_native_batch_matches_python_reader(tmp_path):
     assert np.array_equal(st1, TG.read_tier_batch(paths, tier=0, threads=4)[0]) and got1 == TG.read_tier_batch(paths, tier=0, threads=0)[1]
     st, got = TG.read_tier_batch([], tier=0)
     assert len(st) == 0 and got == []
+
+
+def test_whisper_json_rules(tmp_path):
+    """json_to_textgrid's rules (use_whisper_timestamped.py:330-395) and a round trip through writer and both readers."""
+    import prosody_b200  # noqa: F401
+    from prosody_b200 import textgrid as TG
+    data = {"segments": [{"start": 0.2, "end": 1.4, "words": [{"text": "Bonjour", "start": 0.2, "end": 0.61},
+                                                              {"text": "à", "start": 0.61, "end": 0.61},       # start >= end -> +0.01
+                                                              {"text": "[*]", "start": 0.9, "end": 1.1}]},
+                         {"start": 2.0, "end": 2.5, "words": [{"text": 'dit "oui"', "start": 2.0, "end": 2.5}]}]}
+    ivs, xmax = TG.whisper_json_to_intervals(data)
+    assert ivs == [(0.0, 0.2, " "), (0.2, 0.61, "Bonjour"), (0.61, 0.62, "à"), (0.62, 0.9, " "), (0.9, 1.1, " "), (1.1, 2.0, " "),
+                   (2.0, 2.5, 'dit "oui"')] and xmax == 2.5
+    assert TG.whisper_json_to_intervals({"segments": [{"start": 0.0, "end": 3.2, "words": []}]}) == ([(0.0, 3.2, "...")], 3.2)
+    assert TG.whisper_json_to_intervals({"segments": []}) == ([(0.0, 1.0, "...")], 1.0)
+    p = tmp_path / "w.TextGrid"
+    TG.write_whisper_textgrid(p, data)
+    back = TG.read(p)
+    assert back.tiers[0].name == "words" and list(back.tiers[0].intervals) == ivs and back.xmax == 2.5
+    st, batch = TG.read_tier_batch([p])
+    assert st[0] == 0 and batch[0] == ivs
