@@ -123,7 +123,7 @@ struct PbHandle {
     std::string err;
     // device buffers (grow on demand)
     DevBuf pcm, units, pair_off, cand_f, cand_s, ncand, inten, psi, sel_f, sel_s, med, nvoiced;
-    DevBuf lunits, meters, lstate, lenergy, lufs;
+    DevBuf lunits, meters, lstate, lenergy, lufs, pairpos;
     HostBuf stage_units, stage_pairs, stage_lunits, stage_meters, stage_out;
     size_t su_off = 0, sp_off = 0, sl_off = 0;           // running offsets (elements) into the pinned staging buffers
     std::map<std::pair<int64_t, int>, PitchTables*> tables;
@@ -445,8 +445,14 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
     { const char* e = getenv("PB_FRAMES_CTAS"); if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e); }   // experiments: fewer resident CTAs
     long long cap = (long long)h->sm_count * per_sm;
     int grid = (int)std::max(1LL, std::min(need, cap));
-    PB_LAUNCH(kfn, dim3(grid), dim3(threads), smem, h->stream, d_pcm, d_units, d_pair_off, gm, cand_f, cand_s, ncand, inten);
-    h->last.n_launches++;
+    // frame positions of every pair (float64 arithmetic, once), then the frames kernel itself
+    PB_CKMEM(h->pairpos.ensure((size_t)gm.n_pairs * sizeof(int2) + 16), "pair positions");
+    {
+        const int pgrid = (int)std::max(1LL, std::min(((long long)gm.n_pairs + 255) / 256, (long long)h->sm_count * 8));
+        PB_LAUNCH(pb_pair_pos_kernel, dim3(pgrid), dim3(256), 0, h->stream, d_units, d_pair_off, gm, (int2*)h->pairpos.p);
+    }
+    PB_LAUNCH(kfn, dim3(grid), dim3(threads), smem, h->stream, d_pcm, d_units, d_pair_off, (const int2*)h->pairpos.p, gm, cand_f, cand_s, ncand, inten);
+    h->last.n_launches += 2;
     return PB_OK;
 }
 
@@ -917,7 +923,7 @@ void pb_destroy(PbHandle* h) {
     pbrt_stream_sync(h->copy_stream);
     pbrt_stream_sync(h->lufs_stream);
     DevBuf* dbs[] = {&h->pcm, &h->units, &h->pair_off, &h->cand_f, &h->cand_s, &h->ncand, &h->inten, &h->psi, &h->sel_f, &h->sel_s,
-                     &h->med, &h->nvoiced, &h->lunits, &h->meters, &h->lstate, &h->lenergy, &h->lufs};
+                     &h->med, &h->nvoiced, &h->lunits, &h->meters, &h->lstate, &h->lenergy, &h->lufs, &h->pairpos};
     for (auto* b : dbs) b->release();
     HostBuf* hbs[] = {&h->stage_units, &h->stage_pairs, &h->stage_lunits, &h->stage_meters, &h->stage_out};
     for (auto* b : hbs) b->release();

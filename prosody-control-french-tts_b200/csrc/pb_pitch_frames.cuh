@@ -311,15 +311,27 @@ __device__ __forceinline__ long long pb_frame_start(double t1, double x1, int fr
 // Stage the samples the pair (frames fA, fA+1 of unit u) will read into `dst` with 16-byte cp.async copies issued by the
 // GT threads of the group.  Only chunks entirely inside the pcm buffer are copied asynchronously; the (at most two) chunks
 // straddling its ends are filled sample by sample.  Values outside the unit's part / file are masked at read time.
+// The float64 frame positions of every pair, computed once by a small kernel ahead of the frames kernel: {start0, hop}.
+// (They used to be computed inside the frames kernel: two float64 divisions per pair and ~250 instructions of its loop body.)
+__global__ void __launch_bounds__(256)
+pb_pair_pos_kernel(const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off, PbPitchGeomDev gm, int2* __restrict__ out) {
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < gm.n_pairs; item += gridDim.x * blockDim.x) {
+        const int u = pb_upper_unit(pair_off, gm.n_units, item);
+        const PbUnitDev* ud = units + u;
+        const int fA = 2 * (item - ud->pair_off);
+        const long long s0 = pb_frame_start(ud->t1, ud->x1, fA, gm);
+        const int hop = fA + 1 < ud->n_frames ? (int)(pb_frame_start(ud->t1, ud->x1, fA + 1, gm) - s0) : 0;
+        out[item] = make_int2((int)s0, hop);
+    }
+}
+
 template <int GT>
-__device__ __forceinline__ PbPairPos pb_prefetch_pair(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, int u, int item,
+__device__ __forceinline__ PbPairPos pb_prefetch_pair(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, int u, int2 sp,
                                                       const PbPitchGeomDev& gm, int span_lo, int span_len, int16_t* dst, int g) {
     const PbUnitDev* ud = units + u;
-    const int fA = 2 * (item - ud->pair_off);
-    const double x1 = ud->x1, t1 = ud->t1;
     PbPairPos pos;
-    pos.start0 = pb_frame_start(t1, x1, fA, gm);
-    pos.hop = fA + 1 < ud->n_frames ? (int)(pb_frame_start(t1, x1, fA + 1, gm) - pos.start0) : 0;
+    pos.start0 = sp.x;
+    pos.hop = sp.y;
     // frame A sample n is part sample start0+n = pcm sample pcm_off + ix1 + start0 + n - 2
     const long long gs = ud->pcm_off + ud->ix1 + pos.start0 - 2 + span_lo;
     const long long byte0 = (long long)(size_t)pcm + 2 * gs;            // may lie outside the buffer: never dereferenced there
@@ -345,7 +357,7 @@ __device__ __forceinline__ PbPairPos pb_prefetch_pair(const int16_t* __restrict_
 template <int LOG2N>
 __global__ void __launch_bounds__(PbFftCfg<LOG2N>::WARPS_PER_CTA * 32, PbFftCfg<LOG2N>::MIN_CTAS)
 pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off,
-                       PbPitchGeomDev gm, float* __restrict__ cand_f, float* __restrict__ cand_s,
+                       const int2* __restrict__ pairpos, PbPitchGeomDev gm, float* __restrict__ cand_f, float* __restrict__ cand_s,
                        uint8_t* __restrict__ ncand, float* __restrict__ intensity) {
     typedef PbFftCfg<LOG2N> C;
     constexpr int R = C::R, LR = C::LR, N = C::N, G = C::G, GT = C::GT;
@@ -385,7 +397,7 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
     if (has_items) {
         u_next = pb_upper_unit(pair_off, gm.n_units, item_begin);
         u_next_end = pair_off[u_next + 1];
-        pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, item_begin, gm, span_lo, span_len, pre, g);
+        pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, pairpos[item_begin], gm, span_lo, span_len, pre, g);
     }
     int u = -1;
     PbUnitDev ud;
@@ -490,7 +502,7 @@ pb_pitch_frames_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restr
         // the staged samples are consumed: request the next pair's now, they land while this pair is transformed
         if (item + 1 < item_end) {
             if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); }
-            pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, item + 1, gm, span_lo, span_len, pre, g);
+            pos_next = pb_prefetch_pair<GT>(pcm, units, u_next, pairpos[item + 1], gm, span_lo, span_len, pre, g);
         }
         // ---- two FFTs x two passes through ONE copy of the butterfly code: FFT (step >> 1), pass (step & 1).  The step
         //      index is made opaque so the optimiser neither peels nor unswitches the loop (either duplicates ~450

@@ -48,6 +48,7 @@ static inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a
 static inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{__builtin_fmaf(a.x, b.x, c.x), __builtin_fmaf(a.y, b.y, c.y)}; }
 static inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
+static inline int2 make_int2(int a, int b) { return int2{a, b}; }
 
 namespace pb_emu {
 
