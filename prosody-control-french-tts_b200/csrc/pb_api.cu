@@ -105,7 +105,6 @@ struct BatchPlan {
     std::vector<int32_t> pstat, lflags;
     std::vector<LufsResolved> lres;           // slice arithmetic of every unit (filled in parallel)
     std::vector<int64_t> fbase;               // first frame of every staged pitch unit
-    std::vector<uint8_t> ptodo;               // units planned by the current phase of plan_pitch
     std::vector<std::vector<int64_t>> pids, lids, by_class;
     void reset() {
         classes.clear(); max_cand = 0; total_frames = 0;       // pplan / pclass keep their size: plan_pitch rewrites them
@@ -275,24 +274,15 @@ int validate_units(PbHandle* h, const PbUnits* u, int64_t pcm_len) {
 }
 
 // status / n_frames must be zero-initialised by the caller; only wanted units are touched
-// phase 0: every wanted unit.  phase 1: only the units whose file ends at or before `limit` (the others are marked deferred);
-// phase 2: the deferred ones.  Two phases let the kernels of the first units start while the rest is still being planned.
-int plan_pitch(PbHandle* h, const PbUnits* u, const PbPitchParams* p, const uint8_t* want, int32_t* status, int32_t* n_frames, BatchPlan& bp,
-               int phase = 0, int64_t limit = 0) {
+int plan_pitch(PbHandle* h, const PbUnits* u, const PbPitchParams* p, const uint8_t* want, int32_t* status, int32_t* n_frames, BatchPlan& bp) {
     const int64_t n = u->n_units;
     if (bp.pplan.size() != (size_t)n) bp.pplan.resize((size_t)n);     // every wanted entry is rewritten below: no re-zeroing per call
     bp.pclass.resize((size_t)n);
-    std::vector<uint8_t>& todo = bp.ptodo;
-    todo.assign((size_t)n, 0);
-    // geometry class of every unit of this phase (sequential: a handful of distinct rates), then the float64 planning of the
+    // geometry class of every wanted unit (sequential: a handful of distinct rates), then the float64 planning of the
     // units themselves split over a few host threads, then the totals
     double last_rate = -1.0; int last_cls = -1;
     for (int64_t i = 0; i < n; i++) {
-        if (phase == 2) { if (bp.pclass[(size_t)i] != -2) continue; }
-        else {
-            if (want && !want[i]) { bp.pclass[(size_t)i] = -1; continue; }
-            if (phase == 1 && u->file_off[i] + u->file_nx[i] > limit) { bp.pclass[(size_t)i] = -2; continue; }
-        }
+        if (want && !want[i]) { bp.pclass[(size_t)i] = -1; continue; }
         int ci = last_cls;
         if (u->rate[i] != last_rate) {
             ci = -1;
@@ -303,12 +293,13 @@ int plan_pitch(PbHandle* h, const PbUnits* u, const PbPitchParams* p, const uint
             }
             last_rate = u->rate[i]; last_cls = ci;
         }
-        bp.pclass[(size_t)i] = ci; todo[(size_t)i] = 1;
+        bp.pclass[(size_t)i] = ci;
     }
     pb_parallel_for(n, 16384, [&](int64_t i0, int64_t i1) {
         for (int64_t i = i0; i < i1; i++) {
-            if (!todo[(size_t)i]) continue;
-            const PitchClass& pc = bp.classes[(size_t)bp.pclass[(size_t)i]];
+            const int ci = bp.pclass[(size_t)i];
+            if (ci < 0) continue;
+            const PitchClass& pc = bp.classes[(size_t)ci];
             PbUnitPlan& pl = bp.pplan[(size_t)i];
             pb_plan_pitch_unit(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], *p, pc.g, pc.gstatus, pl);
             status[i] = pl.status; n_frames[i] = pl.n_frames;
@@ -317,7 +308,7 @@ int plan_pitch(PbHandle* h, const PbUnits* u, const PbPitchParams* p, const uint
     });
     for (int64_t i = 0; i < n; i++) {
         const int ci = bp.pclass[(size_t)i];
-        if (todo[(size_t)i] && ci >= 0) { bp.total_frames += bp.pplan[(size_t)i].n_frames; bp.max_cand = bp.classes[(size_t)ci].g.max_cand; }
+        if (ci >= 0) { bp.total_frames += bp.pplan[(size_t)i].n_frames; bp.max_cand = bp.classes[(size_t)ci].g.max_cand; }
     }
     if (bp.max_cand > PB_MAXC) return fail(h, PB_EUNSUPPORTED, "%s", "pitch_ceiling / pitch_floor exceeds 32 candidates per frame");
     return PB_OK;
@@ -726,7 +717,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     // round 0: every unit (one segment or all segments known); round 1: only the units of the first segment (the others
     // are not cut yet); round 2: the rest.  Descriptors already on the device are not uploaded again.
     size_t su_sent = 0, sp_sent = 0;
-    auto stage_upload_pitch = [&](int round, size_t T_hint) -> int {
+    auto stage_upload_pitch = [&](int round) -> int {
         const int n_seg = (int)seg_end.size();
         if (pids.size() < (size_t)n_seg) pids.resize((size_t)n_seg);
         if (pl.size() < (size_t)n_seg) pl.resize((size_t)n_seg);
@@ -750,16 +741,14 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
             frame_off[(size_t)n] = acc;
         }
         // frame arrays are shared by the segments (stream order); when the cuts are not known yet, size them for everything
-        // frame arrays are shared by the launch groups (stream order): the largest group decides, T_hint when the caller knows
-        // what is still to come.  (Growing them while kernels run is safe — cudaFree waits — but stalls, so it is avoided.)
-        const size_t T = std::max(T_hint, (size_t)*std::max_element(seg_frames.begin(), seg_frames.end()));
+        const size_t T = round == 0 ? (size_t)*std::max_element(seg_frames.begin(), seg_frames.end()) : (size_t)bp.total_frames;
         const size_t mc = (size_t)(bp.max_cand > 0 ? bp.max_cand : 1);
-        const size_t n_desc = (size_t)n, n_groups = 16 * 8 + 4;       // descriptors: every unit may follow; launch groups + alignment slack
-        if (n_pok)
+        const size_t n_groups = 16 * bp.classes.size() + 4;           // launch groups (segments x classes) + alignment slack
+        if (n_pok && round != 2)
             PB_CKMEM(h->cand_f.ensure(T * mc * 4) || h->cand_s.ensure(T * mc * 4) || h->ncand.ensure(T) || h->inten.ensure(T * 4) ||
                      h->psi.ensure(T * mc) || h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4) ||
-                     h->stage_units.ensure(n_desc * sizeof(PbUnitDev) + 16) || h->units.ensure(n_desc * sizeof(PbUnitDev) + 16) ||
-                     h->stage_pairs.ensure((n_desc + n_groups) * 4 + 16) || h->pair_off.ensure((n_desc + n_groups) * 4 + 16), "pitch buffers");
+                     h->stage_units.ensure(n_pok * sizeof(PbUnitDev) + 16) || h->units.ensure(n_pok * sizeof(PbUnitDev) + 16) ||
+                     h->stage_pairs.ensure((n_pok + n_groups) * 4 + 16) || h->pair_off.ensure((n_pok + n_groups) * 4 + 16), "pitch buffers");
         for (int s = (round == 2 ? 1 : 0); s < (round == 1 ? 1 : n_seg); s++) {
             int r = stage_pitch(h, u, bp, pids[(size_t)s], want_frames ? &frame_off : nullptr, pl[(size_t)s]);
             if (r != PB_OK) return r;
@@ -801,21 +790,9 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     if (!segmented) {
         // one segment: pitch descriptors up and pitch kernels running before the loudness units are planned
         if (do_pitch) {
-            if (on_device && !want_frames && n >= 32768) {
-                // many units: plan, stage and launch the units of the first 1/16 of the buffer, plan the rest while they run
-                seg_end[0] = bin_edge(NB / 16); seg_end.push_back(pcm_len);
-                memset(o.n_frames, 0, (size_t)n * 4);
-                if ((rc = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp, 1, seg_end[0])) != PB_OK || (rc = stage_upload_pitch(1, 0)) != PB_OK) return rc;
-                for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
-                if ((rc = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp, 2)) != PB_OK) return rc;
-                lap("plan_pitch");
-                if ((rc = stage_upload_pitch(2, 0)) != PB_OK) return rc;
-                for (const PitchLaunch& L : pl[1]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
-            } else {
-                if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch(0, 0)) != PB_OK) return rc;
-                if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
-                for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
-            }
+            if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch(0)) != PB_OK) return rc;
+            if (!on_device) PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
+            for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
             pitch_launched = true;
         }
         if (do_lufs && ((rc = plan_lufs_units()) != PB_OK || (rc = stage_upload_lufs()) != PB_OK)) return rc;
@@ -826,7 +803,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         // when the upload ends) and the ones before it similar amounts (fewer, fuller launches than a fixed grid of cuts).
         double t_first_launch_ms = 0.0, work_first_ms = 0.0;
         if (do_pitch) {
-            if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch(1, (size_t)bp.total_frames)) != PB_OK) return rc;
+            if ((rc = plan_pitch_units()) != PB_OK || (rc = stage_upload_pitch(1)) != PB_OK) return rc;
             PB_CK(pbrt_stream_wait_event(h->stream, seg_done[0]), "stream wait");
             for (const PitchLaunch& L : pl[0]) { rc = launch_pitch_group(h, d_pcm, p, bp, L); if (rc != PB_OK) return rc; }
             pl[0].clear();
@@ -860,7 +837,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         }
         if (tail < NB) { rc = enqueue_upload(bin_edge(tail), pcm_len); if (rc != PB_OK) return rc; }
         lap("segments");
-        if (do_pitch && (rc = stage_upload_pitch(2, 0)) != PB_OK) return rc;
+        if (do_pitch && (rc = stage_upload_pitch(2)) != PB_OK) return rc;
         if (do_lufs && (rc = stage_upload_lufs()) != PB_OK) return rc;
     }
     const int n_seg = (int)seg_end.size();
@@ -902,13 +879,10 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     if (o.duration_s) for (int64_t i = 0; i < n; i++) {
         int st; o.duration_s[i] = pb_part_duration(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], &st);
     }
-    lap("durations");
     PB_CK(pbrt_stream_sync(h->stream), "stream sync");
     PB_CK(pbrt_stream_sync(h->copy_stream), "stream sync");
     PB_CK(pbrt_stream_sync(h->lufs_stream), "stream sync");
-    lap("gpu wait");
     end_call(h);
-    lap("event times");
     const char* so = (const char*)h->stage_out.p;
     if (do_pitch) { memcpy(o.median_f0, so, (size_t)n * 8); memcpy(o.n_voiced, so + (size_t)n * 8, (size_t)n * 4); }
     if (do_lufs) {
@@ -916,7 +890,6 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         for (auto& d : bp.dups) o.lufs[d.first] = o.lufs[d.second];
     }
     if (o.status) for (int64_t i = 0; i < n; i++) o.status[i] = pstat[(size_t)i] | lflags[(size_t)i];
-    lap("results");
     return PB_OK;
 }
 

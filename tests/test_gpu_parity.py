@@ -519,29 +519,3 @@ def test_non_default_pitch_parameters(gpu_extractor, oracle):
             assert rel < F0_TOL, (kw, rel)
             tot += b - a; ok += agree * (b - a)
         assert ok / tot >= VOICING_AGREE, (kw, ok / tot)
-
-
-def test_two_phase_planning_matches_single_phase(gpu_extractor):
-    """Resident PCM with >= 32768 units: the units of the first 1/16 of the buffer are launched while the rest is planned.
-    The records must equal those of the same units sent in smaller (single-phase) calls."""
-    import prosody_b200 as pb
-    from prosody_b200 import synth
-    sr, dur, n_utt = 16000, 5.0, 640
-    pcm = synth.make_corpus(n_utt, dur, sr, seed=91, device="cuda")
-    n = pcm.shape[1]
-    rng = np.random.default_rng(8)
-    items = []
-    for i in range(n_utt):
-        for a in rng.uniform(0.0, 4.4, 56):
-            items.append((i * n, n, sr, float(a), float(a + rng.uniform(0.05, 0.6)), float(sr)))
-    order = rng.permutation(len(items))                                  # units in arbitrary order, not by file
-    items = [items[k] for k in order]
-    units = pb.Units.from_list(items)
-    assert len(units) >= 32768
-    p = pb.pitch_params(75.0, 600.0)
-    flat = pcm.reshape(-1)
-    big = gpu_extractor.extract(flat, units, p)
-    parts = [gpu_extractor.extract(flat, units.select(slice(a, a + 12000)), p) for a in range(0, len(units), 12000)]
-    for k in ("median_f0", "n_voiced", "n_frames", "lufs", "duration_s", "status"):
-        assert np.array_equal(big[k], np.concatenate([q[k] for q in parts]), equal_nan=True), k
-    assert ((big["status"] & 3) != 0).any() and (big["n_voiced"] > 0).any()     # refused (too short) and voiced units both occur
