@@ -42,6 +42,10 @@ def _worker(rank, world, port, tmp):
         ids = np.concatenate([np.arange(first[s], first[s + 1]) for s in mine]) if mine else np.zeros(0, np.int64)
         rows = np.stack([ids * 1.5, np.sin(ids), ids % 7, -ids, ids * ids], 1).astype(np.float64) if len(ids) else np.zeros((0, 5))
         out = shard.gather_rows(torch.from_numpy(rows), torch.from_numpy(ids), dst=0)
+        sizes = shard.row_counts(len(ids), torch.device("cpu"))              # exchanged once, reused by later gathers
+        assert sum(sizes) == int(first[-1]) and sizes[rank] == len(ids)
+        again = shard.gather_rows(torch.from_numpy(rows), torch.from_numpy(ids), dst=0, sizes=sizes)
+        assert (again is None) == (rank != 0) and (rank != 0 or np.array_equal(again.numpy(), out.numpy()))
         if rank == 0:
             total = int(first[-1])
             g = np.arange(total)
