@@ -420,6 +420,15 @@ def test_segmented_host_upload_matches_resident_pcm(gpu_extractor):
         assert np.array_equal(r_dev[k], r_host[k], equal_nan=True), k
         assert np.array_equal(r_dev[k], r_np[k], equal_nan=True), k
     assert (r_dev["n_voiced"] > 0).mean() > 0.5
+    # the single-purpose entry points take the same segmented route
+    mp = gpu_extractor.median_pitch(host, units, p)
+    lu, _ = gpu_extractor.lufs(host, units)
+    assert np.array_equal(mp["median_f0"], r_dev["median_f0"]) and np.array_equal(mp["n_voiced"], r_dev["n_voiced"])
+    assert np.array_equal(lu, r_dev["lufs"], equal_nan=True)
+    # per-frame outputs force a single upload: same values again
+    fr_host = gpu_extractor.median_pitch(host, units, p, frames=True)
+    fr_dev = gpu_extractor.median_pitch(flat, units, p, frames=True)
+    assert np.array_equal(fr_host["frame_f0"], fr_dev["frame_f0"]) and np.array_equal(fr_host["median_f0"], r_dev["median_f0"])
 
 
 def test_interval_reduction_on_word_grids(gpu_extractor):
