@@ -85,3 +85,30 @@ def test_part_duration_matches_oracle(native_lib, oracle):
             assert st[i] == 64
             continue
         assert d[i] == ref and st[i] == 0
+
+
+def test_frame_times_and_intensity_plan_match_oracle(native_lib, oracle):
+    """Host-only planning of the other entry points on random units: pitch frame times (both extract_part modes) and the
+    intensity frame grid, bit for bit against the oracle's float64 arithmetic."""
+    import prosody_b200 as pb
+    rng = np.random.default_rng(7)
+    rates, nx, has, t0, t1 = _random_units(rng, 600)
+    for mode in (1, 2):
+        h = np.where(has != 0, mode, 0).astype(np.int32)
+        units = pb.Units(np.zeros(600, np.int64), nx, rates, h, t0, t1)
+        p = pb.pitch_params(75.0, 600.0)
+        st, nf, _ = pb.pitch_plan(units, p, native_lib)
+        tf, dt = pb.pitch_frame_times(units, p, native_lib)
+        for i in range(600):
+            ost, g, ix1, n, x1 = oracle.pitch_geometry(int(nx[i]), float(rates[i]), float(t0[i]), float(t1[i]) if has[i] else None,
+                                                       oracle.pitch_params(75.0, 600.0), preserve_times=(mode == 1))
+            assert st[i] == ost
+            if ost == 0:
+                assert tf[i] == g.t1 and dt[i] == g.dt and nf[i] == g.nFrames, (mode, i)
+    whole = pb.Units(np.zeros(600, np.int64), nx, rates, np.zeros(600, np.int32), t0, t1)
+    ist, inf, ifo, it1, idt = pb.intensity_plan(whole, 100.0, 0.0, native_lib)
+    for i in range(600):
+        ost, n_frames, t_first, dts, half = oracle.intensity_geometry(int(nx[i]), float(rates[i]))
+        assert (ist[i] == 0) == (ost == 0)
+        if ost == 0:
+            assert inf[i] == n_frames and it1[i] == t_first and idt[i] == dts
