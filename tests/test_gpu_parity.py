@@ -22,7 +22,8 @@ def _units_whole(pb, x, sr):
 
 
 @pytest.mark.parametrize("sr,floor,dur", [(16000, 75.0, 2.0), (16000, 150.0, 1.5), (24000, 75.0, 1.5), (22050, 150.0, 1.0),
-                                          (44100, 150.0, 1.0), (44100, 75.0, 1.0), (8000, 150.0, 1.5)])
+                                          (44100, 150.0, 1.0), (44100, 75.0, 1.0), (8000, 150.0, 1.5),
+                                          (48000, 75.0, 0.8), (96000, 75.0, 0.6)])      # the last one needs the 8192-point FFT (8 warps per frame pair)
 def test_pitch_tracks_match_oracle(gpu_extractor, oracle, sr, floor, dur):
     import prosody_b200 as pb
     x = speechlike(6, dur, sr, seed=100 + sr // 1000)
