@@ -45,7 +45,7 @@ class Units:
         if self.meter_rate is not None:
             self.meter_rate = np.ascontiguousarray(self.meter_rate, np.float64)
         n = len(self.file_off)
-        for a in (self.file_nx, self.rate, self.has_t1, self.t0, self.t1):
+        for a in (self.file_nx, self.rate, self.has_t1, self.t0, self.t1) + (() if self.meter_rate is None else (self.meter_rate,)):
             if len(a) != n:
                 raise ValueError("unit arrays must have the same length")
 

@@ -165,7 +165,7 @@ struct ScopedEv {     // records an event pair around a section of a stream
 enum { EV_TOTAL = 0, EV_H2D, EV_STATS, EV_FRAMES, EV_PATH, EV_LUFS, EV_INTENSITY, EV_D2H };
 
 void begin_call(PbHandle* h) {
-    pbrt_stream_sync(h->lufs_stream);          // a call that failed half-way may have left work there
+    pbrt_stream_sync(h->lufs_stream);          // belt and braces: failed calls drain their streams themselves (DrainOnError)
     h->evs.clear(); h->ev_used = 0;
     h->su_off = h->sp_off = h->sl_off = 0;
     memset(&h->last, 0, sizeof h->last);
@@ -271,6 +271,18 @@ int validate_units(PbHandle* h, const PbUnits* u, int64_t pcm_len) {
         if (u->file_nx[i] > 0x7fffffffLL) return fail(h, PB_EUNSUPPORTED, "unit %s: file longer than 2^31 samples", std::to_string(i).c_str());
     }
     return PB_OK;
+}
+
+// Praat refuses these before any analysis (Sound_to_Pitch_any: minimumPitch / periodsPerWindow positive, at least two
+// candidates); a non-finite or non-positive value would otherwise turn into an undefined int64 in pb_geom_for_rate.
+const char* pitch_params_error(const PbPitchParams* p) {
+    if (!p) return "pitch params is null";
+    if (!(p->pitch_floor > 0.0) || !std::isfinite(p->pitch_floor)) return "pitch_floor must be positive and finite";
+    if (!(p->pitch_ceiling > 0.0) || !std::isfinite(p->pitch_ceiling)) return "pitch_ceiling must be positive and finite";
+    if (!(p->periods_per_window > 0.0) || !std::isfinite(p->periods_per_window)) return "periods_per_window must be positive and finite";
+    if (!(p->time_step >= 0.0) || !std::isfinite(p->time_step)) return "time_step must be >= 0 (0 = automatic)";
+    if (p->max_candidates < 2) return "max_candidates must be at least 2 (Praat: \"maximum number of candidates should be greater than 1\")";
+    return nullptr;
 }
 
 // status / n_frames must be zero-initialised by the caller; only wanted units are touched
@@ -630,8 +642,17 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
               const uint8_t* want_pitch, const uint8_t* want_lufs, const BatchOut& o) {
     int rc = validate_units(h, u, pcm_len);
     if (rc != PB_OK) return rc;
+    if (o.median_f0) { const char* pe = pitch_params_error(p); if (pe) return fail(h, PB_EINVAL, "%s", pe); }
     pbrt_set_device(h->device);
     begin_call(h);
+    // Any early return below may leave copies / kernels in flight that read the caller's (pinned) PCM or the staging
+    // buffers: drain all three streams before handing control back on failure.
+    struct DrainOnError {
+        PbHandle* h; int* rc;
+        ~DrainOnError() { if (*rc != PB_OK) { pbrt_stream_sync(h->copy_stream); pbrt_stream_sync(h->stream); pbrt_stream_sync(h->lufs_stream); } }
+    };
+    int rc_final = PB_ECUDA;                                   // set to PB_OK on the one successful exit
+    DrainOnError drain{h, &rc_final};
     h->cur_pcm_len = pcm_len;
     const int64_t n = u->n_units;
     const bool do_pitch = o.median_f0 && o.n_voiced && o.n_frames, do_lufs = o.lufs != nullptr;
@@ -746,7 +767,8 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         const size_t n_groups = 16 * bp.classes.size() + 4;           // launch groups (segments x classes) + alignment slack
         if (n_pok && round != 2)
             PB_CKMEM(h->cand_f.ensure(T * mc * 4) || h->cand_s.ensure(T * mc * 4) || h->ncand.ensure(T) || h->inten.ensure(T * 4) ||
-                     h->psi.ensure(T * mc) || h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4) ||
+                     h->psi.ensure(T * std::max<size_t>(mc, 8)) ||   /* K3 packs the back-pointers of a frame into one 64-bit word when max_cand <= 16 */
+                     h->sel_f.ensure(T * 4) || h->sel_s.ensure(T * 4) ||
                      h->stage_units.ensure(n_pok * sizeof(PbUnitDev) + 16) || h->units.ensure(n_pok * sizeof(PbUnitDev) + 16) ||
                      h->stage_pairs.ensure((n_pok + n_groups) * 4 + 16) || h->pair_off.ensure((n_pok + n_groups) * 4 + 16), "pitch buffers");
         for (int s = (round == 2 ? 1 : 0); s < (round == 1 ? 1 : n_seg); s++) {
@@ -890,6 +912,7 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
         for (auto& d : bp.dups) o.lufs[d.first] = o.lufs[d.second];
     }
     if (o.status) for (int64_t i = 0; i < n; i++) o.status[i] = pstat[(size_t)i] | lflags[(size_t)i];
+    rc_final = PB_OK;
     return PB_OK;
 }
 

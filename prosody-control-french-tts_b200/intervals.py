@@ -8,9 +8,11 @@ Mirrors, behaviour for behaviour (incl. the cursor drift, SURVEY.md Appendix B.4
     punctuation clamp / inject   /root/reference/Code/audioPipeline.py:470-489
     construct_syntagmes_seq      /root/reference/Code/audioPipeline.py:265-311
 
-The reference asks spaCy (fr_core_news_sm) for part-of-speech tags; that model is a boundary input here: callers
-inject ``pos_of(word) -> POS`` (``spacy_pos()`` builds one when spaCy is installed).  The default tags nothing, i.e.
-no comma or pause is dropped.
+The reference asks spaCy (fr_core_news_sm) for part-of-speech tags; that model is a boundary input here.  Callers
+inject either a TAGGER — an object with ``tag(text) -> [(token, trailing_ws, POS)]`` that tokenises and tags a whole
+mark the way ``_nlp(text)`` does (``spacy_pos()`` builds one on the reference's own model: elisions such as "l'homme,"
+are then split and tagged exactly as the reference sees them) — or, for tests and callers without spaCy, a plain
+``pos_of(word) -> POS`` that is applied to regex-split tokens.  The default tags nothing: no comma or pause is dropped.
 """
 from __future__ import annotations
 
@@ -29,11 +31,26 @@ NO_POS: PosFn = lambda word: "X"
 _TOKENS = re.compile(r"\[\*\]|\w+(?:['’\-]\w+)*['’]?|[^\w\s]", re.UNICODE)
 
 
-def spacy_pos(model: str = "fr_core_news_sm") -> PosFn:
-    """POS predicate backed by the reference's own tagger (only if spaCy and the model are installed)."""
+class SpacyTagger:
+    """The reference's own tagger (`_nlp = spacy.load("fr_core_news_sm")`, audioPipeline.py:26): tag(text) runs the
+    model on the WHOLE mark and returns spaCy's tokens, so the comma filter sees the real previous token ("homme" in
+    "l'homme,") and the pause filter the first token of the previous mark, as at audioPipeline.py:70-79,459."""
+
+    def __init__(self, nlp):
+        self.nlp = nlp
+
+    def tag(self, text: str):
+        return [(t.text, t.whitespace_, t.pos_) for t in self.nlp(text)]
+
+    def __call__(self, word: str) -> str:
+        d = self.nlp(word)
+        return d[0].pos_ if len(d) else "X"
+
+
+def spacy_pos(model: str = "fr_core_news_sm") -> "SpacyTagger":
+    """Tagger backed by the reference's own model (raises when spaCy or the model is not installed)."""
     import spacy
-    nlp = spacy.load(model, disable=["ner"])
-    return lambda word: (lambda d: d[0].pos_ if len(d) else "X")(nlp(word))
+    return SpacyTagger(spacy.load(model))
 
 
 def words_and_pauses(intervals: Iterable) -> list:
@@ -76,6 +93,15 @@ def _pos(token: str, pos_of: PosFn) -> str:
 
 def strip_spurious_commas(text: str, pos_of: PosFn = NO_POS) -> str:
     """Drop a comma (or pause marker) that directly follows a function word; keep the original spacing."""
+    if hasattr(pos_of, "tag"):
+        # the reference's loop on the tagger's own tokens of the whole mark (audioPipeline.py:70-81); like
+        # `"".join(t.text_with_ws ...)`, leading whitespace the tokeniser swallowed is not restored
+        kept = []
+        for tok, ws, pos in pos_of.tag(text):
+            if (tok == "," or tok in PAUSE_MARKERS) and kept and kept[-1][2] in FORBIDDEN_POS:
+                continue
+            kept.append((tok, ws, pos))
+        return "".join(t + w for t, w, _ in kept)
     lead, toks = _split(text)
     kept = []
     for tok, ws in toks:
@@ -86,6 +112,10 @@ def strip_spurious_commas(text: str, pos_of: PosFn = NO_POS) -> str:
 
 
 def first_pos(word: str, pos_of: PosFn) -> str:
+    """`_nlp(ptok.strip())[0].pos_` (audioPipeline.py:459): POS of the first token of the mark."""
+    if hasattr(pos_of, "tag"):
+        toks = pos_of.tag(word.strip())
+        return toks[0][2] if toks else "X"
     _, toks = _split(word.strip())
     return _pos(toks[0][0], pos_of) if toks else "X"
 

@@ -123,11 +123,14 @@ def measure_prosody_and_build_ssml(self, extractor: Extractor | None = None, pos
                    threshold_duration_before_slowing_down=self.threshold_duration_before_slowing_down,
                    slow_floor_per_sec=self.slow_floor_per_sec)
     if pos_of is None:
+        # Like the reference (which fails at import without fr_core_news_sm, audioPipeline.py:26), a missing tagger is an
+        # error: silently dropping the comma / pause filter would change which slices are measured.  Callers that WANT
+        # no filter pass pos_of=intervals.NO_POS explicitly.
         try:
             pos_of = IV.spacy_pos()
-        except Exception:                     # spaCy / fr_core_news_sm not installed: nothing is filtered
-            logging.warning("spaCy fr_core_news_sm unavailable: comma / pause POS filter disabled")
-            pos_of = IV.NO_POS
+        except Exception as e:
+            raise RuntimeError("spaCy model fr_core_news_sm is required for the comma / pause POS filter "
+                               "(pass pos_of=prosody_b200.intervals.NO_POS to run without it)") from e
     ex = extractor or default_extractor()
     pl = S.plan(segs, prosody, pos_of)
     out = S.measure(ex, pcm, pl, prosody)

@@ -529,3 +529,36 @@ def test_non_default_pitch_parameters(gpu_extractor, oracle):
             assert rel < F0_TOL, (kw, rel)
             tot += b - a; ok += agree * (b - a)
         assert ok / tot >= VOICING_AGREE, (kw, ok / tot)
+
+
+def test_fewer_than_eight_candidates_and_parameter_validation(gpu_extractor, oracle):
+    """with floor 150 / ceiling 600 / max_candidates 4 Praat keeps 4 candidates per frame; the path finder's
+    packed back-pointers (one 64-bit word per frame) must not depend on max_cand >= 8.  Parameters Praat refuses
+    (max_candidates < 2, non-positive floor) are refused at the ABI."""
+    import prosody_b200 as pb
+    sr = 16000
+    x = speechlike(5, 2.0, sr, seed=77)
+    units = _units_whole(pb, x, sr)
+    for maxc in (2, 3, 4, 6):
+        p = pb.pitch_params(150.0, 600.0, max_candidates=maxc)
+        r = gpu_extractor.median_pitch(x.reshape(-1), units, p, frames=True)
+        op = oracle.pitch_params(150.0, 600.0); op.maxnCandidates = max(maxc, 4)       # Praat: at least ceiling / floor
+        tot = ok = 0
+        for i in range(x.shape[0]):
+            o = oracle.pitch_track(x[i], sr, params=op)
+            a, b = r["frame_off"][i], r["frame_off"][i + 1]
+            assert b - a == o["n_frames"]
+            agree, rel = compare_tracks(r["frame_f0"][a:b], o["frequency"])
+            assert rel < F0_TOL, (maxc, rel)
+            tot += b - a; ok += agree * (b - a)
+        assert ok / tot >= VOICING_AGREE, (maxc, ok / tot)
+        # the buffers next to the back-pointers were not trampled: a default run right after still matches
+        r2 = gpu_extractor.median_pitch(x.reshape(-1), units, pb.pitch_params(75.0, 600.0))
+        for i in range(x.shape[0]):
+            med = oracle.median_pitch(x[i], sr, 0.0, None, 75.0, 600.0)
+            assert abs(r2["median_f0"][i] - med) <= F0_TOL * max(med, 1.0)
+    for bad in (dict(max_candidates=1), dict(pitch_floor=0.0), dict(pitch_floor=-75.0), dict(pitch_ceiling=float("nan")),
+                dict(periods_per_window=0.0), dict(time_step=-0.01)):
+        kw = dict(pitch_floor=75.0, pitch_ceiling=600.0); kw.update(bad)
+        with pytest.raises(Exception):
+            gpu_extractor.median_pitch(x.reshape(-1), units, pb.pitch_params(**kw))

@@ -127,3 +127,31 @@ def test_segment_baselines_match_numpy_medians():
                 el = float(np.median(list(l[lo:hi]))); er = float(np.median(list(r[lo:hi])))
                 for got, exp in ((f0[i], ef), (loud[i], el), (rate[i], er)):
                     assert (np.isnan(got) and np.isnan(exp)) or got == exp, (n, win, i, got, exp)
+
+
+class _FakeSpacyTagger:
+    """Tokenises like fr_core_news_sm does on elisions and inverted clitics (what the reference's `_nlp(text)` sees)."""
+    TABLE = {"l'homme,": [("l'", "", "DET"), ("homme", "", "NOUN"), (",", "", "PUNCT")],
+             "dit-il,": [("dit", "", "VERB"), ("-il", "", "PRON"), (",", "", "PUNCT")],
+             "l'homme": [("l'", "", "DET"), ("homme", "", "NOUN")],
+             "de, la": [("de", "", "ADP"), (",", " ", "PUNCT"), ("la", "", "DET")]}
+
+    def tag(self, text):
+        return self.TABLE[text]
+
+    def __call__(self, word):
+        return self.TABLE[word][0][2]
+
+
+def test_comma_filter_uses_the_taggers_own_tokens():
+    from prosody_b200 import intervals as IV
+    """ADVICE r1: the reference tags the whole mark and looks at the real previous spaCy token (audioPipeline.py:70-79)."""
+    tg = _FakeSpacyTagger()
+    assert IV.strip_spurious_commas("l'homme,", tg) == "l'homme,"          # previous token is NOUN "homme": comma stays
+    assert IV.strip_spurious_commas("dit-il,", tg) == "dit-il"             # previous token is PRON "-il": comma goes
+    assert IV.strip_spurious_commas("de, la", tg) == "dela"                # text_with_ws of the dropped comma goes with it
+    assert IV.first_pos(" l'homme ", tg) == "DET"                          # `_nlp(ptok.strip())[0].pos_`
+    # the pause after "l'homme" is dropped (first token DET), as the reference's filter does
+    grid = [(0.0, 0.5, "l'homme"), (0.5, 0.9, ""), (0.9, 1.4, "dit-il,")]
+    seq = IV.segment_sequence(grid, tg, 150)
+    assert [k for k, _, _ in seq] == ["word", "word"] and seq[1][1] == "dit-il"
