@@ -114,12 +114,14 @@ def run_cpu_baseline(pcm_host, pl, n_seg_sample, threads=0):
 
 def algorithmic_flops_per_frame(counters, geom):
     """F = 4 nw + 2 (2.5 N log2 N) + 1.5 N + 2 B + 3 L + 8 (sinc terms) + 5 K^2 — the REFERENCE
-    algorithm's work per frame (Praat's FFT size, Brent's sinc evaluations as counted by the oracle on this input)."""
+    algorithm's work per frame (Praat's FFT size, Brent's sinc evaluations as counted by the oracle on this input).
+    -> (autocorrelation part: window, two FFTs, power spectrum, normalisation = kernel K1;
+        candidate part: peak scan, sinc interpolation / Brent refinement = kernel K2;  the path finder's 5 K^2 = K3)"""
     nw, N, B, L = geom["nw"], geom["nfft"], geom["brent_ixmax"], geom["max_lag"]
     fr = max(counters["frames"], 1)
     terms = counters["sinc_terms"] / fr
     K = counters["candidates"] / fr + 1.0
-    return 4 * nw + 2 * 2.5 * N * math.log2(N) + 1.5 * N + 2 * B + 3 * L + 8.0 * terms + 5.0 * K * K
+    return 4 * nw + 2 * 2.5 * N * math.log2(N) + 1.5 * N + 2 * B, 3 * L + 8.0 * terms, 5.0 * K * K
 
 
 # ----------------------------------------------------------------------------------------------------------- clocks
@@ -229,7 +231,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        acc = dict(frames_ms=0.0, lufs_ms=0.0, path_ms=0.0, unit_stats_ms=0.0, h2d_ms=0.0, total_ms=0.0, host_plan_ms=0.0, n_launches=0, n_frames=0)
+        acc = dict(frames_ms=0.0, acf_ms=0.0, cand_ms=0.0, lufs_ms=0.0, path_ms=0.0, unit_stats_ms=0.0, h2d_ms=0.0, total_ms=0.0, host_plan_ms=0.0, n_launches=0, n_frames=0)
         for _ in range(steps):
             out = step(src)
             for k in acc:
@@ -262,30 +264,40 @@ def main():
         from oracle import oracle as O
         _, g, *_ = O.pitch_geometry(nat_n, float(SR), params=O.pitch_params(FLOOR, CEILING))
         geom = dict(nw=g.nsamp_window, nfft=g.nsampFFT, brent_ixmax=g.brent_ixmax, max_lag=g.maximumLag)
-        fpf = algorithmic_flops_per_frame(cpu["counters"], geom)
+        f_acf, f_cand, f_path = algorithmic_flops_per_frame(cpu["counters"], geom)
+        fpf = f_acf + f_cand + f_path
         frames_per_launch = acc["n_frames"] / args.steps
-        kernel_ms = acc["frames_ms"] / args.steps
-        achieved_tflops = fpf * frames_per_launch / (kernel_ms * 1e-3) / 1e12
-        # context only: the same launch with nothing beside it (inside the step the loudness kernels share the SMs with it)
+        kernel_ms = acc["acf_ms"] / args.steps                      # K1, the dominant kernel
+        cand_ms = acc["cand_ms"] / args.steps
+        frames_ms = acc["frames_ms"] / args.steps                   # K1 + K2 (+ the pair-position kernel), the round-1 kernel's job
+        achieved_tflops = f_acf * frames_per_launch / (kernel_ms * 1e-3) / 1e12
+        # context only: the same launches with nothing beside them (inside the step the loudness kernels share the SMs)
         alone = []
         for _ in range(2):
             ex.extract(pcm, pl.units, pb.pitch_params(FLOOR, CEILING), want_pitch=pl.want_pitch, want_lufs=np.zeros(n_units, np.uint8),
                        lufs=False, durations=False)
-            alone.append(ex.timings()["frames_ms"])
-        kernel_ms_alone = min(alone)
+            t_ = ex.timings()
+            alone.append((t_["acf_ms"], t_["cand_ms"], t_["frames_ms"]))
+        kernel_ms_alone = min(a_[0] for a_ in alone)
         peaks = {}
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except Exception:
             pass
-        sm_max = peaks.get("sm_max_mhz", 1965.0)
         info = ex.device_info()
-        fp32_peak = info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12        # FFMA lanes x 2 flop x max SM clock (nominal)
+        # FP32 (non-tensor) peak: MEASURED_PEAKS.json carries none, so it was measured on this pool with a dependent-free
+        # FFMA loop on every SM (scripts/fp32_peak_probe.cu -> profiles/r02_fp32_peak.json); nominal only if that is missing
+        try:
+            fp32_peak = float(json.loads((ROOT / "profiles" / "r02_fp32_peak.json").read_text())["best_burst_tflops"])
+            fp32_src = "measured: profiles/r02_fp32_peak.json (FFMA loop, all SMs)"
+        except Exception:
+            fp32_peak = info["sm_count"] * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+            fp32_src = "nominal: SMs x 128 lanes x 2 x max SM clock"
         alg_bytes = 2.0 * SR * 0.01 + 8.0      # per frame: s16 in once (10 ms hop) + f32 F0 + f32 strength
-        hbm_gbs = alg_bytes * frames_per_launch / (kernel_ms * 1e-3) / 1e9
+        hbm_gbs = alg_bytes * frames_per_launch / (frames_ms * 1e-3) / 1e9
         traffic = None       # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
         try:
-            tr = json.loads((ROOT / "profiles" / "r01_frames_traffic.json").read_text())
+            tr = json.loads((ROOT / "profiles" / "r02_acf_traffic.json").read_text())
             traffic = tr["bytes_per_frame"] * frames_per_launch
         except Exception:
             pass
@@ -303,15 +315,24 @@ def main():
             e2e=dict(value=e2e, unit="audio-s/s", h2d_bytes_per_step=int(host_pcm.numel() * 2 + n_units * 120),
                      d2h_bytes_per_step=int(n_units * 20), ms_per_step=1e3 * dt_e2e / args.steps),
             gpu_launches=int(acc["n_launches"]),
-            kernels_ms_per_step={k: acc[k] / args.steps for k in ("unit_stats_ms", "frames_ms", "path_ms", "lufs_ms", "h2d_ms", "total_ms", "host_plan_ms")},
-            roofline=dict(bound="fp32", kernel="pb_pitch_frames_kernel<10>", achieved=achieved_tflops, peak=fp32_peak, unit="TFLOP/s",
-                          frac=achieved_tflops / fp32_peak, traffic=traffic,
-                          note="non-tensor FP32 pipe: no stage is a dense contraction; peak = SMs x 128 FFMA lanes x 2 x max SM clock "
-                               "(nominal; MEASURED_PEAKS.json has no FP32 figure). achieved = the REFERENCE algorithm's flops per frame "
-                               f"({fpf:.0f}, oracle-counted on this input) x frames per launch / CUDA-event kernel time inside the step, where the "
-                               "loudness kernels run beside it on another stream (kernel_ms_alone / frac_alone: the same launch by itself)",
-                          flops_per_frame=fpf, frames_per_launch=int(frames_per_launch), kernel_ms=kernel_ms,
-                          kernel_ms_alone=kernel_ms_alone, frac_alone=fpf * frames_per_launch / (kernel_ms_alone * 1e-3) / 1e12 / fp32_peak,
+            kernels_ms_per_step={k: acc[k] / args.steps for k in ("unit_stats_ms", "frames_ms", "acf_ms", "cand_ms", "path_ms", "lufs_ms", "h2d_ms", "total_ms", "host_plan_ms")},
+            roofline=dict(bound="fp32", kernel="pb_pitch_acf_kernel<10>", achieved=achieved_tflops, peak=fp32_peak, unit="TFLOP/s",
+                          frac=achieved_tflops / fp32_peak, traffic=traffic, peak_source=fp32_src,
+                          note="non-tensor FP32 pipe: no stage is a dense contraction. Round 2 split the round-1 frames kernel in two: K1 "
+                               "pb_pitch_acf_kernel (window, two FFTs, power spectrum, normalisation; dominant) and K2 pb_pitch_cand_kernel (peak scan, "
+                               "sinc refinement). achieved = the REFERENCE algorithm's flops for K1's part of a frame "
+                               f"({f_acf:.0f} of {fpf:.0f}, oracle-counted on this input) x frames per launch / CUDA-event time of K1 inside the step, where "
+                               "the loudness kernels run beside it on another stream. `path` is K1+K2 together against all of the reference's "
+                               "per-frame flops: the figure comparable with round 1's frames kernel (0.19).",
+                          flops_per_frame=f_acf, frames_per_launch=int(frames_per_launch), kernel_ms=kernel_ms,
+                          kernel_ms_alone=kernel_ms_alone, frac_alone=f_acf * frames_per_launch / (kernel_ms_alone * 1e-3) / 1e12 / fp32_peak,
+                          cand=dict(kernel="pb_pitch_cand_kernel", kernel_ms=cand_ms, flops_per_frame=f_cand,
+                                    achieved=f_cand * frames_per_launch / (cand_ms * 1e-3) / 1e12,
+                                    frac=f_cand * frames_per_launch / (cand_ms * 1e-3) / 1e12 / fp32_peak),
+                          path=dict(kernels="K1+K2", kernel_ms=frames_ms, flops_per_frame=f_acf + f_cand,
+                                    achieved=(f_acf + f_cand) * frames_per_launch / (frames_ms * 1e-3) / 1e12,
+                                    frac=(f_acf + f_cand) * frames_per_launch / (frames_ms * 1e-3) / 1e12 / fp32_peak,
+                                    kernel_ms_alone=min(a_[2] for a_ in alone)),
                           hbm=dict(achieved=hbm_gbs, peak=peaks.get("hbm_gbs"), unit="GB/s",
                                    frac=(hbm_gbs / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None, bytes_per_frame=alg_bytes,
                                    peak_source="MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "absent")),

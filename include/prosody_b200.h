@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 1
+#define PB_ABI_VERSION 2
 
 enum {
     PB_OK = 0,
@@ -99,7 +99,7 @@ typedef struct PbTimings {
     float total_ms;        /* first enqueue .. last result on host */
     float h2d_ms;          /* PCM + descriptor upload */
     float unit_stats_ms;   /* K0: per-unit mean / global peak */
-    float frames_ms;       /* K1+K2: framing, FFT autocorrelation, candidates (dominant kernel) */
+    float frames_ms;       /* K1+K2 together: framing, FFT autocorrelation, candidates (acf_ms + cand_ms + the pair-position kernel) */
     float path_ms;         /* K3: Viterbi path finder + median of voiced */
     float lufs_ms;         /* K4: K-weighting + gated loudness */
     float intensity_ms;    /* K4b */
@@ -108,6 +108,8 @@ typedef struct PbTimings {
     int64_t n_lufs_samples;/* samples filtered */
     int32_t n_launches;    /* kernels launched */
     float host_plan_ms;    /* host wall time spent planning the units before the first enqueue */
+    float acf_ms;          /* K1: windowing + FFT autocorrelation -> global scratch (dominant kernel) */
+    float cand_ms;         /* K2: candidate search + sinc refinement */
 } PbTimings;
 
 int pb_abi_version(void);

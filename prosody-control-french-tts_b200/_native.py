@@ -38,7 +38,8 @@ class PbUnits(C.Structure):
 class PbTimings(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("h2d_ms", C.c_float), ("unit_stats_ms", C.c_float), ("frames_ms", C.c_float),
                 ("path_ms", C.c_float), ("lufs_ms", C.c_float), ("intensity_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("n_frames", C.c_int64), ("n_lufs_samples", C.c_int64), ("n_launches", C.c_int32), ("host_plan_ms", C.c_float)]
+                ("n_frames", C.c_int64), ("n_lufs_samples", C.c_int64), ("n_launches", C.c_int32), ("host_plan_ms", C.c_float),
+                ("acf_ms", C.c_float), ("cand_ms", C.c_float)]
 
 
 class PbDeltaParams(C.Structure):
@@ -103,7 +104,7 @@ def load(path: str | Path | None = None) -> C.CDLL:
             raise NativeError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
                               "(nvcc, sm_100a). There is no CPU fallback.")
         _lib = bind(C.CDLL(str(LIB_PATH)))
-        if _lib.pb_abi_version() != 1:
+        if _lib.pb_abi_version() != 2:
             raise NativeError("libprosody_b200.so has an unexpected ABI version")
     return _lib
 

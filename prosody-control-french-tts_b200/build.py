@@ -10,7 +10,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libprosody_b200.so"
 SOURCES = [CSRC / "pb_api.cu"]
-HEADERS = [CSRC / "pb_api_host.inc", CSRC / "pb_api_next.inc", CSRC / "pb_api_silence.inc", CSRC / "pb_textgrid.inc", CSRC / "pb_silence.cuh", CSRC / "pb_intervals.cuh", CSRC / "pb_stream.cuh", CSRC / "pb_rt.h", CSRC / "pb_plan.h", CSRC / "pb_pitch.cuh", CSRC / "pb_pitch_frames.cuh", CSRC / "pb_pitch_path.cuh", CSRC / "pb_lufs.cuh",
+HEADERS = [CSRC / "pb_api_host.inc", CSRC / "pb_api_next.inc", CSRC / "pb_api_silence.inc", CSRC / "pb_textgrid.inc", CSRC / "pb_silence.cuh", CSRC / "pb_intervals.cuh", CSRC / "pb_stream.cuh", CSRC / "pb_rt.h", CSRC / "pb_plan.h", CSRC / "pb_pitch.cuh", CSRC / "pb_pitch_acf.cuh", CSRC / "pb_pitch_cand.cuh", CSRC / "pb_async.cuh", CSRC / "pb_pitch_path.cuh", CSRC / "pb_lufs.cuh",
            HERE.parent / "include" / "prosody_b200.h"]
 
 

@@ -10,7 +10,8 @@
 #include "pb_rt.h"
 #include "pb_plan.h"
 #include "pb_pitch.cuh"
-#include "pb_pitch_frames.cuh"
+#include "pb_pitch_acf.cuh"
+#include "pb_pitch_cand.cuh"
 #include "pb_pitch_path.cuh"
 #include "pb_lufs.cuh"
 #include "pb_silence.cuh"
@@ -124,6 +125,8 @@ struct PbHandle {
     // device buffers (grow on demand)
     DevBuf pcm, units, pair_off, cand_f, cand_s, ncand, inten, psi, sel_f, sel_s, med, nvoiced;
     DevBuf lunits, meters, lstate, lenergy, lufs, pairpos;
+    DevBuf racf, slot_fr, work_ctr;                        // K1 -> K2: autocorrelations of one launch chunk, slot -> frame map, K2's chunk counter
+    size_t cand_smem = 0; int cand_per_sm = 1;             // K2: footprint its function attribute was set for, resident CTAs per SM
     HostBuf stage_units, stage_pairs, stage_lunits, stage_meters, stage_out;
     size_t su_off = 0, sp_off = 0, sl_off = 0;           // running offsets (elements) into the pinned staging buffers
     std::map<std::pair<int64_t, int>, PitchTables*> tables;
@@ -162,7 +165,7 @@ struct ScopedEv {     // records an event pair around a section of a stream
     }
     ~ScopedEv() { pbrt_event_record(&h->evs[idx].b, s); }
 };
-enum { EV_TOTAL = 0, EV_H2D, EV_STATS, EV_FRAMES, EV_PATH, EV_LUFS, EV_INTENSITY, EV_D2H };
+enum { EV_TOTAL = 0, EV_H2D, EV_STATS, EV_FRAMES, EV_PATH, EV_LUFS, EV_INTENSITY, EV_D2H, EV_ACF, EV_CAND };
 
 void begin_call(PbHandle* h) {
     pbrt_stream_sync(h->lufs_stream);          // belt and braces: failed calls drain their streams themselves (DrainOnError)
@@ -171,8 +174,13 @@ void begin_call(PbHandle* h) {
     memset(&h->last, 0, sizeof h->last);
 }
 void end_call(PbHandle* h) {   // after the streams have been synchronised
-    float* f = &h->last.total_ms;
-    for (auto& p : h->evs) f[p.kind] += pbrt_event_ms(p.a, p.b);
+    float* f = &h->last.total_ms;                       // kinds 0..7 are the first eight floats of PbTimings, in order
+    for (auto& p : h->evs) {
+        const float ms = pbrt_event_ms(p.a, p.b);
+        if (p.kind == EV_ACF) h->last.acf_ms += ms;
+        else if (p.kind == EV_CAND) h->last.cand_ms += ms;
+        else f[p.kind] += ms;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ tables
@@ -426,14 +434,20 @@ int plan_lufs(PbHandle* h, const PbUnits* u, const uint8_t* want, int32_t* flags
 }
 
 // ------------------------------------------------------------------------------------------------ launches
+// K1 (autocorrelation of every frame pair -> global scratch) and K2 (candidates from the scratch), in chunks of pairs so the
+// scratch stays bounded (PB_RACF_BYTES, default 4 GiB): 2 * rstride_g floats per pair.
 template <int LOG2N>
 int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, const int32_t* d_pair_off, const PbPitchGeomDev& gm,
                   float* cand_f, float* cand_s, uint8_t* ncand, float* inten) {
     typedef PbFftCfg<LOG2N> C;
-    const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + 72 * sizeof(float);
+    const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + C::GROUPS_PER_CTA * sizeof(pbMbar);
     const int threads = C::WARPS_PER_CTA * 32;
-    auto kfn = pb_pitch_frames_kernel<LOG2N>;
+    auto kfn = pb_pitch_acf_kernel<LOG2N>;
+    static const int cand_ctas = [] { const char* e = getenv("PB_CAND_CTAS"); return e ? atoi(e) : 10; }();
+    auto cfn = cand_ctas == 8 ? pb_pitch_cand_kernel<8> : cand_ctas == 12 ? pb_pitch_cand_kernel<12> : pb_pitch_cand_kernel<10>;
     int per_sm = 2;
+    const int rstride_g = (gm.brent_ixmax + 2 + 3) & ~3;                 // floats per frame in the scratch (16-byte rows for the bulk copies)
+    const size_t cand_smem = (size_t)PB_CAND_WARPS * ((size_t)(2 * rstride_g + 3 * PB_MAXC) * sizeof(float) + 2 * sizeof(pbMbar)) + 72 * sizeof(float);
 #ifndef PB_SIMT_EMU
     // function attributes persist, so they are (re)applied whenever the shared-memory footprint of this instantiation
     // changes (another analysis geometry with the same FFT size)
@@ -452,19 +466,53 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
         h->occ_cache[okey] = per_sm;
         h->occ_last[LOG2N] = smem;
     } else per_sm = oc->second;
+    if (h->cand_smem != cand_smem) {
+        if (cudaFuncSetAttribute(cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem) != cudaSuccess)
+            return fail(h, PB_ECUDA, "cudaFuncSetAttribute: %s", pbrt_error());
+        cudaFuncSetAttribute(cfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int cps = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, cfn, PB_CAND_WARPS * 32, cand_smem) != cudaSuccess || cps < 1) cps = 1;
+        h->cand_per_sm = cps; h->cand_smem = cand_smem;
+    }
+#else
+    h->cand_per_sm = 2;
 #endif
-    long long need = ((long long)gm.n_pairs + C::GROUPS_PER_CTA - 1) / C::GROUPS_PER_CTA;
     { const char* e = getenv("PB_FRAMES_CTAS"); if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e); }   // experiments: fewer resident CTAs
-    long long cap = (long long)h->sm_count * per_sm;
-    int grid = (int)std::max(1LL, std::min(need, cap));
-    // frame positions of every pair (float64 arithmetic, once), then the frames kernel itself
+    // frame positions of every pair (float64 arithmetic, once)
     PB_CKMEM(h->pairpos.ensure((size_t)gm.n_pairs * sizeof(int2) + 16), "pair positions");
     {
         const int pgrid = (int)std::max(1LL, std::min(((long long)gm.n_pairs + 255) / 256, (long long)h->sm_count * 8));
         PB_LAUNCH(pb_pair_pos_kernel, dim3(pgrid), dim3(256), 0, h->stream, d_units, d_pair_off, gm, (int2*)h->pairpos.p);
+        h->last.n_launches++;
     }
-    PB_LAUNCH(kfn, dim3(grid), dim3(threads), smem, h->stream, d_pcm, d_units, d_pair_off, (const int2*)h->pairpos.p, gm, cand_f, cand_s, ncand, inten);
-    h->last.n_launches += 2;
+    static const size_t racf_budget = [] { const char* e = getenv("PB_RACF_BYTES"); const long long v = e ? atoll(e) : 0; return (size_t)(v > 0 ? v : (4LL << 30)); }();
+    const size_t pair_bytes = 2 * (size_t)rstride_g * sizeof(float);
+    const long long chunk_pairs = std::max<long long>(1024, (long long)(racf_budget / pair_bytes));
+    const long long max_items = std::min<long long>(gm.n_pairs, chunk_pairs);
+    PB_CKMEM(h->racf.ensure((size_t)max_items * pair_bytes + 64) || h->slot_fr.ensure((size_t)max_items * 2 * sizeof(long long) + 64) ||
+             h->work_ctr.ensure(sizeof(unsigned) * 4096), "autocorrelation scratch");
+    const long long n_chunks = ((long long)gm.n_pairs + chunk_pairs - 1) / chunk_pairs;
+    if (n_chunks > 4096) return fail(h, PB_EUNSUPPORTED, "%s", "PB_RACF_BYTES too small for this batch");
+    PB_CK(pbrt_memset(h->work_ctr.p, 0, sizeof(unsigned) * (size_t)n_chunks, h->stream), "memset");
+    for (long long ck = 0; ck < n_chunks; ck++) {
+        const int item0 = (int)(ck * chunk_pairs);
+        const int n_items = (int)std::min<long long>(chunk_pairs, (long long)gm.n_pairs - item0);
+        const long long need = ((long long)n_items + C::GROUPS_PER_CTA - 1) / C::GROUPS_PER_CTA;
+        const int grid = (int)std::max(1LL, std::min(need, (long long)h->sm_count * per_sm));
+        {
+            ScopedEv ev(h, EV_ACF);
+            PB_LAUNCH(kfn, dim3(grid), dim3(threads), smem, h->stream, d_pcm, d_units, d_pair_off, (const int2*)h->pairpos.p, gm, item0, n_items, rstride_g,
+                      (float*)h->racf.p, (long long*)h->slot_fr.p, cand_f, cand_s, ncand, inten);
+        }
+        {
+            ScopedEv ev(h, EV_CAND);
+            const int n_slots = 2 * n_items;
+            const int cgrid = (int)std::max(1LL, std::min<long long>(((long long)n_slots + 32 * PB_CAND_WARPS - 1) / (32 * PB_CAND_WARPS), (long long)h->sm_count * h->cand_per_sm));
+            PB_LAUNCH(cfn, dim3(cgrid), dim3(PB_CAND_WARPS * 32), cand_smem, h->stream, (const float*)h->racf.p, (const long long*)h->slot_fr.p,
+                      n_slots, rstride_g, gm, cand_f, cand_s, ncand, (unsigned*)h->work_ctr.p + ck);
+        }
+        h->last.n_launches += 2;
+    }
     return PB_OK;
 }
 
@@ -946,7 +994,7 @@ void pb_destroy(PbHandle* h) {
     pbrt_stream_sync(h->copy_stream);
     pbrt_stream_sync(h->lufs_stream);
     DevBuf* dbs[] = {&h->pcm, &h->units, &h->pair_off, &h->cand_f, &h->cand_s, &h->ncand, &h->inten, &h->psi, &h->sel_f, &h->sel_s,
-                     &h->med, &h->nvoiced, &h->lunits, &h->meters, &h->lstate, &h->lenergy, &h->lufs, &h->pairpos};
+                     &h->med, &h->nvoiced, &h->lunits, &h->meters, &h->lstate, &h->lenergy, &h->lufs, &h->pairpos, &h->racf, &h->slot_fr, &h->work_ctr};
     for (auto* b : dbs) b->release();
     HostBuf* hbs[] = {&h->stage_units, &h->stage_pairs, &h->stage_lunits, &h->stage_meters, &h->stage_out};
     for (auto* b : hbs) b->release();

@@ -1,0 +1,384 @@
+// pb_pitch_acf.cuh — K1: frames -> normalised autocorrelation, written to a global scratch for K2 (pb_pitch_cand.cuh).
+//
+// Follows the first half of Sound_into_PitchFrame (Praat fon/Sound_to_Pitch.cpp, AC_HANNING): local mean, Hanning window,
+// autocorrelation by FFT, division by the window's autocorrelation.  See pb_pitch.cuh for the layout of the F0 path.
+//
+// Round 1 ran this and the candidate search as ONE kernel (pb_pitch_frames_kernel): its loop body was twice the 32 KB
+// instruction cache, its 128 registers (the radix-32 butterflies) capped residency at 4 warps per scheduler for the
+// latency-bound candidate search as well, and 40 % of its executed instructions were integer / control overhead
+// (profiles/r01_frames_v6_*).  Split in two, K1 is a compact FFT kernel that fits the instruction cache and K2 runs at
+// 3x the residency; r goes through HBM once (1.3 KB per frame at 16 kHz / 75 Hz), far below what the memory system can
+// absorb beside the arithmetic (profiles/r02_*).
+//
+// Per work item a GROUP of G warps (G = 1 for FFT sizes <= 1024) owns a PAIR of consecutive frames:
+//   * the samples both frames read are staged by ONE cp.async.bulk (TMA, pb_async.cuh) issued as soon as the previous
+//     pair has been windowed; they land while that pair is transformed;
+//   * both real frames are windowed into one complex sequence a + i b and transformed together; the two power spectra
+//     are separated with the conjugate-symmetry identity, packed again and transformed back (the spectra are real and
+//     even, so a forward transform returns both autocorrelations);
+//   * r[lag] = ac[lag] / (ac[0] windowR[lag]) for lags 0..B+1 of both frames goes to racf[slot], slot = 2 * item + frame.
+// Everything index-like is hoisted: shared-memory addresses of the FFT passes are one base register plus compile-time
+// offsets, the pass-specific stores are two straight-line variants instead of one with a runtime stride.
+#pragma once
+#include "pb_async.cuh"
+#include "pb_pitch.cuh"
+
+// Where a frame pair's samples sit: part index of frame A's sample 0, distance to frame B, and the offset of frame A's
+// sample `span_lo` inside the staged (16-byte aligned) range.
+struct PbPairPos { int start0; int hop; int shift; int edge; };
+
+// Frame position, Praat's Sampled_indexToX / Sampled_xToLowIndex in float64 with explicit rounding (no FMA contraction):
+// returns the 1-based part index of frame sample n = 0.
+__device__ __forceinline__ long long pb_frame_start(double t1, double x1, int frame, const PbPitchGeomDev& gm) {
+    const double t = __dadd_rn(t1, __dmul_rn((double)frame, gm.dt));
+    const long long left = (long long)floor(__ddiv_rn(__dsub_rn(t, x1), gm.dx)) + 1;
+    return left + 1 - gm.half_nw;
+}
+
+// The float64 frame positions of every pair, computed once by a small kernel ahead of K1: {start0, hop}.
+__global__ void __launch_bounds__(256)
+pb_pair_pos_kernel(const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off, PbPitchGeomDev gm, int2* __restrict__ out) {
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < gm.n_pairs; item += gridDim.x * blockDim.x) {
+        const int u = pb_upper_unit(pair_off, gm.n_units, item);
+        const PbUnitDev* ud = units + u;
+        const int fA = 2 * (item - ud->pair_off);
+        const long long s0 = pb_frame_start(ud->t1, ud->x1, fA, gm);
+        const int hop = fA + 1 < ud->n_frames ? (int)(pb_frame_start(ud->t1, ud->x1, fA + 1, gm) - s0) : 0;
+        out[item] = make_int2((int)s0, hop);
+    }
+}
+
+// Stage the samples the pair (frames fA, fA+1 of unit ud) will read into `dst`: every 16-byte chunk that lies entirely
+// inside the pcm buffer goes in ONE bulk copy issued by thread 0 of the group (completion on `bar`); the (at most two)
+// chunks straddling the ends of the buffer are filled sample by sample and flagged in pos.edge so that the group
+// synchronises before reading them.  Values outside the unit's part / file are masked at read time.
+template <int GT>
+__device__ __forceinline__ PbPairPos pb_stage_pair(const int16_t* __restrict__ pcm, const PbUnitDev& ud, int2 sp, const PbPitchGeomDev& gm,
+                                                   int span_lo, int span_len, int16_t* dst, int g, pbMbar* bar) {
+    PbPairPos pos;
+    pos.start0 = sp.x; pos.hop = sp.y; pos.edge = 0;
+    // frame A sample n is part sample start0+n = pcm sample pcm_off + ix1 + start0 + n - 2
+    const long long gs = ud.pcm_off + ud.ix1 + (long long)pos.start0 - 2 + span_lo;
+    const long long byte0 = (long long)(size_t)pcm + 2 * gs;            // may lie outside the buffer: never dereferenced there
+    const long long a0 = byte0 & ~15LL;
+    pos.shift = (int)((byte0 - a0) >> 1);
+    const long long a1 = a0 + 16LL * ((pos.shift + span_len + pos.hop + 7) >> 3);      // end of the staged range
+    const long long buf_lo = (long long)(size_t)pcm, buf_hi = buf_lo + 2 * gm.pcm_len;
+    const long long lo16 = (buf_lo + 15) & ~15LL, hi16 = buf_hi & ~15LL;                // whole chunks inside the buffer
+    const long long c0 = a0 > lo16 ? a0 : lo16, c1 = a1 < hi16 ? a1 : hi16;
+    if (g == 0) {
+        const unsigned bytes = c1 > c0 ? (unsigned)(c1 - c0) : 0u;
+        pb_mbar_expect_tx(bar, bytes);
+        if (bytes) pb_bulk_g2s((char*)dst + (c0 - a0), (const void*)(size_t)c0, bytes, bar);
+    }
+    if (a0 < c0 || a1 > c1) {
+        // chunks that are not wholly inside the buffer (first / last file of the call only)
+        pos.edge = 1;
+        const long long e0 = c1 > c0 ? c0 : a1, e1 = c1 > c0 ? c1 : a1;    // [a0, e0) and [e1, a1) are filled here
+        for (long long b = a0 + 2 * g; b < a1; b += 2 * GT) {
+            if (b >= e0 && b < e1) continue;
+            *(int16_t*)((char*)dst + (b - a0)) = (b >= buf_lo && b + 2 <= buf_hi) ? *(const int16_t*)(size_t)b : (int16_t)0;
+        }
+    }
+    return pos;
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+template <int LOG2N>
+__global__ void __launch_bounds__(PbFftCfg<LOG2N>::WARPS_PER_CTA * 32, PbFftCfg<LOG2N>::MIN_CTAS)
+pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off,
+                    const int2* __restrict__ pairpos, PbPitchGeomDev gm, int item0, int n_items, int rstride_g,
+                    float* __restrict__ racf, long long* __restrict__ slot_fr,
+                    float* __restrict__ cand_f, float* __restrict__ cand_s, uint8_t* __restrict__ ncand, float* __restrict__ intensity) {
+    typedef PbFftCfg<LOG2N> C;
+    constexpr int R = C::R, LR = C::LR, N = C::N, G = C::G, GT = C::GT;
+    constexpr bool FAST = (R == 32);                    // compile-time shared-memory offsets (all sizes >= 1024)
+    PB_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = warp / G, wg = warp % G;          // group in CTA, warp in group
+    const int g = wg * 32 + lane;                       // thread in group = butterfly index
+    const int bar_id = 1 + group;
+    // per-group shared memory: FFT buffer, a small reduction scratch, the sample staging buffer; CTA-wide: one mbarrier per group
+    const size_t group_bytes = (size_t)(C::BUF + 8 * G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t);
+    unsigned char* gbase = smem_raw + (size_t)group * group_bytes;
+    float2* buf = (float2*)gbase;
+    float* red = (float*)(buf + C::BUF);                // [G][4] floats
+    int16_t* pre = (int16_t*)(buf + C::BUF + 8 * G);    // [pre_cap] staged samples of one pair
+    pbMbar* mbar = (pbMbar*)(smem_raw + (size_t)C::GROUPS_PER_CTA * group_bytes) + group;
+    if (g == 0) pb_mbar_init(mbar, 1);
+    pb_mbar_init_fence();
+    __syncthreads();
+    unsigned phase = 0;
+    const int B = gm.brent_ixmax;
+    const int nw = gm.nw;
+    const int pk_lo = max(0, gm.half_nw - gm.half_period), pk_n = min(nw, gm.half_nw + gm.half_period) - pk_lo;   // [lo, lo + n)
+    const int mean_n0 = gm.half_nw - gm.nsamp_period;   // local mean spans frame samples [mean_n0, mean_n0 + 2 P)
+    const int mean_len = 2 * gm.nsamp_period;
+    const int span_lo = min(0, mean_n0);                // staged range of frame samples: [span_lo, span_lo + span_len)
+    const int span_hi = max(nw, mean_n0 + mean_len);
+    const int span_len = span_hi - span_lo;
+    const float mean_scale = (float)(1.0 / (32768.0 * (double)mean_len));
+
+    // Blocked distribution: a group walks a contiguous range of frame pairs, so consecutive iterations stay in the same
+    // unit and the next pair's samples are staged while the current pair is transformed.
+    const int n_groups = gridDim.x * C::GROUPS_PER_CTA;
+    const int per_group = (n_items + n_groups - 1) / n_groups;
+    const int it_begin = (blockIdx.x * C::GROUPS_PER_CTA + group) * per_group;
+    const int it_end = min(n_items, it_begin + per_group);
+    if (it_begin >= it_end) return;
+    int u_next = pb_upper_unit(pair_off, gm.n_units, item0 + it_begin);
+    int u_next_end = pair_off[u_next + 1];
+    PbUnitDev ud = units[u_next];
+    int u = u_next;
+    PbPairPos pos_next = pb_stage_pair<GT>(pcm, ud, pairpos[item0 + it_begin], gm, span_lo, span_len, pre, g, mbar);
+    // per unit: the part indices that hold samples, [pmin, pmax1)  (inside the part and inside the file)
+    long long pmin = 0, pmax1 = 0;
+    bool unit_fresh = true;
+
+    for (int li = it_begin; li < it_end; li++) {
+        const int item = item0 + li;
+        const PbPairPos pos = pos_next;
+        if (unit_fresh) {
+            pmin = 2 - ud.ix1 > 1 ? 2 - ud.ix1 : 1;
+            const long long e = (long long)ud.file_nx - ud.ix1 + 1;
+            pmax1 = (ud.nx < e ? ud.nx : e) + 1;
+            unit_fresh = false;
+        }
+        const int fA = 2 * (item - ud.pair_off);
+        const bool hasB = fA + 1 < ud.n_frames;
+        const bool global_silent = ud.global_peak == 0.0;
+        const long long frA = ud.frame_off + fA;
+        const float gpk = (float)ud.global_peak;
+        pb_mbar_wait(mbar, phase); phase ^= 1u;          // this pair's samples (requested during the previous pair) have landed
+#ifdef PB_SIMT_EMU
+        pb_group_sync<G>(bar_id);
+#else
+        if (pos.edge) pb_group_sync<G>(bar_id);          // edge chunks were filled with ordinary stores
+#endif
+        const int16_t* sm = pre;
+        const int sb0 = pos.shift - span_lo, sb1 = sb0 + pos.hop;       // staged index of frame sample n is sb + n
+        float pkA = 0.0f, pkB = 0.0f, mxA = 0.0f, mxB = 0.0f;
+        // valid frame samples n: [nlo, nhi)
+        const long long loA = pmin - pos.start0, hiA = pmax1 - pos.start0;
+        const bool interior = hasB && loA <= span_lo && hiA - pos.hop >= span_hi;      // frame B's range is frame A's shifted by hop
+        if (interior) {
+            // ---- local mean: one longest period to both sides of the frame centre (exact integer sums)
+            int s0 = 0, s1 = 0;
+            const int16_t* m0 = sm + sb0 + mean_n0; const int16_t* m1 = sm + sb1 + mean_n0;
+            for (int q = lane; q < mean_len; q += 32) { s0 += (int)m0[q]; s1 += (int)m1[q]; }
+            s0 = pb_warp_sum_i(s0); s1 = pb_warp_sum_i(s1);
+            const float2 nmean = make_float2(-(float)s0 * mean_scale, -(float)s1 * mean_scale);
+            const float2 q15 = make_float2(1.0f / 32768.0f, 1.0f / 32768.0f);
+            // ---- window both frames into the FFT buffer, z = a + i b (natural order), two samples per thread and step
+            const int16_t* pa = sm + sb0; const int16_t* pb = sm + sb1;
+#ifndef PB_SIMT_EMU
+#pragma unroll 2
+#endif
+            for (int n = 2 * g; n < nw; n += 2 * GT) {
+                const float2 w = __ldg((const float2*)(gm.window + n));
+                const float2 x0 = __ffma2_rn(make_float2((float)pa[n], (float)pb[n]), q15, nmean);
+                const float2 x1 = __ffma2_rn(make_float2((float)pa[n + 1], (float)pb[n + 1]), q15, nmean);
+                const float2 ab0 = __fmul2_rn(x0, make_float2(w.x, w.x)), ab1 = __fmul2_rn(x1, make_float2(w.y, w.y));
+                mxA = fmaxf(mxA, fmaxf(fabsf(ab0.x), fabsf(ab1.x))); mxB = fmaxf(mxB, fmaxf(fabsf(ab0.y), fabsf(ab1.y)));
+                if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, fabsf(ab0.x)); pkB = fmaxf(pkB, fabsf(ab0.y)); }
+                if ((unsigned)(n + 1 - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, fabsf(ab1.x)); pkB = fmaxf(pkB, fabsf(ab1.y)); }
+                float2* d = buf + pb_pad5(n);           // n is even: n + 1 shares its 32-element row
+                d[0] = ab0; d[1] = ab1;
+            }
+        } else {
+            // ---- first / last frames of a slice that Praat zero-fills beyond the file, or a unit with an odd frame count
+            int nlo[2], nhi[2], sb[2]; float lmean[2];
+            PB_UNROLL for (int f = 0; f < 2; f++) {
+                long long lo = loA - (f ? pos.hop : 0), hi = hiA - (f ? pos.hop : 0);
+                const long long BIG = 1 << 30;
+                nlo[f] = (int)(lo < -BIG ? -BIG : (lo > BIG ? BIG : lo));
+                nhi[f] = (int)(hi < -BIG ? -BIG : (hi > BIG ? BIG : hi));
+                sb[f] = f ? sb1 : sb0;
+                int s = 0;
+                for (int q = lane; q < mean_len; q += 32) {
+                    const int n = mean_n0 + q;
+                    s += (n >= nlo[f] && n < nhi[f]) ? (int)sm[sb[f] + n] : 0;
+                }
+                s = pb_warp_sum_i(s);
+                lmean[f] = (float)s * mean_scale;
+            }
+            if (!hasB) { nlo[1] = 0; nhi[1] = 0; sb[1] = sb[0]; }
+            const float2 nmean = make_float2(-lmean[0], -lmean[1]), q15 = make_float2(1.0f / 32768.0f, 1.0f / 32768.0f);
+            const float hb = hasB ? 1.0f : 0.0f;
+            for (int n = g; n < nw; n += GT) {
+                const float w = __ldg(&gm.window[n]);
+                const int sa = (n >= nlo[0] && n < nhi[0]) ? (int)sm[sb[0] + n] : 0;
+                const int sbv = (n >= nlo[1] && n < nhi[1]) ? (int)sm[sb[1] + n] : 0;
+                const float2 ab = __fmul2_rn(__ffma2_rn(make_float2((float)sa, (float)sbv), q15, nmean), make_float2(w, w * hb));
+                const float aa = fabsf(ab.x), bb = fabsf(ab.y);
+                mxA = fmaxf(mxA, aa); mxB = fmaxf(mxB, bb);
+                if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, bb); }
+                buf[pb_pad5(n)] = ab;
+            }
+        }
+        for (int n = nw + 2 * g; n < N; n += 2 * GT) { float2* d = buf + pb_pad5(n); d[0] = make_float2(0.0f, 0.0f); d[1] = make_float2(0.0f, 0.0f); }   // zero padding (nw, N even)
+        mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB); pkA = pb_warp_max(pkA); pkB = pb_warp_max(pkB);
+        if (G > 1) {
+            if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; red[wg * 4 + 2] = pkA; red[wg * 4 + 3] = pkB; }
+            pb_group_sync<G>(bar_id);
+            for (int k = 0; k < G; k++) {
+                mxA = fmaxf(mxA, red[k * 4 + 0]); mxB = fmaxf(mxB, red[k * 4 + 1]);
+                pkA = fmaxf(pkA, red[k * 4 + 2]); pkB = fmaxf(pkB, red[k * 4 + 3]);
+            }
+        }
+        const bool active = !global_silent && (pkA > 0.0f || pkB > 0.0f);
+        // bring both frames to comparable magnitude (power-of-two scales are exact and cancel in r = ac/ac[0]):
+        // keeps the weaker frame of a pair out of the stronger one's rounding noise
+        const float sA = mxA > 0.0f ? __int_as_float((254 - ((__float_as_int(mxA) >> 23) & 0xff)) << 23) : 1.0f;
+        const float sB = mxB > 0.0f ? __int_as_float((254 - ((__float_as_int(mxB) >> 23) & 0xff)) << 23) : 1.0f;
+        pb_group_sync<G>(bar_id);                       // the windowed frames are in the buffer, the staged samples are consumed
+        // request the next pair's samples now: they land while this pair is transformed
+        if (li + 1 < it_end) {
+            if (item + 1 >= u_next_end) {
+                do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end);
+            }
+            // the descriptor of the next unit is only adopted at the top of the next iteration
+            pos_next = pb_stage_pair<GT>(pcm, u_next == u ? ud : units[u_next], pairpos[item + 1], gm, span_lo, span_len, pre, g, mbar);
+        }
+
+        // ---- two FFTs x two passes through ONE copy of the butterfly code: FFT (step >> 1), pass (step & 1).  The step
+        //      index is made opaque so the optimiser neither peels nor unswitches the loop (either duplicates the
+        //      ~300-instruction network).
+        float2 v[R];
+        int n_steps = active ? 4 : 0;
+        asm volatile("" : "+r"(n_steps));
+#ifndef PB_SIMT_EMU
+#pragma unroll 1
+#endif
+        for (int s_it = 0; s_it < n_steps; s_it++) {
+            int step = s_it;
+            asm volatile("" : "+r"(step));
+            int pass = step & 1;
+            asm volatile("" : "+r"(pass));
+            // pass 1 reads natural order: the windowed frames (step 0) or the spectra (step 2);
+            // pass 2 reads the pass-1 layout and applies the inter-pass twiddles
+            if (FAST) {
+                // i = g + 32 G t  ->  i + (i >> 5) = g + (g >> 5) + 33 G t: one base, compile-time offsets
+                const float2* src = buf + (g + (g >> 5));
+                PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * (33 * G)];
+            } else {
+                const int sh = pass ? LR : 5;
+                PB_UNROLL for (int t = 0; t < R; t++) { const int i = g + t * (N / R); v[t] = buf[i + (i >> sh)]; }
+            }
+            if (step == 0) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
+            if (pass) {
+                const float2* tw = gm.tw_a + (g & (R - 1));
+                PB_UNROLL for (int t = 1; t < R; t++) {
+                    const float2 w = __ldg(tw + t * R);
+                    const float2 x = v[t];
+                    v[t] = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(x.x, x.x), w));   // x * w
+                }
+            }
+            pb_group_sync<G>(bar_id);                   // every load of this step is done before any store
+            pb_dft<R>(v);
+            // pass 1 (Ns = 1): out[g*R + t], skew (index >> LR);  pass 2 (Ns = R): out[(g/R) R^2 + g%R + t R], skew 5
+            if (FAST) {
+                // pass 1: 32 g + t -> 33 g + t;  pass 2: (g>>5) 1024 + (g&31) + 32 t -> (g>>5) 1056 + (g&31) + 33 t
+                if (pass) {
+                    float2* dst = buf + ((g >> 5) * 1056 + (g & 31));
+                    PB_UNROLL for (int t = 0; t < R; t++) dst[t * 33] = v[pb_bitrev(t, LR)];
+                } else {
+                    float2* dst = buf + 33 * g;
+                    PB_UNROLL for (int t = 0; t < R; t++) dst[t] = v[pb_bitrev(t, LR)];
+                }
+            } else {
+                const int ob = pass ? ((g >> LR) * (R * R) + (g & (R - 1))) : g * R;
+                const int os = pass ? R : 1;
+                const int osh = pass ? 5 : LR;
+                PB_UNROLL for (int t = 0; t < R; t++) { const int o = ob + t * os; buf[o + (o >> osh)] = v[pb_bitrev(t, LR)]; }
+            }
+            pb_group_sync<G>(bar_id);
+            if (pass && C::F > 1) {
+                // ---- final pass (radix F, Ns = R*R): butterflies are in place
+                constexpr int F = C::F > 1 ? C::F : 2, LF = pb_ilog2(F);
+                PB_UNROLL for (int b = 0; b < C::FB; b++) {
+                    const int j = g + b * GT;             // 0 .. N/F-1 = R*R-1
+                    float2 a[F];
+                    PB_UNROLL for (int t = 0; t < F; t++) a[t] = buf[pb_pad5(j + t * (R * R))];
+                    PB_UNROLL for (int t = 1; t < F; t++) {
+                        const float2 w = __ldg(&gm.tw_b[t * (R * R) + j]);
+                        const float2 x = a[t];
+                        a[t] = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+                    }
+                    pb_dft<F>(a);
+                    PB_UNROLL for (int t = 0; t < F; t++) buf[pb_pad5(j + t * (R * R))] = a[pb_bitrev(t, LF)];
+                }
+                pb_group_sync<G>(bar_id);
+            }
+            if (step == 1) {
+                // ---- power spectra of both frames from Z = FFT(a + i b):  4 P_a = |Z_k + conj Z_-k|^2,  4 P_b = |Z_k - conj Z_-k|^2,
+                //      packed again as P_a + i P_b (real and even: written to k and N - k)
+                if (FAST && G == 1) {
+                    // k = g + 32 i -> slot g + 33 i;  N - k = 32 (31 - i) + (32 - g) -> slot (32 - g) + 33 (31 - i)   (g > 0)
+                    // lane 0: N - k = 32 (32 - i) -> slot 33 (32 - i); k = 0 pairs with itself
+                    const float2* pk_ = buf + g;
+                    float2* qk = buf + (g ? 32 - g : 33);
+                    PB_UNROLL for (int i = 0; i < 16; i++) {
+                        const float2 za = pk_[33 * i];
+                        float2 zb = qk[33 * (31 - i)];
+                        if (i == 0 && g == 0) zb = za;
+                        const float2 p = make_float2(za.x + zb.x, za.y - zb.y), q = make_float2(za.x - zb.x, za.y + zb.y);
+                        const float2 w = make_float2(p.x * p.x + p.y * p.y, q.x * q.x + q.y * q.y);
+                        ((float2*)pk_)[33 * i] = w;
+                        if (!(i == 0 && g == 0)) qk[33 * (31 - i)] = w;
+                    }
+                    if (g == 0) {                          // k = 512 pairs with itself
+                        const float2 za = buf[pb_pad5(N / 2)];
+                        buf[pb_pad5(N / 2)] = make_float2(4.0f * za.x * za.x, 4.0f * za.y * za.y);
+                    }
+                } else {
+                    for (int k = g; k <= N / 2; k += GT) {
+                        const int k2 = (N - k) & (N - 1);
+                        const float2 za = buf[pb_pad5(k)], zb = buf[pb_pad5(k2)];
+                        const float2 p = make_float2(za.x + zb.x, za.y - zb.y), q = make_float2(za.x - zb.x, za.y + zb.y);
+                        const float2 w = make_float2(p.x * p.x + p.y * p.y, q.x * q.x + q.y * q.y);
+                        buf[pb_pad5(k)] = w; buf[pb_pad5(k2)] = w;
+                    }
+                }
+                pb_group_sync<G>(bar_id);
+            }
+        }
+
+        // ---- outputs: r[lag] = ac[lag] / (ac[0] * windowR[lag]) for lags 0..B+1 of the active frames, to the global scratch
+        const int slot = 2 * li;
+        const bool actA = active && pkA > 0.0f, actB = active && hasB && pkB > 0.0f;
+        if (active) {
+            const float2 ac0 = buf[0];
+            const float2 inv0 = make_float2(ac0.x > 0.0f ? 1.0f / ac0.x : 0.0f, ac0.y > 0.0f ? 1.0f / ac0.y : 0.0f);
+            float* ra = racf + (size_t)slot * rstride_g;
+            float* rb = ra + rstride_g;
+            const float2* src = buf + (g + (g >> 5));
+            const float* iwp = gm.inv_wr + g;
+            PB_UNROLL for (int q = 0; q < C::RPL; q++) {
+                const int lag = g + q * GT;
+                if (lag <= B + 1) {
+                    const float2 a = FAST ? src[q * (33 * G)] : buf[pb_pad5(lag)];
+                    const float iw = lag <= B ? __ldg(iwp + q * GT) : 0.0f;
+                    float2 r2 = __fmul2_rn(__fmul2_rn(a, inv0), make_float2(iw, iw));
+                    if (lag == 0) r2 = make_float2(1.0f, 1.0f);
+                    if (actA) ra[lag] = r2.x;
+                    if (actB) rb[lag] = r2.y;
+                }
+            }
+        }
+        if (g == 0) {
+            // frames that cannot have a voiced candidate are finished here: one voiceless candidate, intensity as Praat's
+            const int mc = gm.max_cand;
+            slot_fr[slot] = actA ? frA : -1;
+            slot_fr[slot + 1] = actB ? frA + 1 : -1;
+            if (!actA) { cand_f[frA * mc] = 0.0f; cand_s[frA * mc] = 0.0f; ncand[frA] = 1; intensity[frA] = 0.0f; }
+            else { const float t = pkA / gpk; intensity[frA] = t > 1.0f ? 1.0f : t; }
+            if (hasB) {
+                if (!actB) { cand_f[(frA + 1) * mc] = 0.0f; cand_s[(frA + 1) * mc] = 0.0f; ncand[frA + 1] = 1; intensity[frA + 1] = 0.0f; }
+                else { const float t = pkB / gpk; intensity[frA + 1] = t > 1.0f ? 1.0f : t; }
+            }
+        }
+        if (u_next != u) { u = u_next; ud = units[u]; unit_fresh = true; }
+        pb_group_sync<G>(bar_id);     // buf is reused by the next iteration
+    }
+}

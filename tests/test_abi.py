@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert len(syms) >= 14
     for s in syms:
         assert hasattr(native_lib, s), s
-    assert native_lib.pb_abi_version() == 1
+    assert native_lib.pb_abi_version() == 2
 
 
 def test_library_is_sm100a_cuda(native_lib):
