@@ -84,8 +84,10 @@ __device__ __forceinline__ PbPairPos pb_stage_pair(const int16_t* __restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------ K1
-template <int LOG2N>
-__global__ void __launch_bounds__(PbFftCfg<LOG2N>::WARPS_PER_CTA * 32, PbFftCfg<LOG2N>::MIN_CTAS)
+// MINB: resident CTAs per SM the register allocation targets; WSYNC: one-warp groups synchronise with __syncwarp() instead of a
+// named barrier (both chosen at launch: PB_ACF_CTAS / PB_ACF_WSYNC, defaults from the measurements in DESIGN.md)
+template <int LOG2N, int MINB, bool WSYNC>
+__global__ void __launch_bounds__(PbFftCfg<LOG2N>::WARPS_PER_CTA * 32, MINB)
 pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off,
                     const int2* __restrict__ pairpos, PbPitchGeomDev gm, int item0, int n_items, int rstride_g,
                     float* __restrict__ racf, long long* __restrict__ slot_fr,
@@ -98,6 +100,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     const int group = warp / G, wg = warp % G;          // group in CTA, warp in group
     const int g = wg * 32 + lane;                       // thread in group = butterfly index
     const int bar_id = 1 + group;
+#define PB_K1_SYNC() do { if (WSYNC && G == 1) __syncwarp(); else pb_group_sync<G>(bar_id); } while (0)
     // per-group shared memory: FFT buffer, a small reduction scratch, the sample staging buffer; CTA-wide: one mbarrier per group
     const size_t group_bytes = (size_t)(C::BUF + 8 * G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t);
     unsigned char* gbase = smem_raw + (size_t)group * group_bytes;
@@ -118,6 +121,14 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     const int span_hi = max(nw, mean_n0 + mean_len);
     const int span_len = span_hi - span_lo;
     const float mean_scale = (float)(1.0 / (32768.0 * (double)mean_len));
+    const bool fuse_ok = mean_n0 >= 0 && mean_n0 + mean_len <= nw;     // the local-mean span lies inside the window (periods_per_window >= 2)
+    // per thread, loop-invariant: which of its R first-pass inputs n = g + GT t lie inside the window / inside the local-peak span
+    unsigned vmask = 0, pkmask = 0;
+    PB_UNROLL for (int t = 0; t < R; t++) {
+        const int n = g + t * GT;
+        if (n < nw) vmask |= 1u << t;
+        if ((unsigned)(n - pk_lo) < (unsigned)pk_n) pkmask |= 1u << t;
+    }
 
     // Blocked distribution: a group walks a contiguous range of frame pairs, so consecutive iterations stay in the same
     // unit and the next pair's samples are staged while the current pair is transformed.
@@ -128,65 +139,105 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     if (it_begin >= it_end) return;
     int u_next = pb_upper_unit(pair_off, gm.n_units, item0 + it_begin);
     int u_next_end = pair_off[u_next + 1];
-    PbUnitDev ud = units[u_next];
-    int u = u_next;
-    PbPairPos pos_next = pb_stage_pair<GT>(pcm, ud, pairpos[item0 + it_begin], gm, span_lo, span_len, pre, g, mbar);
-    // per unit: the part indices that hold samples, [pmin, pmax1)  (inside the part and inside the file)
-    long long pmin = 0, pmax1 = 0;
-    bool unit_fresh = true;
+    int u = -1;
+    PbPairPos pos_next = pb_stage_pair<GT>(pcm, units[u_next], pairpos[item0 + it_begin], gm, span_lo, span_len, pre, g, mbar);
+    // what the loop needs of the current unit, refreshed when the unit changes (the 80-byte descriptor itself stays in L1 / L2):
+    // first pair, frame count, first frame, global peak, and the part indices that hold samples [pmin, pmax1)
+    int u_pair_off = 0, u_nframes = 0, u_pmin = 0, u_pmax1 = 0;
+    long long u_frame_off = 0;
+    float gpk = 0.0f;
 
     for (int li = it_begin; li < it_end; li++) {
         const int item = item0 + li;
         const PbPairPos pos = pos_next;
-        if (unit_fresh) {
-            pmin = 2 - ud.ix1 > 1 ? 2 - ud.ix1 : 1;
-            const long long e = (long long)ud.file_nx - ud.ix1 + 1;
-            pmax1 = (ud.nx < e ? ud.nx : e) + 1;
-            unit_fresh = false;
+        if (u != u_next) {
+            u = u_next;
+            const PbUnitDev* up = units + u;
+            u_pair_off = up->pair_off; u_nframes = up->n_frames; u_frame_off = up->frame_off; gpk = (float)up->global_peak;
+            const long long ix1 = up->ix1, e = (long long)up->file_nx - ix1 + 1;
+            const long long pmin = 2 - ix1 > 1 ? 2 - ix1 : 1, pmax1 = (up->nx < e ? up->nx : e) + 1;
+            const long long BIG = 1LL << 30;                    // frame positions are ints: saturate
+            u_pmin = (int)(pmin > BIG ? BIG : pmin); u_pmax1 = (int)(pmax1 > BIG ? BIG : (pmax1 < -BIG ? -BIG : pmax1));
         }
-        const int fA = 2 * (item - ud.pair_off);
-        const bool hasB = fA + 1 < ud.n_frames;
-        const bool global_silent = ud.global_peak == 0.0;
-        const long long frA = ud.frame_off + fA;
-        const float gpk = (float)ud.global_peak;
+        const int fA = 2 * (item - u_pair_off);
+        const bool hasB = fA + 1 < u_nframes;
+        const bool global_silent = gpk == 0.0f;
+        const long long frA = u_frame_off + fA;
         pb_mbar_wait(mbar, phase); phase ^= 1u;          // this pair's samples (requested during the previous pair) have landed
 #ifdef PB_SIMT_EMU
-        pb_group_sync<G>(bar_id);
+        PB_K1_SYNC();
 #else
-        if (pos.edge) pb_group_sync<G>(bar_id);          // edge chunks were filled with ordinary stores
+        if (pos.edge) PB_K1_SYNC();          // edge chunks were filled with ordinary stores
 #endif
         const int16_t* sm = pre;
         const int sb0 = pos.shift - span_lo, sb1 = sb0 + pos.hop;       // staged index of frame sample n is sb + n
-        float pkA = 0.0f, pkB = 0.0f, mxA = 0.0f, mxB = 0.0f;
+        float pkA = 0.0f, pkB = 0.0f;       // local peaks (Praat: max |windowed sample| around the frame centre), in SCALED units
+        float sA = 1.0f, sB = 1.0f;         // power-of-two scales of the two frames
+        float2 q15s = make_float2(0.0f, 0.0f), nms = make_float2(0.0f, 0.0f);     // fused windowing: value = (sample * q15s + nms) * window
+        bool any_signal = false;
         // valid frame samples n: [nlo, nhi)
-        const long long loA = pmin - pos.start0, hiA = pmax1 - pos.start0;
-        const bool interior = hasB && loA <= span_lo && hiA - pos.hop >= span_hi;      // frame B's range is frame A's shifted by hop
-        if (interior) {
-            // ---- local mean: one longest period to both sides of the frame centre (exact integer sums)
-            int s0 = 0, s1 = 0;
-            const int16_t* m0 = sm + sb0 + mean_n0; const int16_t* m1 = sm + sb1 + mean_n0;
-            for (int q = lane; q < mean_len; q += 32) { s0 += (int)m0[q]; s1 += (int)m1[q]; }
-            s0 = pb_warp_sum_i(s0); s1 = pb_warp_sum_i(s1);
-            const float2 nmean = make_float2(-(float)s0 * mean_scale, -(float)s1 * mean_scale);
-            const float2 q15 = make_float2(1.0f / 32768.0f, 1.0f / 32768.0f);
-            // ---- window both frames into the FFT buffer, z = a + i b (natural order), two samples per thread and step
-            const int16_t* pa = sm + sb0; const int16_t* pb = sm + sb1;
-#ifndef PB_SIMT_EMU
-#pragma unroll 2
-#endif
-            for (int n = 2 * g; n < nw; n += 2 * GT) {
-                const float2 w = __ldg((const float2*)(gm.window + n));
-                const float2 x0 = __ffma2_rn(make_float2((float)pa[n], (float)pb[n]), q15, nmean);
-                const float2 x1 = __ffma2_rn(make_float2((float)pa[n + 1], (float)pb[n + 1]), q15, nmean);
-                const float2 ab0 = __fmul2_rn(x0, make_float2(w.x, w.x)), ab1 = __fmul2_rn(x1, make_float2(w.y, w.y));
-                mxA = fmaxf(mxA, fmaxf(fabsf(ab0.x), fabsf(ab1.x))); mxB = fmaxf(mxB, fmaxf(fabsf(ab0.y), fabsf(ab1.y)));
-                if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, fabsf(ab0.x)); pkB = fmaxf(pkB, fabsf(ab0.y)); }
-                if ((unsigned)(n + 1 - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, fabsf(ab1.x)); pkB = fmaxf(pkB, fabsf(ab1.y)); }
-                float2* d = buf + pb_pad5(n);           // n is even: n + 1 shares its 32-element row
-                d[0] = ab0; d[1] = ab1;
+        const long long loA = (long long)u_pmin - pos.start0, hiA = (long long)u_pmax1 - pos.start0;
+        // interior pair: every sample both frames touch exists.  Then (FAST sizes) nothing is windowed into shared memory at all:
+        // the first FFT pass reads the staged samples directly and windows them in registers (below); here only the exact
+        // integer statistics of the two frames are taken: sum over the local-mean span, minimum and maximum over the window.
+        const bool fused = FAST && fuse_ok && hasB && loA <= span_lo && hiA - pos.hop >= span_hi;      // frame B's range is frame A's shifted by hop
+        if (fused) {
+            // Both statistics come from ONE sweep over the local-mean span (the central two thirds of the window, where the
+            // Hanning window is large: its extremes decide the frame's magnitude for the purpose of the scale), two samples per
+            // 32-bit load: dp2a adds both halves exactly, the packed min / max keep both.  The span's first / last sample may sit in
+            // a word that is only half inside: lane 0 adds those two samples on their own.
+            int s0, s1, mn0, mx0, mn1, mx1;
+            {
+                int sum[2]; unsigned vmn[2], vmx[2];
+                PB_UNROLL for (int f = 0; f < 2; f++) {
+                    const int M0 = (f ? sb1 : sb0) + mean_n0, M1 = M0 + mean_len;      // staged sample range of the span
+                    const int k0 = (M0 + 1) >> 1, k1 = M1 >> 1;                         // whole words inside it
+                    const unsigned* smw = reinterpret_cast<const unsigned*>(sm);
+                    int acc = 0; unsigned lo = 0x7fff7fffu, hi = 0x80008000u;
+                    for (int k = k0 + g; k < k1; k += GT) {
+                        const unsigned w = smw[k];
+                        acc = __dp2a_lo((int)w, 0x0101, acc);
+                        lo = __vmins2(lo, w); hi = __vmaxs2(hi, w);
+                    }
+                    if (g == 0) {
+                        if (M0 & 1) acc += (int)sm[M0];
+                        if (M1 & 1) acc += (int)sm[M1 - 1];
+                    }
+                    sum[f] = acc; vmn[f] = lo; vmx[f] = hi;
+                }
+                s0 = sum[0]; s1 = sum[1];
+                mn0 = min((int)(short)(vmn[0] & 0xffff), (int)(short)(vmn[0] >> 16)); mx0 = max((int)(short)(vmx[0] & 0xffff), (int)(short)(vmx[0] >> 16));
+                mn1 = min((int)(short)(vmn[1] & 0xffff), (int)(short)(vmn[1] >> 16)); mx1 = max((int)(short)(vmx[1] & 0xffff), (int)(short)(vmx[1] >> 16));
             }
+            s0 = __reduce_add_sync(PB_FULL_MASK, s0); s1 = __reduce_add_sync(PB_FULL_MASK, s1);
+            mn0 = __reduce_min_sync(PB_FULL_MASK, mn0); mx0 = __reduce_max_sync(PB_FULL_MASK, mx0);
+            mn1 = __reduce_min_sync(PB_FULL_MASK, mn1); mx1 = __reduce_max_sync(PB_FULL_MASK, mx1);
+            if (G > 1) {
+                int* redi = (int*)red;
+                if (lane == 0) { redi[wg * 6 + 0] = s0; redi[wg * 6 + 1] = s1; redi[wg * 6 + 2] = mn0; redi[wg * 6 + 3] = mx0; redi[wg * 6 + 4] = mn1; redi[wg * 6 + 5] = mx1; }
+                PB_K1_SYNC();
+                s0 = 0; s1 = 0;
+                for (int k = 0; k < G; k++) {
+                    s0 += redi[k * 6 + 0]; s1 += redi[k * 6 + 1];
+                    mn0 = min(mn0, redi[k * 6 + 2]); mx0 = max(mx0, redi[k * 6 + 3]); mn1 = min(mn1, redi[k * 6 + 4]); mx1 = max(mx1, redi[k * 6 + 5]);
+                }
+            }
+            const float q15 = 1.0f / 32768.0f;
+            const float meanA = (float)s0 * mean_scale, meanB = (float)s1 * mean_scale;
+            // the larger distance of the span's extremes from the mean: the frame's magnitude to within the window's taper
+            const float mA = fmaxf(fabsf((float)mx0 * q15 - meanA), fabsf((float)mn0 * q15 - meanA));
+            const float mB = fmaxf(fabsf((float)mx1 * q15 - meanB), fabsf((float)mn1 * q15 - meanB));
+            // bring both frames to comparable magnitude (power-of-two scales are exact and cancel in r = ac/ac[0]):
+            // keeps the weaker frame of a pair out of the stronger one's rounding noise
+            sA = mA > 0.0f ? __int_as_float((254 - ((__float_as_int(mA) >> 23) & 0xff)) << 23) : 1.0f;
+            sB = mB > 0.0f ? __int_as_float((254 - ((__float_as_int(mB) >> 23) & 0xff)) << 23) : 1.0f;
+            q15s = make_float2(q15 * sA, q15 * sB);
+            nms = make_float2(-meanA * sA, -meanB * sB);
+            any_signal = mA > 0.0f || mB > 0.0f;
         } else {
-            // ---- first / last frames of a slice that Praat zero-fills beyond the file, or a unit with an odd frame count
+            // ---- first / last frames of a slice that Praat zero-fills beyond the file, a unit with an odd frame count, or a small
+            //      FFT geometry: window both frames into the FFT buffer, z = a + i b (natural order, zero padded)
+            float mxA = 0.0f, mxB = 0.0f;
             int nlo[2], nhi[2], sb[2]; float lmean[2];
             PB_UNROLL for (int f = 0; f < 2; f++) {
                 long long lo = loA - (f ? pos.hop : 0), hi = hiA - (f ? pos.hop : 0);
@@ -215,31 +266,29 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                 if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, bb); }
                 buf[pb_pad5(n)] = ab;
             }
-        }
-        for (int n = nw + 2 * g; n < N; n += 2 * GT) { float2* d = buf + pb_pad5(n); d[0] = make_float2(0.0f, 0.0f); d[1] = make_float2(0.0f, 0.0f); }   // zero padding (nw, N even)
-        mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB); pkA = pb_warp_max(pkA); pkB = pb_warp_max(pkB);
-        if (G > 1) {
-            if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; red[wg * 4 + 2] = pkA; red[wg * 4 + 3] = pkB; }
-            pb_group_sync<G>(bar_id);
-            for (int k = 0; k < G; k++) {
-                mxA = fmaxf(mxA, red[k * 4 + 0]); mxB = fmaxf(mxB, red[k * 4 + 1]);
-                pkA = fmaxf(pkA, red[k * 4 + 2]); pkB = fmaxf(pkB, red[k * 4 + 3]);
+            for (int n = nw + g; n < N; n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding
+            mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB);
+            if (G > 1) {
+                if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; }
+                PB_K1_SYNC();
+                for (int k = 0; k < G; k++) { mxA = fmaxf(mxA, red[k * 4 + 0]); mxB = fmaxf(mxB, red[k * 4 + 1]); }
             }
+            sA = mxA > 0.0f ? __int_as_float((254 - ((__float_as_int(mxA) >> 23) & 0xff)) << 23) : 1.0f;
+            sB = mxB > 0.0f ? __int_as_float((254 - ((__float_as_int(mxB) >> 23) & 0xff)) << 23) : 1.0f;
+            pkA *= sA; pkB *= sB;               // scaled units, like the fused path
+            any_signal = mxA > 0.0f || mxB > 0.0f;
+            PB_K1_SYNC();                       // the windowed frames are in the buffer
         }
-        const bool active = !global_silent && (pkA > 0.0f || pkB > 0.0f);
-        // bring both frames to comparable magnitude (power-of-two scales are exact and cancel in r = ac/ac[0]):
-        // keeps the weaker frame of a pair out of the stronger one's rounding noise
-        const float sA = mxA > 0.0f ? __int_as_float((254 - ((__float_as_int(mxA) >> 23) & 0xff)) << 23) : 1.0f;
-        const float sB = mxB > 0.0f ? __int_as_float((254 - ((__float_as_int(mxB) >> 23) & 0xff)) << 23) : 1.0f;
-        pb_group_sync<G>(bar_id);                       // the windowed frames are in the buffer, the staged samples are consumed
-        // request the next pair's samples now: they land while this pair is transformed
-        if (li + 1 < it_end) {
-            if (item + 1 >= u_next_end) {
-                do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end);
-            }
-            // the descriptor of the next unit is only adopted at the top of the next iteration
-            pos_next = pb_stage_pair<GT>(pcm, u_next == u ? ud : units[u_next], pairpos[item + 1], gm, span_lo, span_len, pre, g, mbar);
-        }
+        const bool active = !global_silent && any_signal;
+        bool staged_next = false;
+        // the next pair's samples are requested as soon as this pair's have been consumed (after the first pass's loads when
+        // the windowing is fused into them): they land while this pair is transformed
+#define PB_K1_STAGE_NEXT() do { \
+            staged_next = true; \
+            if (li + 1 < it_end) { \
+                if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); } \
+                pos_next = pb_stage_pair<GT>(pcm, units[u_next], pairpos[item + 1], gm, span_lo, span_len, pre, g, mbar); \
+            } } while (0)
 
         // ---- two FFTs x two passes through ONE copy of the butterfly code: FFT (step >> 1), pass (step & 1).  The step
         //      index is made opaque so the optimiser neither peels nor unswitches the loop (either duplicates the
@@ -255,17 +304,31 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
             asm volatile("" : "+r"(step));
             int pass = step & 1;
             asm volatile("" : "+r"(pass));
-            // pass 1 reads natural order: the windowed frames (step 0) or the spectra (step 2);
+            // pass 1 reads natural order: the frames (step 0) or the spectra (step 2);
             // pass 2 reads the pass-1 layout and applies the inter-pass twiddles
-            if (FAST) {
+            if (FAST && step == 0 && fused) {
+                // frame sample n = g + GT t straight from the staging buffer: ((a, b) q15 s - mean s) w, zero beyond the window
+                const int16_t* pa = sm + sb0 + g; const int16_t* pb = sm + sb1 + g;
+                const float* win = gm.window + g;
+                PB_UNROLL for (int t = 0; t < R; t++) {
+                    float2 x = make_float2(0.0f, 0.0f);
+                    if (vmask & (1u << t)) {
+                        const float w = __ldg(win + t * GT);
+                        x = __fmul2_rn(__ffma2_rn(make_float2((float)pa[t * GT], (float)pb[t * GT]), q15s, nms), make_float2(w, w));
+                        if (pkmask & (1u << t)) { pkA = fmaxf(pkA, fabsf(x.x)); pkB = fmaxf(pkB, fabsf(x.y)); }
+                    }
+                    v[t] = x;
+                }
+            } else if (FAST) {
                 // i = g + 32 G t  ->  i + (i >> 5) = g + (g >> 5) + 33 G t: one base, compile-time offsets
                 const float2* src = buf + (g + (g >> 5));
                 PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * (33 * G)];
+                if (step == 0) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
             } else {
                 const int sh = pass ? LR : 5;
                 PB_UNROLL for (int t = 0; t < R; t++) { const int i = g + t * (N / R); v[t] = buf[i + (i >> sh)]; }
+                if (step == 0) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
             }
-            if (step == 0) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
             if (pass) {
                 const float2* tw = gm.tw_a + (g & (R - 1));
                 PB_UNROLL for (int t = 1; t < R; t++) {
@@ -274,7 +337,8 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                     v[t] = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(x.x, x.x), w));   // x * w
                 }
             }
-            pb_group_sync<G>(bar_id);                   // every load of this step is done before any store
+            PB_K1_SYNC();                   // every load of this step is done before any store
+            if (step == 0) PB_K1_STAGE_NEXT();
             pb_dft<R>(v);
             // pass 1 (Ns = 1): out[g*R + t], skew (index >> LR);  pass 2 (Ns = R): out[(g/R) R^2 + g%R + t R], skew 5
             if (FAST) {
@@ -292,7 +356,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                 const int osh = pass ? 5 : LR;
                 PB_UNROLL for (int t = 0; t < R; t++) { const int o = ob + t * os; buf[o + (o >> osh)] = v[pb_bitrev(t, LR)]; }
             }
-            pb_group_sync<G>(bar_id);
+            PB_K1_SYNC();
             if (pass && C::F > 1) {
                 // ---- final pass (radix F, Ns = R*R): butterflies are in place
                 constexpr int F = C::F > 1 ? C::F : 2, LF = pb_ilog2(F);
@@ -308,7 +372,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                     pb_dft<F>(a);
                     PB_UNROLL for (int t = 0; t < F; t++) buf[pb_pad5(j + t * (R * R))] = a[pb_bitrev(t, LF)];
                 }
-                pb_group_sync<G>(bar_id);
+                PB_K1_SYNC();
             }
             if (step == 1) {
                 // ---- power spectra of both frames from Z = FFT(a + i b):  4 P_a = |Z_k + conj Z_-k|^2,  4 P_b = |Z_k - conj Z_-k|^2,
@@ -340,29 +404,40 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                         buf[pb_pad5(k)] = w; buf[pb_pad5(k2)] = w;
                     }
                 }
-                pb_group_sync<G>(bar_id);
+                PB_K1_SYNC();
             }
         }
+        if (!staged_next) PB_K1_STAGE_NEXT();          // silent pair: nothing was transformed
+#undef PB_K1_STAGE_NEXT
+        // local peaks of the two frames: over the lanes (and warps) of the group, back to unscaled units (exact: powers of two)
+        pkA = pb_warp_max(pkA); pkB = pb_warp_max(pkB);
+        if (G > 1) {
+            PB_K1_SYNC();
+            if (lane == 0) { red[wg * 4 + 2] = pkA; red[wg * 4 + 3] = pkB; }
+            PB_K1_SYNC();
+            for (int k = 0; k < G; k++) { pkA = fmaxf(pkA, red[k * 4 + 2]); pkB = fmaxf(pkB, red[k * 4 + 3]); }
+        }
+        pkA = pkA / sA; pkB = pkB / sB;
 
         // ---- outputs: r[lag] = ac[lag] / (ac[0] * windowR[lag]) for lags 0..B+1 of the active frames, to the global scratch
         const int slot = 2 * li;
         const bool actA = active && pkA > 0.0f, actB = active && hasB && pkB > 0.0f;
         if (active) {
+            // both rows of the slot pair are written whenever the pair is active (K2 only reads the rows slot_fr marks)
             const float2 ac0 = buf[0];
             const float2 inv0 = make_float2(ac0.x > 0.0f ? 1.0f / ac0.x : 0.0f, ac0.y > 0.0f ? 1.0f / ac0.y : 0.0f);
-            float* ra = racf + (size_t)slot * rstride_g;
+            float* ra = racf + (size_t)slot * rstride_g + g;
             float* rb = ra + rstride_g;
             const float2* src = buf + (g + (g >> 5));
-            const float* iwp = gm.inv_wr + g;
+            const float* iwp = gm.inv_wr + g;                  // inv_wr[B + 1] = 0
             PB_UNROLL for (int q = 0; q < C::RPL; q++) {
                 const int lag = g + q * GT;
                 if (lag <= B + 1) {
                     const float2 a = FAST ? src[q * (33 * G)] : buf[pb_pad5(lag)];
-                    const float iw = lag <= B ? __ldg(iwp + q * GT) : 0.0f;
-                    float2 r2 = __fmul2_rn(__fmul2_rn(a, inv0), make_float2(iw, iw));
-                    if (lag == 0) r2 = make_float2(1.0f, 1.0f);
-                    if (actA) ra[lag] = r2.x;
-                    if (actB) rb[lag] = r2.y;
+                    const float iw = __ldg(iwp + q * GT);
+                    float2 r2 = __fmul2_rn(a, __fmul2_rn(inv0, make_float2(iw, iw)));
+                    if (q == 0 && g == 0) r2 = make_float2(1.0f, 1.0f);
+                    ra[q * GT] = r2.x; rb[q * GT] = r2.y;
                 }
             }
         }
@@ -378,7 +453,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                 else { const float t = pkB / gpk; intensity[frA + 1] = t > 1.0f ? 1.0f : t; }
             }
         }
-        if (u_next != u) { u = u_next; ud = units[u]; unit_fresh = true; }
-        pb_group_sync<G>(bar_id);     // buf is reused by the next iteration
+        PB_K1_SYNC();     // buf is reused by the next iteration
     }
 }
+#undef PB_K1_SYNC

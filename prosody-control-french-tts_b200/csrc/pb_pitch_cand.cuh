@@ -13,14 +13,31 @@
 #include "pb_pitch.cuh"
 
 // ------------------------------------------------------------------------------------------------ sinc interpolation
-// Praat NUM_interpolate_sinc (melder/NUMinterpol.cpp) on y[1..2B+1] = r[-B..B] at lag x, by 8 cooperating lanes
-// (sl = lane within the group; every lane of the group passes the same x).  With phi = frac(x), il = floor(x),
-// D = min(depth, B - il) the usable depth:
+// r in shared memory is preceded by its own mirror image, r[-j] = r[j] for j < PB_MIR, so the depth-70 sums (and the
+// peak scan's left neighbour of lag 0) index it directly; only the depth-700 evaluations (candidates above 0.3 / dx, which
+// exist when the ceiling is close to the Nyquist frequency) reach further down and take |index| (ABS = true).
+#define PB_MIR 72
+
+// Praat NUM_interpolate_sinc (melder/NUMinterpol.cpp) on y[1..2B+1] = r[-B..B] at lag x, by `nl` cooperating lanes
+// (8, 16 or 32, warp-uniform; sl = lane within the group; every lane of the group passes the same x).  With
+// phi = frac(x), il = floor(x), D = min(depth, B - il) the usable depth:
 //   y(x) = sin(pi phi)/(2 pi) * sum_{m<D} (-1)^m [ r[il-m]   (1 + cos(pi (phi+m)   / (phi+D)))   / (phi+m)
 //                                                + r[il+1+m] (1 + cos(pi (1-phi+m) / (1-phi+D))) / (1-phi+m) ]
-// Lane sl takes one side (sl & 1) and every 4th m starting at sl >> 1, so side, sign and the window scale are
-// loop-invariant; the loop body is one shared load, two MUFU (cos, rcp) and a handful of FP32 ops.
-// `nl` (8, 16 or 32, warp-uniform) lanes cooperate on one evaluation; sl = lane within that group.
+// Lane sl takes one side (sl & 1) and every (nl/2)-th m starting at sl >> 1, so side, sign and the window scale are
+// loop-invariant.  The window's cosine advances by a fixed angle per term: it is carried by the three-term recurrence
+// c[m+1] = 2 cos(delta) c[m] - c[m-1] (one FFMA) instead of a multiply and a MUFU per term; over the <= 18 terms a lane
+// sums its error stays below 1e-5 of a factor that multiplies the smallest terms.  Loop body: one shared load, one
+// MUFU (rcp) and five FP32 operations.  ABS = true keeps the direct cosine (up to 350 terms per lane) and |index|.
+// 1 / x in one MUFU (x is a sample distance >= 2^-24 here: no range fix-up as in __fdividef)
+__device__ __forceinline__ float pb_rcp(float x) {
+#ifdef PB_SIMT_EMU
+    return 1.0f / x;
+#else
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+
+template <bool ABS>
 __device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, float x, int depth, int sl, int nl = 8) {
     const float fl = floorf(x);
     const float phi = x - fl;
@@ -28,7 +45,7 @@ __device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, fl
     int D = B - il; if (depth < D) D = depth;
     float acc = 0.0f;
     if (phi == 0.0f) {                                        // on a sample: Praat returns y[x] (no early return:
-        if (sl == 0 && depth > 0) acc = r[abs(il)];           // the other groups of the warp still shuffle below)
+        if (sl == 0 && depth > 0) acc = r[ABS ? abs(il) : il];   // the other groups of the warp still shuffle below)
     } else if (D > 0) {
         const int side = sl & 1, j0 = sl >> 1, hs = nl >> 1;  // hs (4, 8, 16) is even: the sign of a lane's terms is fixed
         const float e = side ? 1.0f - phi : phi;
@@ -37,18 +54,37 @@ __device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, fl
         float d = e + (float)j0;
         int idx = side ? il + 1 + j0 : il - j0;
         const int step = side ? hs : -hs;
+        if (ABS) {
+            for (int m = j0; m < D; m += hs) {
+                const float yv = r[abs(idx)];
+                acc += __fdividef(yv * (1.0f + __cosf(d * k)), d);
+                d += fhs; idx += step;
+            }
+        } else {
+            const float dl = fhs * k;
+            const float tw = 2.0f * __cosf(dl);
+            float c = __cosf(d * k), cp = __cosf(d * k - dl);
+            const float* p = r + idx;
+            float a2 = 0.0f;
+            const int n_it = D > j0 ? (D - j0 + hs - 1) >> (__ffs(hs) - 1) : 0;      // hs is 4, 8 or 16
 #ifndef PB_SIMT_EMU
 #pragma unroll 2
 #endif
-        for (int m = j0; m < D; m += hs) {
-            const float yv = r[abs(idx)];
-            acc += __fdividef(yv * (1.0f + __cosf(d * k)), d);
-            d += fhs; idx += step;
+            for (int it = 0; it < n_it; it++) {
+                const float t = *p * pb_rcp(d);
+                acc += t; a2 = fmaf(t, c, a2);
+                const float cn = fmaf(tw, c, -cp); cp = c; c = cn;
+                d += fhs; p += step;
+            }
+            acc += a2;
         }
         if (j0 & 1) acc = -acc;
         acc *= sinpif(phi) * (0.5f / PB_PI_F);
     }
-    for (int o = 1; o < nl; o <<= 1) acc += __shfl_xor_sync(PB_FULL_MASK, acc, o);
+    // sum over the nl >= 8 lanes of the group
+    acc += __shfl_xor_sync(PB_FULL_MASK, acc, 1); acc += __shfl_xor_sync(PB_FULL_MASK, acc, 2); acc += __shfl_xor_sync(PB_FULL_MASK, acc, 4);
+    if (nl > 8) acc += __shfl_xor_sync(PB_FULL_MASK, acc, 8);
+    if (nl > 16) acc += __shfl_xor_sync(PB_FULL_MASK, acc, 16);
     return acc;
 }
 // vertex of the parabola through (xa,fa),(xb,fb),(xc,fc), xa < xb < xc; xb if not concave
@@ -83,7 +119,7 @@ __device__ PB_NOINLINE int pb_candidates_overflow(const float* __restrict__ r, f
             const int ip = have ? base + __ffs((int)m) - 1 : 2;
             const float dr = 0.5f * (r[ip + 1] - r[ip - 1]), d2r = 2.0f * r[ip] - r[ip - 1] - r[ip + 1];
             const float x0 = (float)ip + ((have && d2r > 0.0f) ? __fdividef(dr, d2r) : 0.0f);
-            float st = pb_sinc8(r, B, x0, have ? 30 : 0, sl);
+            float st = pb_sinc8<false>(r, B, x0, have ? 30 : 0, sl);
             if (st > 1.0f) st = __fdividef(1.0f, st);
             const float fq0 = __fdividef(gm.sr, x0);
             for (int q = 0; q < 4; q++) {
@@ -120,13 +156,14 @@ __device__ PB_NOINLINE int pb_candidates_overflow(const float* __restrict__ r, f
 // thing: golden-section / parabolic minimisation of -y(x) over [i-1, i+1] (Brent 1973, the routine Praat calls), to a
 // lag tolerance of 1e-3 samples (4e-5 relative at the shortest refined lag), one candidate at a time with all 32 lanes on
 // each sinc evaluation.
+template <bool ABS>
 __device__ PB_NOINLINE void pb_brent_refine(const float* __restrict__ r, int B, float fi, int depth, int lane, float* bx, float* by) {
     const float golden = 0.38196601125f, tol = 1.0e-3f;
     float a = fi - 1.0f, b = fi + 1.0f;
     float t = a + golden * (b - a);
     float x = t, v = t, w = t, fx = 0.0f, fv = 0.0f, fw = 0.0f;
     for (int iter = 0; iter < 32; iter++) {                   // every lane carries the same state: the loop is warp-uniform
-        const float ft = -pb_sinc8(r, B, t, depth, lane, 32);
+        const float ft = -pb_sinc8<ABS>(r, B, t, depth, lane, 32);
         if (iter == 0) { fx = fv = fw = ft; }
         else if (ft <= fx) { if (t < x) b = x; else a = x; v = w; w = x; x = t; fv = fw; fw = fx; fx = ft; }
         else {
@@ -161,20 +198,40 @@ __device__ PB_NOINLINE void pb_brent_refine(const float* __restrict__ r, int B, 
 // reproduces Brent's optimum to ~1e-4 relative in lag and ~1e-6 in strength (DESIGN.md "candidate refinement").
 // Maxima below min_refine_lag stay above the pitch ceiling wherever in [i-1, i+1] their refinement lands: the path
 // finder treats them as voiceless whatever their strength, so they keep their first-pass values.
+template <bool ABS>
 __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r, float* scratch, const PbPitchGeomDev& gm,
                                                     int lane, float* __restrict__ out_f, float* __restrict__ out_s,
                                                     uint8_t* __restrict__ out_n, const float* __restrict__ half_tab) {
     int* imax = (int*)(scratch + 2 * PB_MAXC); // lag of the maximum
     const int B = gm.brent_ixmax, lim = gm.scan_lim, maxc = gm.max_cand;
     // ---- the maxima, in lag order; slot arrays hold PB_MAXC-1 of them, anything beyond max_cand-1 is the rare path
+    // four consecutive lags per lane and pass (one 16-byte load plus the two neighbours); maxima come out in lag order:
+    // pass, lane, bit
     int total = 0;
-    for (int base = 2; base < lim; base += 32) {
-        const int i = base + lane;
-        const bool pk = i < lim && r[i] > gm.half_voicing && r[i] > r[i - 1] && r[i] >= r[i + 1];
-        const unsigned mask = __ballot_sync(PB_FULL_MASK, pk);
-        const int slot = 1 + total + __popc(mask & ((1u << lane) - 1u));
-        if (pk && slot < maxc) imax[slot] = i;
-        total += __popc(mask);
+    const float hv = gm.half_voicing;
+    for (int base = 0; base < lim; base += 128) {
+        const int i0 = base + 4 * lane;
+        unsigned m4 = 0;
+        if (i0 < lim) {
+            const float4 q = *reinterpret_cast<const float4*>(r + i0);
+            const float pv = r[i0 - 1], nx = r[i0 + 4];
+            m4 = ((unsigned)((q.x > hv) & (q.x > pv) & (q.x >= q.y))) | ((unsigned)((q.y > hv) & (q.y > q.x) & (q.y >= q.z)) << 1) |
+                 ((unsigned)((q.z > hv) & (q.z > q.y) & (q.z >= q.w)) << 2) | ((unsigned)((q.w > hv) & (q.w > q.z) & (q.w >= nx)) << 3);
+            if (i0 == 0) m4 &= ~3u;                              // candidate lags start at 2
+            const int rem = lim - i0;
+            if (rem < 4) m4 &= (1u << rem) - 1u;
+        }
+        const int cnt = __popc(m4);
+        int incl = cnt;
+        PB_UNROLL for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(PB_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        int slot = 1 + total + incl - cnt;
+        while (m4) {
+            const int j = __ffs((int)m4) - 1;
+            m4 &= m4 - 1;
+            if (slot < maxc) imax[slot] = i0 + j;
+            slot++;
+        }
+        total += __shfl_sync(PB_FULL_MASK, incl, 31);
     }
     const bool overflow = total > maxc - 1;
     int ncf = 1 + total;
@@ -220,22 +277,33 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
         // The two half-sample points have phi = 1/2: their windowed-sinc coefficients do not depend on the candidate
         // (depth 70, away from the end of r), so both are dot products against one 70-entry table — no MUFU.
         const bool tab = have && depth == 70 && (B - i) >= 70;
+        // each lane of the group takes a run of consecutive m: both sums walk r outwards from the maximum, so every step
+        // loads one new value per side and reuses the previous one
         float ta = 0.0f, tb = 0.0f;
         if (tab) {
-            for (int m = sl; m < 70; m += nl) {
-                const float cm = half_tab[m];
-                ta = fmaf(cm, r[abs(i - 1 - m)] + r[i + m], ta);
-                tb = fmaf(cm, r[abs(i - m)] + r[i + 1 + m], tb);
+            const int per = (70 + nl - 1) / nl;                 // 9, 5 or 3 coefficients per lane
+            const int m0 = sl * per, m1 = min(70, m0 + per);
+            if (m0 < m1) {
+                float lc = r[i - m0], rc = r[i + m0];
+                for (int m = m0; m < m1; m++) {
+                    const float cm = half_tab[m];
+                    const float ln = r[i - 1 - m], rn = r[i + 1 + m];
+                    ta = fmaf(cm, ln + rc, ta);
+                    tb = fmaf(cm, lc + rn, tb);
+                    lc = ln; rc = rn;
+                }
             }
         }
-        for (int o = 1; o < nl; o <<= 1) { ta += __shfl_xor_sync(PB_FULL_MASK, ta, o); tb += __shfl_xor_sync(PB_FULL_MASK, tb, o); }
+        PB_UNROLL for (int o = 1; o < 8; o <<= 1) { ta += __shfl_xor_sync(PB_FULL_MASK, ta, o); tb += __shfl_xor_sync(PB_FULL_MASK, tb, o); }
+        if (nl > 8) { ta += __shfl_xor_sync(PB_FULL_MASK, ta, 8); tb += __shfl_xor_sync(PB_FULL_MASK, tb, 8); }
+        if (nl > 16) { ta += __shfl_xor_sync(PB_FULL_MASK, ta, 16); tb += __shfl_xor_sync(PB_FULL_MASK, tb, 16); }
         // four evaluations through ONE call site (code size): y(i-.5), y(i+.5), y(x1), y(x2)
         float xe = fi - 0.5f, ya = 0.0f, xc = fi, yc = r0, yl = 0.0f, yr = 0.0f, x1 = fi, y1 = 0.0f, y2 = 0.0f;
 #ifndef PB_SIMT_EMU
 #pragma unroll 1
 #endif
         for (int e = 0; e < 4; e++) {
-            float y = pb_sinc8(r, B, xe, (tab && e < 2) ? 0 : depth, sl, nl);
+            float y = pb_sinc8<ABS>(r, B, xe, (tab && e < 2) ? 0 : depth, sl, nl);
             if (tab && e < 2) y = e ? tb : ta;
             if (e == 0) { ya = y; xe = fi + 0.5f; }
             else if (e == 1) {
@@ -277,7 +345,7 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
         for (int k = 0; k < n_flagged; k++) {
             const int code = flagged[k], c = code & 0xff;
             float bx, by;
-            pb_brent_refine(r, B, (float)imax[c], (code & 0x100) ? 700 : 70, lane, &bx, &by);
+            pb_brent_refine<ABS>(r, B, (float)imax[c], (code & 0x100) ? 700 : 70, lane, &bx, &by);
             if (by > 1.0f) by = __fdividef(1.0f, by);
             if (lane == 0) { out_f[c] = __fdividef(gm.sr, bx); out_s[c] = by; }
         }
@@ -289,17 +357,19 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
 #define PB_CAND_WARPS 4
 
 // MIN_CTAS: residency target (10 -> 48 registers with a few spilled words, 8 -> 64 registers); chosen at launch (PB_CAND_CTAS)
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool ABS>
 __global__ void __launch_bounds__(PB_CAND_WARPS * 32, MIN_CTAS)
 pb_pitch_cand_kernel(const float* __restrict__ racf, const long long* __restrict__ slot_fr, int n_slots, int rstride_g, PbPitchGeomDev gm,
                      float* __restrict__ cand_f, float* __restrict__ cand_s, uint8_t* __restrict__ ncand, unsigned* __restrict__ work_counter) {
     PB_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per warp: two r buffers (16-byte aligned: rstride_g is a multiple of 4), candidate scratch, two mbarriers; CTA-wide: half-sample table
-    const size_t warp_bytes = (size_t)(2 * rstride_g + 3 * PB_MAXC) * sizeof(float) + 2 * sizeof(pbMbar);
+    // per warp: two r buffers, each behind PB_MIR words for its mirror image (16-byte aligned: rstride_g and PB_MIR are multiples
+    // of 4), candidate scratch, two mbarriers; CTA-wide: half-sample table
+    const int rrow = rstride_g + PB_MIR;
+    const size_t warp_bytes = (size_t)(2 * rrow + 3 * PB_MAXC) * sizeof(float) + 2 * sizeof(pbMbar);
     unsigned char* wbase = smem_raw + (size_t)warp * warp_bytes;
     float* rbuf = (float*)wbase;
-    float* scratch = rbuf + 2 * rstride_g;
+    float* scratch = rbuf + 2 * rrow;
     pbMbar* mbar = (pbMbar*)(scratch + 3 * PB_MAXC);
     float* half_tab = (float*)(smem_raw + (size_t)PB_CAND_WARPS * warp_bytes);
     if (threadIdx.x < 72) half_tab[threadIdx.x] = threadIdx.x < 70 ? __ldg(&gm.half_tab[threadIdx.x]) : 0.0f;
@@ -323,7 +393,7 @@ pb_pitch_cand_kernel(const float* __restrict__ racf, const long long* __restrict
         if (lane == 0) {
             const int j = __ffs((int)mask) - 1;
             pb_mbar_expect_tx(mbar, r_bytes);
-            pb_bulk_g2s(rbuf, racf + (size_t)(s0 + j) * rstride_g, r_bytes, mbar);
+            pb_bulk_g2s(rbuf + PB_MIR, racf + (size_t)(s0 + j) * rstride_g, r_bytes, mbar);
         }
         while (mask) {
             const int j = __ffs((int)mask) - 1;
@@ -331,14 +401,17 @@ pb_pitch_cand_kernel(const float* __restrict__ racf, const long long* __restrict
             if (mask && lane == 0) {                   // the next active slot lands in the other buffer meanwhile
                 const int jn = __ffs((int)mask) - 1;
                 pb_mbar_expect_tx(mbar + (b ^ 1), r_bytes);
-                pb_bulk_g2s(rbuf + (b ^ 1) * rstride_g, racf + (size_t)(s0 + jn) * rstride_g, r_bytes, mbar + (b ^ 1));
+                pb_bulk_g2s(rbuf + (b ^ 1) * rrow + PB_MIR, racf + (size_t)(s0 + jn) * rstride_g, r_bytes, mbar + (b ^ 1));
             }
             if (b) { pb_mbar_wait(mbar + 1, phase1); phase1 ^= 1u; } else { pb_mbar_wait(mbar, phase0); phase0 ^= 1u; }
 #ifdef PB_SIMT_EMU
             __syncwarp();
 #endif
             const long long fr = __shfl_sync(PB_FULL_MASK, fr_l, j);
-            pb_frame_candidates(rbuf + b * rstride_g, scratch, gm, lane, cand_f + fr * mc, cand_s + fr * mc, ncand + fr, half_tab);
+            float* r = rbuf + b * rrow + PB_MIR;
+            for (int q = 1 + lane; q < PB_MIR && q < rstride_g; q += 32) r[-q] = r[q];     // the mirror image
+            __syncwarp();
+            pb_frame_candidates<ABS>(r, scratch, gm, lane, cand_f + fr * mc, cand_s + fr * mc, ncand + fr, half_tab);
             __syncwarp();                              // every lane is done with this buffer before it is refilled
             b ^= 1;
         }

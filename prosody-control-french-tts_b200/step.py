@@ -139,14 +139,25 @@ def measure(ex: Extractor, pcm, pl: Plan, prosody: dict | None = None, pitch: di
         bad = np.nonzero((st & (N.PB_UNIT_LUFS_ERROR | N.PB_UNIT_SLICE_ERROR)) != 0)[0]
         if len(bad):
             raise ValueError(f"unit {int(bad[0])}: Audio must have length greater than the block size.")
-    med, lufs, dur = r["median_f0"], r["lufs"], r["duration_s"]
+    out = finish(pl, r["median_f0"], r["lufs"], r["duration_s"], prm, ex._lib)
+    out["status"] = st
+    out["timings"] = ex.timings()
+    return out
+
+
+def finish(pl: Plan, med, lufs, dur, prm: dict, lib=None) -> dict:
+    """The host half of the step on per-unit measurements laid out like the plan's units: pass-1 statistics and
+    baselines (:375-424), per-syntagme raw deltas (:515-577), EMA + jump clamp (:593-602).  float64 throughout."""
+    lib = lib if lib is not None else N.load()
+    S, K = pl.n_seg, pl.n_syn
+    med = np.asarray(med, np.float64); lufs = np.asarray(lufs, np.float64); dur = np.asarray(dur, np.float64)
     # ---- pass 1 (:375-400)
     p_nat, l_nat, d_nat = med[:S], lufs[:S], dur[:S]
     l_syn, d_syn = lufs[S:2 * S], dur[S:2 * S]
     wc = pl.word_counts.astype(np.float64)
     with np.errstate(divide="ignore", invalid="ignore"):
         rate_ratio = np.where((pl.word_counts > 0) & (d_syn > 0), (wc / d_nat) / (wc / d_syn), 1.0)
-    b_f0, b_loud, b_rate = baselines(p_nat, l_nat, rate_ratio, prm["baseline_window"], ex._lib)
+    b_f0, b_loud, b_rate = baselines(p_nat, l_nat, rate_ratio, prm["baseline_window"], lib)
     # ---- pass 2 (:495-589)
     a = slice(2 * S, 2 * S + 2 * K, 2); b = slice(2 * S + 1, 2 * S + 2 * K, 2)
     sp_nat = np.ascontiguousarray(med[a]); sl_syn = np.ascontiguousarray(lufs[b])
@@ -155,7 +166,6 @@ def measure(ex: Extractor, pcm, pl: Plan, prosody: dict | None = None, pitch: di
     dprm = N.PbDeltaParams(prm["pitch_semitones"], prm["pitch_lower_clip_factor"], prm["volume_pct"], prm["rate_percent"],
                            prm["threshold_duration_before_slowing_down"], prm["slow_floor_per_sec"])
     bf = np.ascontiguousarray(b_f0[pl.syn_seg]); bl = np.ascontiguousarray(b_loud[pl.syn_seg])
-    lib = ex._lib
     N.check(lib, None, lib.pb_syntagme_deltas(K, _dp(sp_nat), _dp(bf), _dp(bl), _dp(sl_syn), _ip(pl.syn_wc), _dp(nat_total),
                                               _dp(syn_total), _ip(pl.syn_pause_ms), C.byref(dprm), _dp(raw_p), _dp(raw_v), _dp(raw_r)),
             "pb_syntagme_deltas")
@@ -167,5 +177,4 @@ def measure(ex: Extractor, pcm, pl: Plan, prosody: dict | None = None, pitch: di
     return dict(seg_stats=dict(p_nat=p_nat, l_nat=l_nat, l_syn=l_syn, d_nat=d_nat, d_syn=d_syn, wc=pl.word_counts, rate_ratio=rate_ratio),
                 baselines=dict(f0=b_f0, loud=b_loud, rate=b_rate),
                 syn=dict(p_nat=sp_nat, l_syn=sl_syn, nat_total=nat_total, syn_total=syn_total),
-                raw_pitch=raw_p, raw_volume=raw_v, raw_rate=raw_r, sm_pitch=sm_p, sm_rate=sm_r, status=st,
-                timings=ex.timings())
+                raw_pitch=raw_p, raw_volume=raw_v, raw_rate=raw_r, sm_pitch=sm_p, sm_rate=sm_r)

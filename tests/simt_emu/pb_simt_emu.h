@@ -151,6 +151,34 @@ static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
     pb_emu::warp_sync();
     return r;
 }
+// packed 16-bit SIMD intrinsics used by the kernels
+static inline int __dp2a_lo(int a, int b, int c) {
+    return c + (int)(short)(a & 0xffff) * (int)(signed char)(b & 0xff) + (int)(short)((unsigned)a >> 16) * (int)(signed char)((b >> 8) & 0xff);
+}
+static inline unsigned __vmins2(unsigned a, unsigned b) {
+    const short al = (short)(a & 0xffff), ah = (short)(a >> 16), bl = (short)(b & 0xffff), bh = (short)(b >> 16);
+    return (unsigned)(unsigned short)(al < bl ? al : bl) | ((unsigned)(unsigned short)(ah < bh ? ah : bh) << 16);
+}
+static inline unsigned __vmaxs2(unsigned a, unsigned b) {
+    const short al = (short)(a & 0xffff), ah = (short)(a >> 16), bl = (short)(b & 0xffff), bh = (short)(b >> 16);
+    return (unsigned)(unsigned short)(al > bl ? al : bl) | ((unsigned)(unsigned short)(ah > bh ? ah : bh) << 16);
+}
+// sm_80+ integer warp reductions (REDUX)
+static inline int pb_emu_reduce_i(int v, int op) {
+    const int base = pb_emu::warp() * 32;
+    pb_emu::g_blk->xchg[base + pb_emu::lane()] = (uint64_t)(uint32_t)v;
+    pb_emu::warp_sync();
+    int r = (int)(uint32_t)pb_emu::g_blk->xchg[base];
+    for (int i = 1; i < pb_emu::warp_width(); i++) {
+        const int o = (int)(uint32_t)pb_emu::g_blk->xchg[base + i];
+        r = op == 0 ? r + o : op == 1 ? (o < r ? o : r) : (o > r ? o : r);
+    }
+    pb_emu::warp_sync();
+    return r;
+}
+static inline int __reduce_add_sync(unsigned, int v) { return pb_emu_reduce_i(v, 0); }
+static inline int __reduce_min_sync(unsigned, int v) { return pb_emu_reduce_i(v, 1); }
+static inline int __reduce_max_sync(unsigned, int v) { return pb_emu_reduce_i(v, 2); }
 static inline int __any_sync(unsigned, int p) { return pb_emu::ballot(p) != 0; }
 static inline int __all_sync(unsigned, int p) {
     unsigned full = pb_emu::warp_width() == 32 ? 0xffffffffu : ((1u << pb_emu::warp_width()) - 1);
