@@ -33,18 +33,20 @@ def is_stale() -> bool:
     return any(p.stat().st_mtime > t for p in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if force or is_stale():
-        cmd = nvcc_command(extra=["-Xptxas", "-v"] if verbose else None)
+def build(force: bool = False, verbose: bool = False, out: Path = LIB, defines: list[str] | None = None) -> Path:
+    """defines: extra -D macros (development: variant libraries for A/B timing, loaded with PB_LIB / Extractor(lib=...))."""
+    if force or is_stale() or out != LIB:
+        cmd = nvcc_command(out=out, extra=(["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in (defines or [])])
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
         if verbose:
             print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
     import sys
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=Path(outs[0]) if outs else LIB, defines=defs))

@@ -126,7 +126,7 @@ struct PbHandle {
     DevBuf pcm, units, pair_off, cand_f, cand_s, ncand, inten, psi, sel_f, sel_s, med, nvoiced;
     DevBuf lunits, meters, lstate, lenergy, lufs, pairpos;
     DevBuf racf, slot_fr, work_ctr;                        // K1 -> K2: autocorrelations of one launch chunk, slot -> frame map, K2's chunk counter
-    size_t cand_smem = 0; int cand_per_sm = 1, cand_deep = -1;             // K2: footprint its function attribute was set for, resident CTAs per SM
+    size_t cand_smem = 0; int cand_per_sm = 1;             // K2: footprint its function attribute was set for, resident CTAs per SM
     HostBuf stage_units, stage_pairs, stage_lunits, stage_meters, stage_out;
     size_t su_off = 0, sp_off = 0, sl_off = 0;           // running offsets (elements) into the pinned staging buffers
     std::map<std::pair<int64_t, int>, PitchTables*> tables;
@@ -443,17 +443,14 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
     const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + C::GROUPS_PER_CTA * sizeof(pbMbar);
     const int threads = C::WARPS_PER_CTA * 32;
     static const int acf_ctas = [] { const char* e = getenv("PB_ACF_CTAS"); return e ? atoi(e) : 0; }();
-    static const int acf_wsync = [] { const char* e = getenv("PB_ACF_WSYNC"); return e ? atoi(e) : 0; }();
+    static const int acf_wsync = [] { const char* e = getenv("PB_ACF_WSYNC"); return e ? atoi(e) : 1; }();     // measured 3 % faster than named barriers
     auto kfn = pb_pitch_acf_kernel<LOG2N, C::MIN_CTAS, false>;
     if constexpr (LOG2N == 10) {
         if (acf_ctas == 5) kfn = acf_wsync ? pb_pitch_acf_kernel<LOG2N, 5, true> : pb_pitch_acf_kernel<LOG2N, 5, false>;
         else if (acf_wsync) kfn = pb_pitch_acf_kernel<LOG2N, C::MIN_CTAS, true>;
     }
     static const int cand_ctas = [] { const char* e = getenv("PB_CAND_CTAS"); return e ? atoi(e) : 8; }();
-    // candidates above 0.3 / dx are refined at depth 700 (index reach beyond the mirrored part of r): only possible when
-    // the ceiling allows lags below 4 to be voiced
-    const bool deep = gm.min_refine_lag < 4;
-    auto cfn = deep ? pb_pitch_cand_kernel<8, true> : cand_ctas == 8 ? pb_pitch_cand_kernel<8, false> : cand_ctas == 12 ? pb_pitch_cand_kernel<12, false> : pb_pitch_cand_kernel<10, false>;
+    auto cfn = cand_ctas == 10 ? pb_pitch_cand_kernel<10> : cand_ctas == 12 ? pb_pitch_cand_kernel<12> : pb_pitch_cand_kernel<8>;
     int per_sm = 2;
     const int rstride_g = (gm.brent_ixmax + 2 + 3) & ~3;                 // floats per frame in the scratch (16-byte rows for the bulk copies)
     const size_t cand_smem = (size_t)PB_CAND_WARPS * ((size_t)(2 * (rstride_g + PB_MIR) + 3 * PB_MAXC) * sizeof(float) + 2 * sizeof(pbMbar)) + 72 * sizeof(float);
@@ -475,13 +472,13 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
         h->occ_cache[okey] = per_sm;
         h->occ_last[LOG2N] = smem;
     } else per_sm = oc->second;
-    if (h->cand_smem != cand_smem || h->cand_deep != (int)deep) {
+    if (h->cand_smem != cand_smem) {
         if (cudaFuncSetAttribute(cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem) != cudaSuccess)
             return fail(h, PB_ECUDA, "cudaFuncSetAttribute: %s", pbrt_error());
         cudaFuncSetAttribute(cfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int cps = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, cfn, PB_CAND_WARPS * 32, cand_smem) != cudaSuccess || cps < 1) cps = 1;
-        h->cand_per_sm = cps; h->cand_smem = cand_smem; h->cand_deep = (int)deep;
+        h->cand_per_sm = cps; h->cand_smem = cand_smem;
     }
 #else
     h->cand_per_sm = 2;

@@ -23,6 +23,14 @@
 #include "pb_async.cuh"
 #include "pb_pitch.cuh"
 
+// How interior frame pairs are windowed: 1 = into the shared FFT buffer by a separate loop (conflict-free rows n, n + GT), scale
+// folded in; 2 = in registers, inside the first FFT pass's loads (no windowed copy in shared memory).  Mode 2 moves 20 % fewer
+// shared-memory wavefronts but its unrolled, predicated first pass makes the loop body miss the instruction cache and exposes the
+// window-table loads: 5.8 ms against 5.0 ms for mode 1 on 2 M frames (profiles/r02_acf_modes.txt), so mode 1 ships.
+#ifndef PB_K1_MODE
+#define PB_K1_MODE 1
+#endif
+
 // Where a frame pair's samples sit: part index of frame A's sample 0, distance to frame B, and the offset of frame A's
 // sample `span_lo` inside the staged (16-byte aligned) range.
 struct PbPairPos { int start0; int hop; int shift; int edge; };
@@ -180,8 +188,9 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
         // interior pair: every sample both frames touch exists.  Then (FAST sizes) nothing is windowed into shared memory at all:
         // the first FFT pass reads the staged samples directly and windows them in registers (below); here only the exact
         // integer statistics of the two frames are taken: sum over the local-mean span, minimum and maximum over the window.
-        const bool fused = FAST && fuse_ok && hasB && loA <= span_lo && hiA - pos.hop >= span_hi;      // frame B's range is frame A's shifted by hop
-        if (fused) {
+        const bool interior = FAST && fuse_ok && hasB && loA <= span_lo && hiA - pos.hop >= span_hi;      // frame B's range is frame A's shifted by hop
+        const bool fused = PB_K1_MODE == 2 && interior;
+        if (interior) {
             // Both statistics come from ONE sweep over the local-mean span (the central two thirds of the window, where the
             // Hanning window is large: its extremes decide the frame's magnitude for the purpose of the scale), two samples per
             // 32-bit load: dp2a adds both halves exactly, the packed min / max keep both.  The span's first / last sample may sit in
@@ -234,6 +243,25 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
             q15s = make_float2(q15 * sA, q15 * sB);
             nms = make_float2(-meanA * sA, -meanB * sB);
             any_signal = mA > 0.0f || mB > 0.0f;
+            if (PB_K1_MODE != 2) {
+                // ---- window both frames into the FFT buffer, z = a + i b (natural order, already scaled), rows n and n + GT per step
+                const int16_t* pa = sm + sb0; const int16_t* pb = sm + sb1;
+                for (int n = g; n < nw; n += 2 * GT) {
+                    const float w0 = __ldg(gm.window + n);
+                    const float2 x0 = __fmul2_rn(__ffma2_rn(make_float2((float)pa[n], (float)pb[n]), q15s, nms), make_float2(w0, w0));
+                    if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, fabsf(x0.x)); pkB = fmaxf(pkB, fabsf(x0.y)); }
+                    buf[pb_pad5(n)] = x0;
+                    const int n1 = n + GT;
+                    if (n1 < nw) {
+                        const float w1 = __ldg(gm.window + n1);
+                        const float2 x1 = __fmul2_rn(__ffma2_rn(make_float2((float)pa[n1], (float)pb[n1]), q15s, nms), make_float2(w1, w1));
+                        if ((unsigned)(n1 - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, fabsf(x1.x)); pkB = fmaxf(pkB, fabsf(x1.y)); }
+                        buf[pb_pad5(n1)] = x1;
+                    }
+                }
+                for (int n = nw + g; n < N; n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding
+                PB_K1_SYNC();                   // the windowed frames are in the buffer
+            }
         } else {
             // ---- first / last frames of a slice that Praat zero-fills beyond the file, a unit with an odd frame count, or a small
             //      FFT geometry: window both frames into the FFT buffer, z = a + i b (natural order, zero padded)
@@ -323,7 +351,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                 // i = g + 32 G t  ->  i + (i >> 5) = g + (g >> 5) + 33 G t: one base, compile-time offsets
                 const float2* src = buf + (g + (g >> 5));
                 PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * (33 * G)];
-                if (step == 0) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
+                if (step == 0 && !interior) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
             } else {
                 const int sh = pass ? LR : 5;
                 PB_UNROLL for (int t = 0; t < R; t++) { const int i = g + t * (N / R); v[t] = buf[i + (i >> sh)]; }

@@ -14,8 +14,9 @@
 
 // ------------------------------------------------------------------------------------------------ sinc interpolation
 // r in shared memory is preceded by its own mirror image, r[-j] = r[j] for j < PB_MIR, so the depth-70 sums (and the
-// peak scan's left neighbour of lag 0) index it directly; only the depth-700 evaluations (candidates above 0.3 / dx, which
-// exist when the ceiling is close to the Nyquist frequency) reach further down and take |index| (ABS = true).
+// peak scan's left neighbour of lag 0) index it directly; only the depth-700 evaluations (candidates above 0.3 / dx, i.e. lags
+// below 3.33: refined when the ceiling is close to the Nyquist frequency, or when a frame has more maxima than candidate slots)
+// reach further down: those take |index| and the direct cosine.
 #define PB_MIR 72
 
 // Praat NUM_interpolate_sinc (melder/NUMinterpol.cpp) on y[1..2B+1] = r[-B..B] at lag x, by `nl` cooperating lanes
@@ -27,7 +28,7 @@
 // loop-invariant.  The window's cosine advances by a fixed angle per term: it is carried by the three-term recurrence
 // c[m+1] = 2 cos(delta) c[m] - c[m-1] (one FFMA) instead of a multiply and a MUFU per term; over the <= 18 terms a lane
 // sums its error stays below 1e-5 of a factor that multiplies the smallest terms.  Loop body: one shared load, one
-// MUFU (rcp) and five FP32 operations.  ABS = true keeps the direct cosine (up to 350 terms per lane) and |index|.
+// MUFU (rcp) and five FP32 operations.  Depth 700 keeps the direct cosine (up to 350 terms per lane) and |index|.
 // 1 / x in one MUFU (x is a sample distance >= 2^-24 here: no range fix-up as in __fdividef)
 __device__ __forceinline__ float pb_rcp(float x) {
 #ifdef PB_SIMT_EMU
@@ -37,7 +38,6 @@ __device__ __forceinline__ float pb_rcp(float x) {
 #endif
 }
 
-template <bool ABS>
 __device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, float x, int depth, int sl, int nl = 8) {
     const float fl = floorf(x);
     const float phi = x - fl;
@@ -45,7 +45,7 @@ __device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, fl
     int D = B - il; if (depth < D) D = depth;
     float acc = 0.0f;
     if (phi == 0.0f) {                                        // on a sample: Praat returns y[x] (no early return:
-        if (sl == 0 && depth > 0) acc = r[ABS ? abs(il) : il];   // the other groups of the warp still shuffle below)
+        if (sl == 0 && depth > 0) acc = r[il];                // the other groups of the warp still shuffle below)
     } else if (D > 0) {
         const int side = sl & 1, j0 = sl >> 1, hs = nl >> 1;  // hs (4, 8, 16) is even: the sign of a lane's terms is fixed
         const float e = side ? 1.0f - phi : phi;
@@ -54,7 +54,7 @@ __device__ __forceinline__ float pb_sinc8(const float* __restrict__ r, int B, fl
         float d = e + (float)j0;
         int idx = side ? il + 1 + j0 : il - j0;
         const int step = side ? hs : -hs;
-        if (ABS) {
+        if (depth > 70) {                                     // rare: candidates above 0.3 / dx (lags below 3.33)
             for (int m = j0; m < D; m += hs) {
                 const float yv = r[abs(idx)];
                 acc += __fdividef(yv * (1.0f + __cosf(d * k)), d);
@@ -119,7 +119,7 @@ __device__ PB_NOINLINE int pb_candidates_overflow(const float* __restrict__ r, f
             const int ip = have ? base + __ffs((int)m) - 1 : 2;
             const float dr = 0.5f * (r[ip + 1] - r[ip - 1]), d2r = 2.0f * r[ip] - r[ip - 1] - r[ip + 1];
             const float x0 = (float)ip + ((have && d2r > 0.0f) ? __fdividef(dr, d2r) : 0.0f);
-            float st = pb_sinc8<false>(r, B, x0, have ? 30 : 0, sl);
+            float st = pb_sinc8(r, B, x0, have ? 30 : 0, sl);
             if (st > 1.0f) st = __fdividef(1.0f, st);
             const float fq0 = __fdividef(gm.sr, x0);
             for (int q = 0; q < 4; q++) {
@@ -156,14 +156,13 @@ __device__ PB_NOINLINE int pb_candidates_overflow(const float* __restrict__ r, f
 // thing: golden-section / parabolic minimisation of -y(x) over [i-1, i+1] (Brent 1973, the routine Praat calls), to a
 // lag tolerance of 1e-3 samples (4e-5 relative at the shortest refined lag), one candidate at a time with all 32 lanes on
 // each sinc evaluation.
-template <bool ABS>
 __device__ PB_NOINLINE void pb_brent_refine(const float* __restrict__ r, int B, float fi, int depth, int lane, float* bx, float* by) {
     const float golden = 0.38196601125f, tol = 1.0e-3f;
     float a = fi - 1.0f, b = fi + 1.0f;
     float t = a + golden * (b - a);
     float x = t, v = t, w = t, fx = 0.0f, fv = 0.0f, fw = 0.0f;
     for (int iter = 0; iter < 32; iter++) {                   // every lane carries the same state: the loop is warp-uniform
-        const float ft = -pb_sinc8<ABS>(r, B, t, depth, lane, 32);
+        const float ft = -pb_sinc8(r, B, t, depth, lane, 32);
         if (iter == 0) { fx = fv = fw = ft; }
         else if (ft <= fx) { if (t < x) b = x; else a = x; v = w; w = x; x = t; fv = fw; fw = fx; fx = ft; }
         else {
@@ -198,7 +197,6 @@ __device__ PB_NOINLINE void pb_brent_refine(const float* __restrict__ r, int B, 
 // reproduces Brent's optimum to ~1e-4 relative in lag and ~1e-6 in strength (DESIGN.md "candidate refinement").
 // Maxima below min_refine_lag stay above the pitch ceiling wherever in [i-1, i+1] their refinement lands: the path
 // finder treats them as voiceless whatever their strength, so they keep their first-pass values.
-template <bool ABS>
 __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r, float* scratch, const PbPitchGeomDev& gm,
                                                     int lane, float* __restrict__ out_f, float* __restrict__ out_s,
                                                     uint8_t* __restrict__ out_n, const float* __restrict__ half_tab) {
@@ -303,7 +301,7 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
 #pragma unroll 1
 #endif
         for (int e = 0; e < 4; e++) {
-            float y = pb_sinc8<ABS>(r, B, xe, (tab && e < 2) ? 0 : depth, sl, nl);
+            float y = pb_sinc8(r, B, xe, (tab && e < 2) ? 0 : depth, sl, nl);
             if (tab && e < 2) y = e ? tb : ta;
             if (e == 0) { ya = y; xe = fi + 0.5f; }
             else if (e == 1) {
@@ -345,7 +343,7 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
         for (int k = 0; k < n_flagged; k++) {
             const int code = flagged[k], c = code & 0xff;
             float bx, by;
-            pb_brent_refine<ABS>(r, B, (float)imax[c], (code & 0x100) ? 700 : 70, lane, &bx, &by);
+            pb_brent_refine(r, B, (float)imax[c], (code & 0x100) ? 700 : 70, lane, &bx, &by);
             if (by > 1.0f) by = __fdividef(1.0f, by);
             if (lane == 0) { out_f[c] = __fdividef(gm.sr, bx); out_s[c] = by; }
         }
@@ -357,7 +355,7 @@ __device__ __forceinline__ void pb_frame_candidates(const float* __restrict__ r,
 #define PB_CAND_WARPS 4
 
 // MIN_CTAS: residency target (10 -> 48 registers with a few spilled words, 8 -> 64 registers); chosen at launch (PB_CAND_CTAS)
-template <int MIN_CTAS, bool ABS>
+template <int MIN_CTAS>
 __global__ void __launch_bounds__(PB_CAND_WARPS * 32, MIN_CTAS)
 pb_pitch_cand_kernel(const float* __restrict__ racf, const long long* __restrict__ slot_fr, int n_slots, int rstride_g, PbPitchGeomDev gm,
                      float* __restrict__ cand_f, float* __restrict__ cand_s, uint8_t* __restrict__ ncand, unsigned* __restrict__ work_counter) {
@@ -411,7 +409,7 @@ pb_pitch_cand_kernel(const float* __restrict__ racf, const long long* __restrict
             float* r = rbuf + b * rrow + PB_MIR;
             for (int q = 1 + lane; q < PB_MIR && q < rstride_g; q += 32) r[-q] = r[q];     // the mirror image
             __syncwarp();
-            pb_frame_candidates<ABS>(r, scratch, gm, lane, cand_f + fr * mc, cand_s + fr * mc, ncand + fr, half_tab);
+            pb_frame_candidates(r, scratch, gm, lane, cand_f + fr * mc, cand_s + fr * mc, ncand + fr, half_tab);
             __syncwarp();                              // every lane is done with this buffer before it is refilled
             b ^= 1;
         }

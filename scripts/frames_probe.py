@@ -13,7 +13,7 @@ pcm = synth.make_corpus(n_utt, dur, sr, seed=1234, device="cuda")
 n = pcm.shape[1]
 units = pb.Units.from_list([(i * n, n, sr, 0.0, None, float(sr)) for i in range(n_utt)])
 p = pb.pitch_params(75.0, 600.0)
-ex = pb.Extractor(0)
+ex = pb.Extractor(0, lib=pb._native.load(os.environ["PB_LIB"])) if os.environ.get("PB_LIB") else pb.Extractor(0)
 flat = pcm.reshape(-1)
 best = None
 for it in range(5):
@@ -22,6 +22,6 @@ for it in range(5):
     if it >= 2 and (best is None or t["frames_ms"] < best["frames_ms"]):
         best = t
 fr = best["n_frames"]
-print({k: os.environ.get(k) for k in ("PB_CAND_CTAS", "PB_FRAMES_CTAS", "PB_RACF_BYTES") if os.environ.get(k)},
+print({k: os.environ.get(k) for k in ("PB_LIB", "PB_CAND_CTAS", "PB_ACF_CTAS", "PB_ACF_WSYNC", "PB_RACF_BYTES") if os.environ.get(k)},
       f"frames {fr}  acf {best['acf_ms']:.3f} ms  cand {best['cand_ms']:.3f} ms  frames(K1+K2) {best['frames_ms']:.3f} ms  path {best['path_ms']:.3f} ms  "
       f"-> {best['frames_ms'] * 1e6 / fr:.2f} ns/frame; voiced {r['n_voiced'].sum() / fr:.3f}")

@@ -185,3 +185,27 @@ def test_emulated_interval_reduction_matches_numpy(emu, oracle):
     # the whole-unit interval reproduces get_median_pitch
     whole = emu.reduce_intervals(r["frame_off"], t_first, dt, r["frame_f0"], [(i, -1.0, 99.0) for i in range(4)])
     assert np.array_equal(whole["median_f0"], r["median_f0"]) and np.array_equal(whole["n_voiced"], r["n_voiced"])
+
+
+def _many_maxima(sr, dur, seed):
+    """Voiced speech-like fundamental plus strong tonal high-frequency content: more autocorrelation maxima than candidate slots."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(int(sr * dur)) / sr
+    x = 0.25 * np.sin(2 * np.pi * 190.0 * t) + 0.3 * np.sin(2 * np.pi * 2500.0 * t + 0.3) + 0.2 * np.sin(2 * np.pi * 3100.0 * t) + 0.01 * rng.standard_normal(len(t))
+    return (x * 20000).astype(np.int16)
+
+
+@pytest.mark.parametrize("floor,ceiling", [(75.0, 600.0), (150.0, 4800.0)])
+def test_emulated_overflow_and_deep_refinement_paths(emu, oracle, floor, ceiling):
+    """More maxima than candidate slots (Praat's replace-the-weakest insertion), and candidates above 0.3 / dx that are refined at
+    interpolation depth 700 (reach beyond the mirrored part of r): both are rare on speech, so they get their own input."""
+    import prosody_b200 as pb
+    sr = 16000
+    x = _many_maxima(sr, 0.3, 5)
+    units = pb.Units.from_list([(0, len(x), sr, 0.0, None)])
+    r = emu.median_pitch(x, units, pb.pitch_params(floor, ceiling), frames=True)
+    o = oracle.pitch_track(x, sr, params=oracle.pitch_params(floor, ceiling))
+    assert r["n_frames"][0] == o["n_frames"]
+    agree, rel = compare_tracks(r["frame_f0"], o["frequency"])
+    assert agree >= 1.0 - 1.0 / o["n_frames"] and rel < 5e-3
+    assert np.max(np.abs(r["frame_strength"] - o["strength"])) < 2e-3

@@ -562,3 +562,23 @@ def test_fewer_than_eight_candidates_and_parameter_validation(gpu_extractor, ora
         kw = dict(pitch_floor=75.0, pitch_ceiling=600.0); kw.update(bad)
         with pytest.raises(Exception):
             gpu_extractor.median_pitch(x.reshape(-1), units, pb.pitch_params(**kw))
+
+
+@pytest.mark.parametrize("floor,ceiling", [(75.0, 600.0), (150.0, 4800.0)])
+def test_overflow_and_deep_refinement_paths(gpu_extractor, oracle, floor, ceiling):
+    """More autocorrelation maxima than candidate slots (Praat's replace-the-weakest insertion) and candidates above 0.3 / dx
+    (interpolation depth 700, index reach beyond the mirrored part of r in shared memory): rare on speech, so they get an input of
+    their own — a voiced fundamental under strong tonal high-frequency content — at several rates."""
+    import prosody_b200 as pb
+    from test_emu_parity import _many_maxima
+    for sr in (16000, 48000):
+        x = np.stack([_many_maxima(sr, 0.5, s) for s in (5, 6, 7)])
+        units = _units_whole(pb, x, sr)
+        r = gpu_extractor.median_pitch(x.reshape(-1), units, pb.pitch_params(floor, ceiling), frames=True)
+        for i in range(x.shape[0]):
+            o = oracle.pitch_track(x[i], sr, params=oracle.pitch_params(floor, ceiling))
+            a, b = r["frame_off"][i], r["frame_off"][i + 1]
+            assert b - a == o["n_frames"]
+            agree, rel = compare_tracks(r["frame_f0"][a:b], o["frequency"])
+            assert agree >= VOICING_AGREE and rel < F0_TOL, (sr, floor, ceiling, agree, rel)
+            assert np.max(np.abs(r["frame_strength"][a:b] - o["strength"])) < 2e-3
