@@ -151,6 +151,19 @@ int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_o
                      double* median_f0, int32_t* n_voiced, int32_t* n_frames,
                      double* lufs, double* duration_s, int32_t* status);
 
+/* The same call in two halves, so that the host can prepare the next batch while the GPU works on this one (the reference's own
+ * concurrency is one process per voice, Code/audioPipeline.py:1141-1150; here it is batches in flight).  pb_extract_submit plans
+ * the units, enqueues the uploads, the kernels and the result download on the handle's streams and returns; n_frames and
+ * duration_s (host arithmetic) are already final.  pb_extract_wait blocks until the GPU is done and fills median_f0, n_voiced,
+ * lufs and status.  The unit arrays may be reused after submit returns; pcm (host) and the output arrays must stay valid until
+ * wait returns.  One batch per handle may be pending: use two handles to keep two batches in flight. */
+int pb_extract_submit(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device,
+                      const PbUnits* u, const PbPitchParams* p,
+                      const uint8_t* want_pitch, const uint8_t* want_lufs,
+                      double* median_f0, int32_t* n_voiced, int32_t* n_frames,
+                      double* lufs, double* duration_s, int32_t* status);
+int pb_extract_wait(PbHandle* h);
+
 /* Praat Sound_to_Intensity (parselmouth Sound.to_intensity(minimum_pitch=100, time_step=0, subtract_mean=True)),
  * whole files only.  n_frames[f] / frame_off from pb_intensity_plan; intensity_db has frame_off[n] entries. */
 int pb_intensity_plan(const PbUnits* u, double minimum_pitch, double time_step, int32_t* status,

@@ -52,7 +52,8 @@ EXPORTS = ["pb_syntagme_deltas", "pb_ema_clamp", "pb_abi_version", "pb_create", 
            "pb_device_info", "pb_pitch_params_default", "pb_pitch_plan", "pb_median_pitch_batch", "pb_lufs_batch",
            "pb_part_duration_batch", "pb_extract_batch", "pb_intensity_plan", "pb_intensity_batch", "pb_legacy_loudness_batch", "pb_split_on_silence_bound",
            "pb_split_on_silence_batch", "pb_segment_baselines", "pb_textgrid_parse_files",
-           "pb_textgrid_sizes", "pb_textgrid_copy", "pb_textgrid_free", "pb_pitch_frame_times", "pb_reduce_intervals"]
+           "pb_textgrid_sizes", "pb_textgrid_copy", "pb_textgrid_free", "pb_pitch_frame_times", "pb_reduce_intervals",
+           "pb_extract_submit", "pb_extract_wait"]
 
 
 def bind(lib: C.CDLL) -> C.CDLL:
@@ -71,6 +72,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.pb_lufs_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, dp, i32p]
     lib.pb_part_duration_batch.argtypes = [U, dp, i32p]
     lib.pb_extract_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, P, u8p, u8p, dp, i32p, i32p, dp, dp, i32p]
+    lib.pb_extract_submit.argtypes = [vp, vp, C.c_int64, C.c_int, U, P, u8p, u8p, dp, i32p, i32p, dp, dp, i32p]
+    lib.pb_extract_wait.argtypes = [vp]
     lib.pb_intensity_plan.argtypes = [U, C.c_double, C.c_double, i32p, i32p, i64p, dp, dp]
     lib.pb_intensity_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, C.c_double, C.c_double, C.c_int, fp, i32p]
     lib.pb_legacy_loudness_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, dp, i64p, i64p]

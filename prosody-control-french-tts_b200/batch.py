@@ -199,6 +199,34 @@ class Extractor:
         del keep
         return dict(median_f0=med, n_voiced=nv, n_frames=nf, lufs=lu, duration_s=du, status=st)
 
+    def submit(self, pcm, units: Units, params: N.PbPitchParams | None = None, want_pitch=None, want_lufs=None) -> None:
+        """First half of extract(): plan the units, enqueue uploads / kernels / result download, return at once.  The host is free
+        (to plan the next batch on ANOTHER Extractor, to post-process the previous one) while the GPU works; wait() collects."""
+        params = params or pitch_params()
+        addr, n_samp, on_dev, keep = _pcm_pointer(pcm)
+        n = len(units)
+        out = dict(median_f0=np.zeros(n), n_voiced=np.zeros(n, np.int32), n_frames=np.zeros(n, np.int32), lufs=np.full(n, np.nan),
+                   duration_s=np.zeros(n), status=np.zeros(n, np.int32))
+        wp = None if want_pitch is None else np.ascontiguousarray(want_pitch, np.uint8)
+        wl = None if want_lufs is None else np.ascontiguousarray(want_lufs, np.uint8)
+        cu = units.c_struct()
+        rc = self._lib.pb_extract_submit(self._h, C.c_void_p(addr), n_samp, on_dev, C.byref(cu), C.byref(params),
+                                         _ptr(wp, C.c_uint8) if wp is not None else None, _ptr(wl, C.c_uint8) if wl is not None else None,
+                                         _ptr(out["median_f0"], C.c_double), _ptr(out["n_voiced"], C.c_int32), _ptr(out["n_frames"], C.c_int32),
+                                         _ptr(out["lufs"], C.c_double), _ptr(out["duration_s"], C.c_double), _ptr(out["status"], C.c_int32))
+        N.check(self._lib, self._h, rc, "pb_extract_submit")
+        self._pending = (out, keep, units, wp, wl)          # keeps the PCM and the output arrays alive until wait()
+
+    def wait(self) -> dict:
+        """Second half of extract(): blocks until the submitted batch is done, returns its per-unit results."""
+        if getattr(self, "_pending", None) is None:
+            raise RuntimeError("no submitted batch to wait for")
+        out = self._pending[0]
+        rc = self._lib.pb_extract_wait(self._h)
+        self._pending = None
+        N.check(self._lib, self._h, rc, "pb_extract_wait")
+        return out
+
 
     def intensity(self, pcm, units: Units, minimum_pitch: float = 100.0, time_step: float = 0.0, subtract_mean: bool = True) -> dict:
         """parselmouth ``Sound.to_intensity(minimum_pitch, time_step, subtract_mean)`` for every (whole-file) unit.

@@ -138,6 +138,9 @@ struct PbHandle {
     std::map<int, size_t> occ_last;                        // LOG2N -> footprint the function attributes were last set for
     BatchPlan plan;                                        // host plan of the call in progress (scratch reused across calls)
     int64_t cur_pcm_len = 0;                               // samples in the pcm buffer of the call in progress
+    // a submitted batch whose results have not been collected yet (pb_extract_submit / pb_extract_wait)
+    struct Pending { bool active = false; int64_t n = 0; bool do_pitch = false, do_lufs = false;
+                     double* median_f0 = nullptr; int32_t* n_voiced = nullptr; double* lufs = nullptr; int32_t* status = nullptr; } pending;
     size_t sil_smem = 0; int sil_per_sm = 2, sil_nv = 0;               // K5: footprint its function attribute was set for, resident CTAs per SM
 };
 
@@ -692,8 +695,13 @@ struct BatchOut {
     float* frame_f0 = nullptr; float* frame_strength = nullptr; float* frame_intensity = nullptr;   // force a single segment
 };
 
-int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, const PbUnits* u, const PbPitchParams* p,
-              const uint8_t* want_pitch, const uint8_t* want_lufs, const BatchOut& o) {
+int finish_batch(PbHandle* h);
+
+// Plans the batch, enqueues every copy and kernel and the result download, and returns without waiting for the GPU.  The outputs are
+// filled by finish_batch (which the blocking entry points call right away, and pb_extract_wait later).
+int submit_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, const PbUnits* u, const PbPitchParams* p,
+                 const uint8_t* want_pitch, const uint8_t* want_lufs, const BatchOut& o) {
+    if (h->pending.active) return fail(h, PB_EINVAL, "%s", "a submitted batch is still pending on this handle: call pb_extract_wait first");
     int rc = validate_units(h, u, pcm_len);
     if (rc != PB_OK) return rc;
     if (o.median_f0) { const char* pe = pitch_params_error(p); if (pe) return fail(h, PB_EINVAL, "%s", pe); }
@@ -955,19 +963,38 @@ int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, c
     if (o.duration_s) for (int64_t i = 0; i < n; i++) {
         int st; o.duration_s[i] = pb_part_duration(u->file_nx[i], u->rate[i], u->has_t1[i], u->t0[i], u->t1[i], &st);
     }
-    PB_CK(pbrt_stream_sync(h->stream), "stream sync");
-    PB_CK(pbrt_stream_sync(h->copy_stream), "stream sync");
-    PB_CK(pbrt_stream_sync(h->lufs_stream), "stream sync");
-    end_call(h);
-    const char* so = (const char*)h->stage_out.p;
-    if (do_pitch) { memcpy(o.median_f0, so, (size_t)n * 8); memcpy(o.n_voiced, so + (size_t)n * 8, (size_t)n * 4); }
-    if (do_lufs) {
-        memcpy(o.lufs, so + (size_t)n * 12, (size_t)n * 8);
-        for (auto& d : bp.dups) o.lufs[d.first] = o.lufs[d.second];
-    }
-    if (o.status) for (int64_t i = 0; i < n; i++) o.status[i] = pstat[(size_t)i] | lflags[(size_t)i];
+    h->pending.active = true; h->pending.n = n; h->pending.do_pitch = do_pitch; h->pending.do_lufs = do_lufs;
+    h->pending.median_f0 = o.median_f0; h->pending.n_voiced = o.n_voiced; h->pending.lufs = o.lufs; h->pending.status = o.status;
     rc_final = PB_OK;
     return PB_OK;
+}
+
+// Waits for the submitted batch and hands its results to the caller's arrays.
+int finish_batch(PbHandle* h) {
+    if (!h->pending.active) return fail(h, PB_EINVAL, "%s", "no submitted batch to wait for");
+    h->pending.active = false;
+    pbrt_set_device(h->device);
+    int rc = PB_OK;
+    if (pbrt_stream_sync(h->stream) | pbrt_stream_sync(h->copy_stream) | pbrt_stream_sync(h->lufs_stream))
+        rc = fail(h, PB_ECUDA, "%s", (std::string("stream sync: ") + pbrt_error()).c_str());
+    if (rc != PB_OK) return rc;
+    end_call(h);
+    const BatchPlan& bp = h->plan;
+    const int64_t n = h->pending.n;
+    const char* so = (const char*)h->stage_out.p;
+    if (h->pending.do_pitch) { memcpy(h->pending.median_f0, so, (size_t)n * 8); memcpy(h->pending.n_voiced, so + (size_t)n * 8, (size_t)n * 4); }
+    if (h->pending.do_lufs) {
+        memcpy(h->pending.lufs, so + (size_t)n * 12, (size_t)n * 8);
+        for (auto& d : bp.dups) h->pending.lufs[d.first] = h->pending.lufs[d.second];
+    }
+    if (h->pending.status) for (int64_t i = 0; i < n; i++) h->pending.status[i] = bp.pstat[(size_t)i] | bp.lflags[(size_t)i];
+    return PB_OK;
+}
+
+int run_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, const PbUnits* u, const PbPitchParams* p,
+              const uint8_t* want_pitch, const uint8_t* want_lufs, const BatchOut& o) {
+    const int rc = submit_batch(h, pcm, pcm_len, on_device, u, p, want_pitch, want_lufs, o);
+    return rc != PB_OK ? rc : finish_batch(h);
 }
 
 }  // namespace
@@ -1063,6 +1090,21 @@ int pb_extract_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_o
     BatchOut o;
     o.median_f0 = median_f0; o.n_voiced = n_voiced; o.n_frames = n_frames; o.lufs = lufs; o.duration_s = duration_s; o.status = status;
     return run_batch(h, pcm, pcm_len, pcm_on_device, u, p, want_pitch, want_lufs, o);
+}
+
+int pb_extract_submit(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int pcm_on_device, const PbUnits* u, const PbPitchParams* p,
+                      const uint8_t* want_pitch, const uint8_t* want_lufs,
+                      double* median_f0, int32_t* n_voiced, int32_t* n_frames, double* lufs, double* duration_s, int32_t* status) {
+    if (!h) return PB_EINVAL;
+    if (!pcm || !p || !status) return fail(h, PB_EINVAL, "%s", "null argument");
+    BatchOut o;
+    o.median_f0 = median_f0; o.n_voiced = n_voiced; o.n_frames = n_frames; o.lufs = lufs; o.duration_s = duration_s; o.status = status;
+    return submit_batch(h, pcm, pcm_len, pcm_on_device, u, p, want_pitch, want_lufs, o);
+}
+
+int pb_extract_wait(PbHandle* h) {
+    if (!h) return PB_EINVAL;
+    return finish_batch(h);
 }
 
 #include "pb_api_host.inc"

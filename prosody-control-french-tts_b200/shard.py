@@ -29,20 +29,23 @@ def partition_by_cost(costs: Sequence[float], world: int) -> list[list[int]]:
 
 
 def row_counts(n_local: int, device) -> list[int]:
-    """Row count of every rank (one all_gather).  A caller whose shards do not change from step to step exchanges them
-    once and passes them to gather_rows, which then needs no host synchronisation on the sending ranks."""
+    """Row count of every rank (ONE all_gather_into_tensor).  A caller whose shards do not change from step to step exchanges them
+    once and passes them to gather_rows, which then needs no size exchange and no host synchronisation on the sending ranks."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
     mine = torch.tensor([n_local], dtype=torch.int64, device=device)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(sizes, mine)
-    return [int(s.item()) for s in sizes]
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sizes, mine)
+    return [int(v) for v in sizes.tolist()]
 
 
-def gather_rows(rows, index, dst: int = 0, sizes: list[int] | None = None):
-    """Gather [n_r, k] float64 rows and their global row ids [n_r] from every rank onto `dst`; returns the rows in
-    global order on dst (None elsewhere).  Works for gloo (CPU tensors) and NCCL (CUDA tensors)."""
+def gather_rows(rows, index=None, dst: int = 0, sizes: list[int] | None = None, order=None):
+    """Ragged gather of [n_r, k] float64 rows from every rank onto `dst`: every rank sends exactly its rows (point-to-point, true
+    counts — nothing is padded to the largest shard), `dst` receives them rank by rank.  Global order: either `order`, the global
+    row id of every gathered row in rank-major order, which `dst` can compute itself when the partition is deterministic (no ids
+    travel at all), or `index`, this rank's int64 ids, which then travel as their own int64 message.  Returns the rows in global
+    order on dst (None elsewhere).  Works for gloo (CPU tensors) and NCCL (CUDA tensors)."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -50,18 +53,37 @@ def gather_rows(rows, index, dst: int = 0, sizes: list[int] | None = None):
     k = rows.shape[1]
     if sizes is None:
         sizes = row_counts(rows.shape[0], dev)
-    mx = max(sizes + [1])
-    pad = torch.zeros(mx, k + 1, dtype=torch.float64, device=dev)
-    pad[:rows.shape[0], :k] = rows
-    pad[:rows.shape[0], k] = index.to(torch.float64)
-    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst)
+    rows = rows.contiguous()
+    send_ids = index is not None and order is None
     if rank != dst:
+        ops = []
+        if rows.shape[0]:
+            ops.append(dist.P2POp(dist.isend, rows, dst))
+            if send_ids:
+                ops.append(dist.P2POp(dist.isend, index.to(torch.int64).contiguous(), dst))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
         return None
-    allr = torch.cat([b[:n] for b, n in zip(bufs, sizes)], 0)
-    ids = allr[:, k].to(torch.int64)
+    parts = [rows if r == dst else torch.empty(sizes[r], k, dtype=torch.float64, device=dev) for r in range(world)]
+    idp = [(index.to(torch.int64) if r == dst else torch.empty(sizes[r], dtype=torch.int64, device=dev)) for r in range(world)] if send_ids else None
+    ops = []
+    for r in range(world):
+        if r != dst and sizes[r]:
+            ops.append(dist.P2POp(dist.irecv, parts[r], r))
+            if send_ids:
+                ops.append(dist.P2POp(dist.irecv, idp[r], r))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    allr = torch.cat(parts, 0)
+    ids = None
+    if order is not None:
+        ids = torch.as_tensor(order, dtype=torch.int64, device=dev)
+    elif send_ids:
+        ids = torch.cat(idp, 0)
     # rows come sorted per rank; only an interleaved partition needs the global sort (done where the data lives: on the GPU
     # for NCCL, where a 5e5-row argsort is microseconds instead of the tens of milliseconds of a single host thread)
-    if ids.numel() > 1 and not bool((ids[1:] >= ids[:-1]).all()):
+    if ids is not None and ids.numel() > 1 and not bool((ids[1:] >= ids[:-1]).all()):
         allr = allr[torch.argsort(ids, stable=True)]
-    return allr[:, :k].cpu()
+    return allr.cpu()

@@ -130,19 +130,42 @@ def measure(ex: Extractor, pcm, pl: Plan, prosody: dict | None = None, pitch: di
     S, K = pl.n_seg, pl.n_syn
     r = ex.extract(pcm, pl.units, pp, want_pitch=pl.want_pitch, want_lufs=pl.want_lufs)
     st = r["status"]
-    if strict:
-        bad = np.nonzero(((st & N.PB_UNIT_PITCH_MASK) != 0) & (pl.want_pitch != 0))[0]
-        if len(bad):
-            u = int(bad[0])
-            raise PraatError(f"unit {u} (t0={pl.units.t0[u]}, t1={pl.units.t1[u]}): Praat refuses this slice "
-                             f"(status {int(st[u]) & N.PB_UNIT_PITCH_MASK}); the reference step aborts here")
-        bad = np.nonzero((st & (N.PB_UNIT_LUFS_ERROR | N.PB_UNIT_SLICE_ERROR)) != 0)[0]
-        if len(bad):
-            raise ValueError(f"unit {int(bad[0])}: Audio must have length greater than the block size.")
+    _raise_like_the_reference(st, pl, strict)
     out = finish(pl, r["median_f0"], r["lufs"], r["duration_s"], prm, ex._lib)
     out["status"] = st
     out["timings"] = ex.timings()
     return out
+
+
+def submit(ex: Extractor, pcm, pl: Plan, pitch: dict | None = None) -> None:
+    """Asynchronous first half of measure(): everything up to the GPU results is enqueued on `ex`; collect() finishes the step.
+    With two Extractors a caller keeps two batches in flight: batch k+1 is planned and enqueued, batch k-1 post-processed, while the
+    GPU runs batch k."""
+    ex.submit(pcm, pl.units, pitch_params(**(pitch or REFERENCE_PITCH)), want_pitch=pl.want_pitch, want_lufs=pl.want_lufs)
+
+
+def collect(ex: Extractor, pl: Plan, prosody: dict | None = None, strict: bool = True) -> dict:
+    """Second half of measure() for a batch submitted with submit()."""
+    prm = dict(DEFAULT_PROSODY); prm.update(prosody or {})
+    r = ex.wait()
+    _raise_like_the_reference(r["status"], pl, strict)
+    out = finish(pl, r["median_f0"], r["lufs"], r["duration_s"], prm, ex._lib)
+    out["status"] = r["status"]
+    out["timings"] = ex.timings()
+    return out
+
+
+def _raise_like_the_reference(st, pl: Plan, strict: bool) -> None:
+    if not strict:
+        return
+    bad = np.nonzero(((st & N.PB_UNIT_PITCH_MASK) != 0) & (pl.want_pitch != 0))[0]
+    if len(bad):
+        u = int(bad[0])
+        raise PraatError(f"unit {u} (t0={pl.units.t0[u]}, t1={pl.units.t1[u]}): Praat refuses this slice "
+                         f"(status {int(st[u]) & N.PB_UNIT_PITCH_MASK}); the reference step aborts here")
+    bad = np.nonzero((st & (N.PB_UNIT_LUFS_ERROR | N.PB_UNIT_SLICE_ERROR)) != 0)[0]
+    if len(bad):
+        raise ValueError(f"unit {int(bad[0])}: Audio must have length greater than the block size.")
 
 
 def finish(pl: Plan, med, lufs, dur, prm: dict, lib=None) -> dict:

@@ -46,6 +46,10 @@ def _worker(rank, world, port, tmp):
         assert sum(sizes) == int(first[-1]) and sizes[rank] == len(ids)
         again = shard.gather_rows(torch.from_numpy(rows), torch.from_numpy(ids), dst=0, sizes=sizes)
         assert (again is None) == (rank != 0) and (rank != 0 or np.array_equal(again.numpy(), out.numpy()))
+        # the partition is deterministic: rank 0 can work out the global order itself, so no ids travel at all
+        order = np.concatenate([np.concatenate([np.arange(first[s], first[s + 1]) for s in p]) if p else np.zeros(0, np.int64) for p in parts])
+        third = shard.gather_rows(torch.from_numpy(rows), None, dst=0, sizes=sizes, order=order if rank == 0 else None)
+        assert (third is None) == (rank != 0) and (rank != 0 or np.array_equal(third.numpy(), out.numpy()))
         if rank == 0:
             total = int(first[-1])
             g = np.arange(total)

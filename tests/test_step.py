@@ -155,3 +155,34 @@ def test_comma_filter_uses_the_taggers_own_tokens():
     grid = [(0.0, 0.5, "l'homme"), (0.5, 0.9, ""), (0.9, 1.4, "dit-il,")]
     seq = IV.segment_sequence(grid, tg, 150)
     assert [k for k, _, _ in seq] == ["word", "word"] and seq[1][1] == "dit-il"
+
+
+def test_submit_wait_is_measure_in_two_halves(emu_lib):
+    """pb_extract_submit / pb_extract_wait: same results as the blocking call, one pending batch per handle, and two handles
+    keep two batches in flight (here on the emulator, where 'in flight' only means 'not collected yet')."""
+    import prosody_b200 as pb
+    from prosody_b200 import step as S
+    nat = speechlike(2, 1.2, 16000, seed=61); syn = speechlike(2, 1.1, 16000, seed=62)
+    bufs, segs, off = [], [], 0
+    for i, grid in enumerate((GRID_A[:5], GRID_B[:4])):
+        bufs += [nat[i], syn[i]]
+        segs.append(S.Segment(f"segment_ph{i + 1}", off, len(nat[i]), 16000, grid, off + len(nat[i]), len(syn[i]), 16000))
+        off += len(nat[i]) + len(syn[i])
+    pcm = np.concatenate(bufs)
+    pl = S.plan(segs, None, pos_of)
+    with pb.Extractor(0, lib=emu_lib) as a, pb.Extractor(0, lib=emu_lib) as b:
+        want = S.measure(a, pcm, pl)
+        S.submit(a, pcm, pl)
+        S.submit(b, pcm, pl)                                   # a second handle takes the next batch meanwhile
+        with pytest.raises(Exception):
+            S.submit(a, pcm, pl)                               # one pending batch per handle
+        with pytest.raises(Exception):
+            a.lufs(pcm, pl.units)                              # nor any other work on that handle
+        got_a = S.collect(a, pl); got_b = S.collect(b, pl)
+        with pytest.raises(Exception):
+            a.wait()
+        for got in (got_a, got_b):
+            for k in ("raw_pitch", "raw_volume", "raw_rate", "sm_pitch", "sm_rate"):
+                assert np.array_equal(got[k], want[k], equal_nan=True)
+            assert np.array_equal(got["status"], want["status"])
+        assert np.array_equal(S.measure(a, pcm, pl)["sm_pitch"], want["sm_pitch"])      # the handle is reusable afterwards
