@@ -584,6 +584,7 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
 // every group: launches are stream-ordered, and per-frame values are only read back when there is a single segment.
 // Results land in h->med / h->nvoiced (device, caller-indexed).
 int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p, const BatchPlan& bp, const PitchLaunch& L) {
+    PbRange r_("pb: launch K0 stats / K1 acf / K2 candidates / K3 path");
     {
         const PitchClass& pc = bp.classes[(size_t)L.cls];
         const size_t m = L.m;
@@ -664,6 +665,7 @@ void stage_lufs(PbHandle* h, const BatchPlan& bp, const std::vector<int64_t>& id
 }
 
 int launch_lufs_group(PbHandle* h, const int16_t* d_pcm, const LufsLaunch& L, pbStream_t stream) {
+    PbRange r_("pb: launch K4 loudness (peak, chunk, scan, chunk, gate)");
     const size_t m = L.m;
     if (!m) return PB_OK;
     PbLufsUnitDev* du = (PbLufsUnitDev*)h->lunits.p + L.off;
@@ -702,6 +704,7 @@ int finish_batch(PbHandle* h);
 int submit_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device, const PbUnits* u, const PbPitchParams* p,
                  const uint8_t* want_pitch, const uint8_t* want_lufs, const BatchOut& o) {
     if (h->pending.active) return fail(h, PB_EINVAL, "%s", "a submitted batch is still pending on this handle: call pb_extract_wait first");
+    PbRange r_submit("pb: submit batch (plan + enqueue)");
     int rc = validate_units(h, u, pcm_len);
     if (rc != PB_OK) return rc;
     if (o.median_f0) { const char* pe = pitch_params_error(p); if (pe) return fail(h, PB_EINVAL, "%s", pe); }
@@ -750,6 +753,7 @@ int submit_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device
     constexpr int NB = 512;                                          // planning histogram: work per 1/512 of the buffer
     auto bin_edge = [&](int b) { return b >= NB ? pcm_len : std::min<int64_t>(pcm_len, (((pcm_len * b) / NB + 127) & ~(int64_t)127)); };
     auto enqueue_upload = [&](int64_t a, int64_t b) -> int {
+        PbRange r_("pb: enqueue PCM upload segment");
         ScopedEv ev(h, EV_H2D, h->copy_stream);
         if (b > a) PB_CK(pbrt_h2d((char*)h->pcm.p + a * 2, pcm + a, (size_t)(b - a) * 2, h->copy_stream), "pcm upload");
         seg_end.push_back(b);
@@ -786,12 +790,14 @@ int submit_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device
     bool pitch_launched = false;
 
     auto plan_pitch_units = [&]() -> int {
+        PbRange r_("pb: plan pitch units (host, float64)");
         memset(o.n_frames, 0, (size_t)n * 4);
         int r = plan_pitch(h, u, p, want_pitch, pstat.data(), o.n_frames, bp);
         lap("plan_pitch");
         return r;
     };
     auto plan_lufs_units = [&]() -> int {
+        PbRange r_("pb: plan loudness units (host, float64)");
         int r = plan_lufs(h, u, want_lufs, lflags.data(), bp);
         lap("plan_lufs");
         return r;
@@ -801,6 +807,7 @@ int submit_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device
     // are not cut yet); round 2: the rest.  Descriptors already on the device are not uploaded again.
     size_t su_sent = 0, sp_sent = 0;
     auto stage_upload_pitch = [&](int round) -> int {
+        PbRange r_("pb: stage + upload pitch descriptors");
         const int n_seg = (int)seg_end.size();
         if (pids.size() < (size_t)n_seg) pids.resize((size_t)n_seg);
         if (pl.size() < (size_t)n_seg) pl.resize((size_t)n_seg);
@@ -845,6 +852,7 @@ int submit_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device
         return PB_OK;
     };
     auto stage_upload_lufs = [&]() -> int {
+        PbRange r_("pb: stage + upload loudness descriptors");
         const int n_seg = (int)seg_end.size();
         if (lids.size() < (size_t)n_seg) lids.resize((size_t)n_seg);
         for (auto& v : lids) v.clear();
@@ -972,6 +980,7 @@ int submit_batch(PbHandle* h, const int16_t* pcm, int64_t pcm_len, int on_device
 // Waits for the submitted batch and hands its results to the caller's arrays.
 int finish_batch(PbHandle* h) {
     if (!h->pending.active) return fail(h, PB_EINVAL, "%s", "no submitted batch to wait for");
+    PbRange r_wait("pb: wait for batch + copy results out");
     h->pending.active = false;
     pbrt_set_device(h->device);
     int rc = PB_OK;

@@ -28,6 +28,19 @@ typedef cudaEvent_t pbEvent_t;
 
 #define PB_FULL_MASK 0xffffffffu
 
+// ---- NVTX ranges (header-only NVTX3: no library to link; a no-op unless a profiler is attached).  The reference has no tracing
+// at all; these mark the host phases and kernel groups of a batch call on an Nsight timeline.
+#ifdef PB_SIMT_EMU
+struct PbRange { explicit PbRange(const char*) {} };
+#else
+#include <nvtx3/nvToolsExt.h>
+struct PbRange {
+    explicit PbRange(const char* name) { nvtxRangePushA(name); }
+    ~PbRange() { nvtxRangePop(); }
+    PbRange(const PbRange&) = delete; PbRange& operator=(const PbRange&) = delete;
+};
+#endif
+
 // ---- thin runtime wrappers (return 0 on success; the message of a failure is fetched with pbrt_error())
 #ifdef PB_SIMT_EMU
 #include <chrono>

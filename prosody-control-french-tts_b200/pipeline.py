@@ -29,6 +29,17 @@ class CouldntDecodeError(Exception):
     """Stands in for pydub.exceptions.CouldntDecodeError (the reference falls back to natural audio on it)."""
 
 
+class UnsupportedAudioError(Exception):
+    """A WAV file the reference WOULD decode but this path does not measure: anything but mono 16-bit PCM.
+
+    The reference hands any container to pydub / Praat: for interleaved stereo its loudness closure treats the interleaved
+    samples as a mono signal of twice the length (np.array(AudioSegment.get_array_of_samples()), Code/audioPipeline.py:343-348)
+    while Praat analyses the channels jointly, and 8 / 24 / 32-bit files are rescaled by each library in its own way.  None of
+    that is reproduced here (the pipeline's own steps only ever write mono s16).  It is deliberately NOT a CouldntDecodeError:
+    that one makes the step fall back to natural-audio metrics for a raw file (:385-388, :506-509), which would silently change
+    results; this one stops the step with the file name."""
+
+
 class Meter:
     """Shim for ``pyln.Meter(rate)``: the hot path only needs the rate the meter was built with."""
 
@@ -41,7 +52,8 @@ def read_wav(path):
     try:
         with wave.open(str(path), "rb") as w:
             if w.getsampwidth() != 2 or w.getnchannels() != 1 or w.getcomptype() != "NONE":
-                raise CouldntDecodeError(f"{path}: only mono 16-bit PCM WAV is supported")
+                raise UnsupportedAudioError(f"{path}: {w.getnchannels()} channel(s), {8 * w.getsampwidth()}-bit, {w.getcomptype()}: only mono 16-bit "
+                                            f"PCM WAV (what the pipeline itself writes) is measured; convert the file first")
             return np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").astype(np.int16), w.getframerate()
     except (wave.Error, EOFError, FileNotFoundError) as e:
         raise CouldntDecodeError(str(e)) from e

@@ -10,6 +10,10 @@ import pytest
 
 from conftest import speechlike
 
+# attempted in BOTH suites: the CPU one here, and (gpu-marked twin) on the GPU box, whichever machine happens to have the packages;
+# the install attempt on the GPU box is logged in profiles/r02_pip_real_packages.log (no network, not in /opt/wheelhouse)
+BOTH = pytest.mark.parametrize("where", ["build-box", pytest.param("gpu-box", marks=pytest.mark.gpu)])
+
 
 def _wav(path, pcm, sr):
     with wave.open(str(path), "wb") as w:
@@ -18,7 +22,8 @@ def _wav(path, pcm, sr):
     return str(path)
 
 
-def test_pitch_against_parselmouth(tmp_path, oracle):
+@BOTH
+def test_pitch_against_parselmouth(tmp_path, oracle, where):
     parselmouth = pytest.importorskip("parselmouth")
     for sr, floor in ((16000, 75.0), (44100, 150.0), (24000, 150.0)):
         x = speechlike(1, 2.0, sr, seed=sr // 100)[0]
@@ -38,7 +43,8 @@ def test_pitch_against_parselmouth(tmp_path, oracle):
         assert np.max(np.abs(oracle.intensity(x, sr) - inten)) < 1e-6
 
 
-def test_loudness_against_pyloudnorm(oracle):
+@BOTH
+def test_loudness_against_pyloudnorm(oracle, where):
     pyln = pytest.importorskip("pyloudnorm")
     for sr in (16000, 24000, 44100):
         x = speechlike(1, 3.0, sr, seed=sr // 50)[0]
@@ -48,7 +54,8 @@ def test_loudness_against_pyloudnorm(oracle):
             assert abs(oracle.lufs(x, sr, float(mr)) - pyln.Meter(mr).integrated_loudness(data)) < 1e-9
 
 
-def test_slicing_and_silence_against_pydub(tmp_path, oracle):
+@BOTH
+def test_slicing_and_silence_against_pydub(tmp_path, oracle, where):
     pydub = pytest.importorskip("pydub")
     from pydub.silence import split_on_silence
     from test_emu_parity import _gappy
