@@ -274,7 +274,8 @@ def bench_steps(args, rank, world, local):
             gathered = [None] * world if rank == 0 else None
             dist.gather_object(keys, gathered, dst=0)
             if rank == 0:
-                perm = torch.from_numpy(np.argsort(np.concatenate(gathered), kind="stable"))
+                perm = torch.from_numpy(np.argsort(np.concatenate(gathered), kind="stable")).to(dev)
+    gathered_host = torch.empty(sum(row_sizes), 5, dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0) else None
 
     def finish_step(ex):
         out = S.collect(ex, pl, prosody)
@@ -284,10 +285,12 @@ def bench_steps(args, rank, world, local):
         if world > 1:
             # final gather of the per-syntagme results on rank 0 (the path's only exchange): ragged, true counts, no ids on the wire
             rows = torch.from_numpy(np.stack([out["raw_pitch"], out["raw_volume"], out["raw_rate"], out["sm_pitch"], out["sm_rate"]], 1)).to(dev)
-            g = shard.gather_rows(rows, None, dst=0, sizes=row_sizes)
+            # (rank 0 puts them in global order on its GPU and copies them to pinned memory asynchronously: the copy is waited for by the
+            # synchronize that closes the timed region, not by every step)
+            g = shard.gather_rows(rows, None, dst=0, sizes=row_sizes, perm=perm, out=gathered_host)
             if rank == 0:
-                out["gathered"] = g[perm] if perm is not None else g
-                assert out["gathered"].shape == (sum(row_sizes), 5)
+                out["gathered"] = g
+                assert g.shape == (sum(row_sizes), 5)
         return out
 
     keys_t = ("frames_ms", "acf_ms", "cand_ms", "lufs_ms", "path_ms", "unit_stats_ms", "h2d_ms", "total_ms", "host_plan_ms", "n_launches", "n_frames")
@@ -328,12 +331,16 @@ def bench_steps(args, rank, world, local):
 
     W_ = max(args.warmup, 3)
     timed(pcm, W_, F)
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local)
+    if rank == 0:                   # one nvidia-smi poller per node, not one per rank
+        sampler.start()
     dt_dev, _, out, busy_dev = timed(pcm, args.steps, F)
     timed(host_pcm, 2, F)
     dt_e2e, _, _, busy_e2e = timed(host_pcm, args.steps, F)
     dt_ser, acc, _, _ = timed(pcm, args.steps, 1)
-    sampler.stop_flag.set(); sampler.join(timeout=2)
+    sampler.stop_flag.set()
+    if rank == 0:
+        sampler.join(timeout=2)
 
     if rank == 0:
         total_audio = wl.total_audio_s if strong else world * wl.audio_s

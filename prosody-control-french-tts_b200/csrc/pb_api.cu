@@ -488,10 +488,10 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
 #endif
     { const char* e = getenv("PB_FRAMES_CTAS"); if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e); }   // experiments: fewer resident CTAs
     // frame positions of every pair (float64 arithmetic, once)
-    PB_CKMEM(h->pairpos.ensure((size_t)gm.n_pairs * sizeof(int2) + 16), "pair positions");
+    PB_CKMEM(h->pairpos.ensure((size_t)gm.n_pairs * sizeof(int4) + 16), "pair positions");
     {
         const int pgrid = (int)std::max(1LL, std::min(((long long)gm.n_pairs + 255) / 256, (long long)h->sm_count * 8));
-        PB_LAUNCH(pb_pair_pos_kernel, dim3(pgrid), dim3(256), 0, h->stream, d_units, d_pair_off, gm, (int2*)h->pairpos.p);
+        PB_LAUNCH(pb_pair_pos_kernel, dim3(pgrid), dim3(256), 0, h->stream, d_pcm, d_units, d_pair_off, gm, (int4*)h->pairpos.p);
         h->last.n_launches++;
     }
     static const size_t racf_budget = [] { const char* e = getenv("PB_RACF_BYTES"); const long long v = e ? atoll(e) : 0; return (size_t)(v > 0 ? v : (4LL << 30)); }();
@@ -510,7 +510,7 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
         const int grid = (int)std::max(1LL, std::min(need, (long long)h->sm_count * per_sm));
         {
             ScopedEv ev(h, EV_ACF);
-            PB_LAUNCH(kfn, dim3(grid), dim3(threads), smem, h->stream, d_pcm, d_units, d_pair_off, (const int2*)h->pairpos.p, gm, item0, n_items, rstride_g,
+            PB_LAUNCH(kfn, dim3(grid), dim3(threads), smem, h->stream, d_pcm, d_units, d_pair_off, (const int4*)h->pairpos.p, gm, item0, n_items, rstride_g,
                       (float*)h->racf.p, (long long*)h->slot_fr.p, cand_f, cand_s, ncand, inten);
         }
         {

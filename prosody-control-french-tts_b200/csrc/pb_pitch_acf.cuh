@@ -43,25 +43,41 @@ __device__ __forceinline__ long long pb_frame_start(double t1, double x1, int fr
     return left + 1 - gm.half_nw;
 }
 
-// The float64 frame positions of every pair, computed once by a small kernel ahead of K1: {start0, hop}.
+// Everything K1 needs to stage a pair, computed once by a small kernel ahead of it (float64 frame positions, 64-bit address
+// arithmetic): {start0, hop, packed, src16}.  packed = shift | edge << 4 | dst16 << 8 | n16 << 16: the bulk copy moves n16
+// 16-byte chunks from pcm_base16 + 16 * src16 to the staging buffer + 16 * dst16; `edge` marks the pairs whose staged range is not
+// wholly inside the pcm buffer (first / last file of a call) or does not fit the packing: K1 stages those the long way.
+__device__ __forceinline__ int pb_span_lo(const PbPitchGeomDev& gm) { const int m = gm.half_nw - gm.nsamp_period; return m < 0 ? m : 0; }
+__device__ __forceinline__ int pb_span_hi(const PbPitchGeomDev& gm) { const int m = gm.half_nw + gm.nsamp_period; return m > gm.nw ? m : gm.nw; }
+
 __global__ void __launch_bounds__(256)
-pb_pair_pos_kernel(const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off, PbPitchGeomDev gm, int2* __restrict__ out) {
+pb_pair_pos_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off, PbPitchGeomDev gm, int4* __restrict__ out) {
+    const int span_lo = pb_span_lo(gm), span_len = pb_span_hi(gm) - span_lo;
+    const long long buf_lo = (long long)(size_t)pcm, buf_hi = buf_lo + 2 * gm.pcm_len;
+    const long long base16 = buf_lo & ~15LL, lo16 = (buf_lo + 15) & ~15LL, hi16 = buf_hi & ~15LL;
     for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < gm.n_pairs; item += gridDim.x * blockDim.x) {
         const int u = pb_upper_unit(pair_off, gm.n_units, item);
         const PbUnitDev* ud = units + u;
         const int fA = 2 * (item - ud->pair_off);
         const long long s0 = pb_frame_start(ud->t1, ud->x1, fA, gm);
         const int hop = fA + 1 < ud->n_frames ? (int)(pb_frame_start(ud->t1, ud->x1, fA + 1, gm) - s0) : 0;
-        out[item] = make_int2((int)s0, hop);
+        // frame A sample n is part sample start0+n = pcm sample pcm_off + ix1 + start0 + n - 2
+        const long long byte0 = buf_lo + 2 * (ud->pcm_off + ud->ix1 + s0 - 2 + span_lo);
+        const long long a0 = byte0 & ~15LL;
+        const int shift = (int)((byte0 - a0) >> 1);
+        const long long a1 = a0 + 16LL * ((shift + span_len + hop + 7) >> 3);
+        const long long src16 = (a0 - base16) >> 4, n16 = (a1 - a0) >> 4;
+        const bool edge = a0 < lo16 || a1 > hi16 || src16 < 0 || src16 > 0x7fffffffLL || n16 > 0xffff;
+        out[item] = make_int4((int)s0, hop, shift | (edge ? 16 : 0) | (int)((edge ? 0 : n16) << 16), (int)(edge ? 0 : src16));
     }
 }
 
-// Stage the samples the pair (frames fA, fA+1 of unit ud) will read into `dst`: every 16-byte chunk that lies entirely
+// The long way (edge pairs only, out of line).  Stage the samples the pair (frames fA, fA+1 of unit ud) will read into `dst`: every 16-byte chunk that lies entirely
 // inside the pcm buffer goes in ONE bulk copy issued by thread 0 of the group (completion on `bar`); the (at most two)
 // chunks straddling the ends of the buffer are filled sample by sample and flagged in pos.edge so that the group
 // synchronises before reading them.  Values outside the unit's part / file are masked at read time.
 template <int GT>
-__device__ __forceinline__ PbPairPos pb_stage_pair(const int16_t* __restrict__ pcm, const PbUnitDev& ud, int2 sp, const PbPitchGeomDev& gm,
+__device__ PB_NOINLINE PbPairPos pb_stage_pair_edge(const int16_t* __restrict__ pcm, const PbUnitDev& ud, int2 sp, long long pcm_len,
                                                    int span_lo, int span_len, int16_t* dst, int g, pbMbar* bar) {
     PbPairPos pos;
     pos.start0 = sp.x; pos.hop = sp.y; pos.edge = 0;
@@ -71,7 +87,7 @@ __device__ __forceinline__ PbPairPos pb_stage_pair(const int16_t* __restrict__ p
     const long long a0 = byte0 & ~15LL;
     pos.shift = (int)((byte0 - a0) >> 1);
     const long long a1 = a0 + 16LL * ((pos.shift + span_len + pos.hop + 7) >> 3);      // end of the staged range
-    const long long buf_lo = (long long)(size_t)pcm, buf_hi = buf_lo + 2 * gm.pcm_len;
+    const long long buf_lo = (long long)(size_t)pcm, buf_hi = buf_lo + 2 * pcm_len;
     const long long lo16 = (buf_lo + 15) & ~15LL, hi16 = buf_hi & ~15LL;                // whole chunks inside the buffer
     const long long c0 = a0 > lo16 ? a0 : lo16, c1 = a1 < hi16 ? a1 : hi16;
     if (g == 0) {
@@ -91,13 +107,28 @@ __device__ __forceinline__ PbPairPos pb_stage_pair(const int16_t* __restrict__ p
     return pos;
 }
 
+// The short way: the descriptor already holds the copy; thread 0 of the group issues it.
+template <int GT>
+__device__ __forceinline__ PbPairPos pb_stage_pair(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, int u, int4 d, long long pcm_len,
+                                                   int span_lo, int span_len, int16_t* dst, int g, pbMbar* bar) {
+    if (d.z & 16) return pb_stage_pair_edge<GT>(pcm, units[u], make_int2(d.x, d.y), pcm_len, span_lo, span_len, dst, g, bar);
+    PbPairPos pos;
+    pos.start0 = d.x; pos.hop = d.y; pos.shift = d.z & 15; pos.edge = 0;
+    if (g == 0) {
+        const unsigned bytes = ((unsigned)d.z >> 16) << 4;
+        pb_mbar_expect_tx(bar, bytes);
+        pb_bulk_g2s(dst, (const char*)((size_t)pcm & ~(size_t)15) + ((size_t)(unsigned)d.w << 4), bytes, bar);
+    }
+    return pos;
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 // MINB: resident CTAs per SM the register allocation targets; WSYNC: one-warp groups synchronise with __syncwarp() instead of a
 // named barrier (both chosen at launch: PB_ACF_CTAS / PB_ACF_WSYNC, defaults from the measurements in DESIGN.md)
 template <int LOG2N, int MINB, bool WSYNC>
 __global__ void __launch_bounds__(PbFftCfg<LOG2N>::WARPS_PER_CTA * 32, MINB)
 pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off,
-                    const int2* __restrict__ pairpos, PbPitchGeomDev gm, int item0, int n_items, int rstride_g,
+                    const int4* __restrict__ pairpos, PbPitchGeomDev gm, int item0, int n_items, int rstride_g,
                     float* __restrict__ racf, long long* __restrict__ slot_fr,
                     float* __restrict__ cand_f, float* __restrict__ cand_s, uint8_t* __restrict__ ncand, float* __restrict__ intensity) {
     typedef PbFftCfg<LOG2N> C;
@@ -148,7 +179,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     int u_next = pb_upper_unit(pair_off, gm.n_units, item0 + it_begin);
     int u_next_end = pair_off[u_next + 1];
     int u = -1;
-    PbPairPos pos_next = pb_stage_pair<GT>(pcm, units[u_next], pairpos[item0 + it_begin], gm, span_lo, span_len, pre, g, mbar);
+    PbPairPos pos_next = pb_stage_pair<GT>(pcm, units, u_next, pairpos[item0 + it_begin], gm.pcm_len, span_lo, span_len, pre, g, mbar);
     // what the loop needs of the current unit, refreshed when the unit changes (the 80-byte descriptor itself stays in L1 / L2):
     // first pair, frame count, first frame, global peak, and the part indices that hold samples [pmin, pmax1)
     int u_pair_off = 0, u_nframes = 0, u_pmin = 0, u_pmax1 = 0;
@@ -315,7 +346,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
             staged_next = true; \
             if (li + 1 < it_end) { \
                 if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); } \
-                pos_next = pb_stage_pair<GT>(pcm, units[u_next], pairpos[item + 1], gm, span_lo, span_len, pre, g, mbar); \
+                pos_next = pb_stage_pair<GT>(pcm, units, u_next, pairpos[item + 1], gm.pcm_len, span_lo, span_len, pre, g, mbar); \
             } } while (0)
 
         // ---- two FFTs x two passes through ONE copy of the butterfly code: FFT (step >> 1), pass (step & 1).  The step

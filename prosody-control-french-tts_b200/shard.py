@@ -40,12 +40,14 @@ def row_counts(n_local: int, device) -> list[int]:
     return [int(v) for v in sizes.tolist()]
 
 
-def gather_rows(rows, index=None, dst: int = 0, sizes: list[int] | None = None, order=None):
+def gather_rows(rows, index=None, dst: int = 0, sizes: list[int] | None = None, order=None, perm=None, out=None):
     """Ragged gather of [n_r, k] float64 rows from every rank onto `dst`: every rank sends exactly its rows (point-to-point, true
     counts — nothing is padded to the largest shard), `dst` receives them rank by rank.  Global order: either `order`, the global
     row id of every gathered row in rank-major order, which `dst` can compute itself when the partition is deterministic (no ids
-    travel at all), or `index`, this rank's int64 ids, which then travel as their own int64 message.  Returns the rows in global
-    order on dst (None elsewhere).  Works for gloo (CPU tensors) and NCCL (CUDA tensors)."""
+    travel at all), or `index`, this rank's int64 ids, which then travel as their own int64 message; or `perm`, a precomputed
+    index tensor on the rows' device (rank-major position of every global row: the order worked out once for shards that do not
+    change).  Returns the rows in global order on dst (None elsewhere): a CPU tensor, or — when `out` (a pinned CPU tensor of the
+    full size) is given — `out`, filled by an asynchronous copy the caller synchronises.  Works for gloo and NCCL."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -84,6 +86,11 @@ def gather_rows(rows, index=None, dst: int = 0, sizes: list[int] | None = None, 
         ids = torch.cat(idp, 0)
     # rows come sorted per rank; only an interleaved partition needs the global sort (done where the data lives: on the GPU
     # for NCCL, where a 5e5-row argsort is microseconds instead of the tens of milliseconds of a single host thread)
-    if ids is not None and ids.numel() > 1 and not bool((ids[1:] >= ids[:-1]).all()):
+    if perm is not None:
+        allr = allr.index_select(0, perm)
+    elif ids is not None and ids.numel() > 1 and not bool((ids[1:] >= ids[:-1]).all()):
         allr = allr[torch.argsort(ids, stable=True)]
+    if out is not None:
+        out.copy_(allr, non_blocking=True)
+        return out
     return allr.cpu()
