@@ -261,7 +261,7 @@ def bench_steps(args, rank, world, local):
     torch.cuda.synchronize()
     F = max(1, args.in_flight)
     exs = [pb.Extractor(local) for _ in range(F)]
-    names = [segs[i].name for i in pl.syn_seg] if cfg == "c3" else None
+    pools = SSML.TextPools([segs[i].name for i in pl.syn_seg], pl.syn_words) if cfg == "c3" else None
     # the shards are fixed for the whole run: their row counts (and, for the interleaved c5 partition, the global order of the
     # gathered rows) are exchanged once, not in every step
     row_sizes, perm = None, None
@@ -279,9 +279,9 @@ def bench_steps(args, rank, world, local):
 
     def finish_step(ex):
         out = S.collect(ex, pl, prosody)
-        if names is not None:            # c3: full SSML-delta output, the three CSV tables built as strings every step
-            out["ssml"] = SSML.build(names, pl.syn_words, pl.syn_pause_ms, out["sm_pitch"], out["sm_rate"], out["raw_volume"], "fr-FR-HenriNeural",
-                                     prosody["inter_syntagme_pause_factor"])
+        if pools is not None:            # c3: full SSML-delta output, the three CSV tables built (as bytes, natively) every step
+            out["ssml"] = SSML.build_csv_bytes(pools, pl.syn_pause_ms, out["sm_pitch"], out["sm_rate"], out["raw_volume"], "fr-FR-HenriNeural",
+                                               prosody["inter_syntagme_pause_factor"], lib=ex._lib)
         if world > 1:
             # final gather of the per-syntagme results on rank 0 (the path's only exchange): ragged, true counts, no ids on the wire
             rows = torch.from_numpy(np.stack([out["raw_pitch"], out["raw_volume"], out["raw_rate"], out["sm_pitch"], out["sm_rate"]], 1)).to(dev)

@@ -249,6 +249,17 @@ int pb_textgrid_copy(const PbTextGridBatch* b, int32_t* status, double* xmin, do
                      double* tmin, double* tmax, int64_t* mark_off, char* marks);
 void pb_textgrid_free(PbTextGridBatch* b);
 
+/* ---- SSML emitters + CSV tables at corpus scale (host only, no handle): Code/audioPipeline.py:604-711.
+ * One row per syntagme: segment name and text as UTF-8 pools with n+1 offsets, pause in ms, the three percentages the emitters print
+ * with '{x:+.2f}%'.  Produces the exact bytes pandas.DataFrame(rows).to_csv(path, index=False) writes for BDD_ssml.csv (one row per
+ * segment, in order of first appearance), BDD_syntagme_ssml.csv and BDD_syntagme_for_synth.csv, as malloc'ed buffers the caller
+ * releases with pb_ssml_free.  pause_factor = inter_syntagme_pause_factor; n_threads <= 0: up to 16 host threads. */
+int pb_ssml_csv(int64_t n, const char* seg_names, const int64_t* seg_off, const char* texts, const int64_t* text_off,
+                const int32_t* pause_ms, const double* pitch, const double* rate, const double* volume, double pause_factor,
+                const char* voice, int n_threads, char** csv_final, int64_t* n_final, char** csv_syntagme, int64_t* n_syntagme,
+                char** csv_synth, int64_t* n_synth);
+void pb_ssml_free(char* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,7 +53,7 @@ EXPORTS = ["pb_syntagme_deltas", "pb_ema_clamp", "pb_abi_version", "pb_create", 
            "pb_part_duration_batch", "pb_extract_batch", "pb_intensity_plan", "pb_intensity_batch", "pb_legacy_loudness_batch", "pb_split_on_silence_bound",
            "pb_split_on_silence_batch", "pb_segment_baselines", "pb_textgrid_parse_files",
            "pb_textgrid_sizes", "pb_textgrid_copy", "pb_textgrid_free", "pb_pitch_frame_times", "pb_reduce_intervals",
-           "pb_extract_submit", "pb_extract_wait"]
+           "pb_extract_submit", "pb_extract_wait", "pb_ssml_csv", "pb_ssml_free"]
 
 
 def bind(lib: C.CDLL) -> C.CDLL:
@@ -74,6 +74,9 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.pb_extract_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, P, u8p, u8p, dp, i32p, i32p, dp, dp, i32p]
     lib.pb_extract_submit.argtypes = [vp, vp, C.c_int64, C.c_int, U, P, u8p, u8p, dp, i32p, i32p, dp, dp, i32p]
     lib.pb_extract_wait.argtypes = [vp]
+    lib.pb_ssml_csv.argtypes = [C.c_int64, C.c_char_p, i64p, C.c_char_p, i64p, i32p, dp, dp, dp, C.c_double, C.c_char_p, C.c_int,
+                                C.POINTER(vp), i64p, C.POINTER(vp), i64p, C.POINTER(vp), i64p]
+    lib.pb_ssml_free.argtypes = [vp]; lib.pb_ssml_free.restype = None
     lib.pb_intensity_plan.argtypes = [U, C.c_double, C.c_double, i32p, i32p, i64p, dp, dp]
     lib.pb_intensity_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, C.c_double, C.c_double, C.c_int, fp, i32p]
     lib.pb_legacy_loudness_batch.argtypes = [vp, vp, C.c_int64, C.c_int, U, dp, i64p, i64p]

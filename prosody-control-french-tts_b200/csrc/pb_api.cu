@@ -27,6 +27,7 @@ __global__ void pb_copy16_kernel(const int4* __restrict__ src, int4* __restrict_
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -1120,5 +1121,6 @@ int pb_extract_wait(PbHandle* h) {
 #include "pb_api_next.inc"
 #include "pb_api_silence.inc"
 #include "pb_textgrid.inc"
+#include "pb_ssml.inc"
 
 }  // extern "C"

@@ -140,6 +140,7 @@ __device__ PB_NOINLINE int pb_candidates_overflow(const float* __restrict__ r, f
                     }
                     if (sq - gm.octave_cost * log2f(gm.min_pitch / fq) > ls) place = li;
                 }
+                __syncwarp();                               // every lane has read its slot before lane 0 overwrites one
                 if (place && lane == 0) { cf[place] = fq; cs[place] = sq; imax[place] = iq; }
                 __syncwarp();
             }

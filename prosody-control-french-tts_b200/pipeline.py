@@ -147,9 +147,11 @@ def measure_prosody_and_build_ssml(self, extractor: Extractor | None = None, pos
     pl = S.plan(segs, prosody, pos_of)
     out = S.measure(ex, pcm, pl, prosody)
     names = [segs[i].name for i in pl.syn_seg]
-    final, syn_rows, synth_rows = SSML.build(names, pl.syn_words, pl.syn_pause_ms, out["sm_pitch"], out["sm_rate"],
-                                             out["raw_volume"], self.azure_voice, self.inter_syntagme_pause_factor)
-    SSML.write_csvs(final, syn_rows, synth_rows, self.bdd_ssml_csv, self.bdd_syntagme_ssml_csv, self.bdd_syntagme_synth_csv)
+    # the three tables, formatted natively into the bytes pandas' to_csv(index=False) would write for the Python emitters' rows
+    # (ssml.build / ssml.write_csvs: same output, tests/test_ssml_pipeline.py), which matters once a voice has 10^5 rows
+    tables = SSML.build_csv_bytes(SSML.TextPools(names, pl.syn_words), pl.syn_pause_ms, out["sm_pitch"], out["sm_rate"], out["raw_volume"],
+                                  self.azure_voice, self.inter_syntagme_pause_factor, lib=ex._lib)
+    SSML.write_csv_bytes(tables, self.bdd_ssml_csv, self.bdd_syntagme_ssml_csv, self.bdd_syntagme_synth_csv)
     return out
 
 

@@ -54,3 +54,53 @@ def write_csvs(final, syn_rows, synth_rows, bdd_ssml_csv, bdd_syntagme_ssml_csv,
     for rows, path in ((final, bdd_ssml_csv), (syn_rows, bdd_syntagme_ssml_csv), (synth_rows, bdd_syntagme_synth_csv)):
         Path(path).parent.mkdir(parents=True, exist_ok=True)
         pd.DataFrame(rows).to_csv(path, index=False)
+
+
+def _pool(strings):
+    """-> (UTF-8 bytes of all strings back to back, int64 offsets [n + 1])"""
+    import numpy as np
+    enc = [s.encode("utf-8") for s in strings]
+    off = np.zeros(len(enc) + 1, np.int64)
+    np.cumsum([len(e) for e in enc], out=off[1:])
+    return b"".join(enc), off
+
+
+class TextPools:
+    """The per-row strings of a plan (segment names, syntagme texts) packed once: they do not change from step to step."""
+
+    def __init__(self, segment_names: Sequence[str], words: Sequence[str]):
+        self.n = len(words)
+        self.seg, self.seg_off = _pool(segment_names)
+        self.txt, self.txt_off = _pool(words)
+
+
+def build_csv_bytes(pools: TextPools, pauses, sm_pitch, sm_rate, raw_volume, voice: str, factor=1, lib=None, n_threads: int = 0):
+    """The three CSV tables as bytes — what write_csvs(build(...)) puts on disk — formatted natively (pb_ssml_csv) on host threads.
+    -> (BDD_ssml.csv, BDD_syntagme_ssml.csv, BDD_syntagme_for_synth.csv)"""
+    import ctypes as C
+    import numpy as np
+    from . import _native as N
+    lib = lib if lib is not None else N.load()
+    n = pools.n
+    pa = np.ascontiguousarray(pauses, np.int32); p = np.ascontiguousarray(sm_pitch, np.float64)
+    r = np.ascontiguousarray(sm_rate, np.float64); v = np.ascontiguousarray(raw_volume, np.float64)
+    if not (len(pa) == len(p) == len(r) == len(v) == n):
+        raise ValueError("row arrays must have one entry per syntagme")
+    outs = [C.c_void_p() for _ in range(3)]; lens = [C.c_int64() for _ in range(3)]
+    i64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    dbl = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = lib.pb_ssml_csv(n, pools.seg, i64(pools.seg_off), pools.txt, i64(pools.txt_off), pa.ctypes.data_as(C.POINTER(C.c_int32)), dbl(p), dbl(r), dbl(v),
+                         float(factor), voice.encode("utf-8"), int(n_threads), C.byref(outs[0]), C.byref(lens[0]), C.byref(outs[1]), C.byref(lens[1]),
+                         C.byref(outs[2]), C.byref(lens[2]))
+    N.check(lib, None, rc, "pb_ssml_csv")
+    try:
+        return tuple(C.string_at(o, l.value) for o, l in zip(outs, lens))
+    finally:
+        for o in outs:
+            lib.pb_ssml_free(o)
+
+
+def write_csv_bytes(tables, bdd_ssml_csv, bdd_syntagme_ssml_csv, bdd_syntagme_synth_csv) -> None:
+    for data, path in zip(tables, (bdd_ssml_csv, bdd_syntagme_ssml_csv, bdd_syntagme_synth_csv)):
+        Path(path).parent.mkdir(parents=True, exist_ok=True)
+        Path(path).write_bytes(data)

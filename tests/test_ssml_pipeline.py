@@ -90,3 +90,31 @@ def test_file_level_dropin_writes_the_reference_csvs(tmp_path, emu_lib, oracle):
             assert gr == wr and gv == wv                                 # float64 paths: identical strings
             assert abs(float(gp) - float(wp)) <= 0.02                    # pitch carries the FP32 F0 (documented rounding boundary)
     assert [strip(s) for s in got_seg["ssml"]] == [strip(r["ssml"]) for r in ref["bdd_ssml"]]
+
+
+def test_native_csv_tables_equal_the_pandas_writer_byte_for_byte(tmp_path, native_lib):
+    """pb_ssml_csv: the three tables formatted natively are the bytes pandas.DataFrame(rows).to_csv(index=False) writes for the
+    Python emitters' rows (which are checked against the oracle's restatement of audioPipeline.py:604-711 above) — incl. XML
+    escapes, CSV quoting of commas / quotes / line breaks, non-ASCII text, the .2f lattice (-0.00, ties), NaN / inf, break tags
+    on both sides of the 50 ms threshold and after sentence-final punctuation, a fractional pause factor, and a segment name that
+    comes back after another one."""
+    from prosody_b200 import ssml as SSML
+    rng = np.random.default_rng(11)
+    texts = ["Bonjour le monde.", "", 'il <dit> & "rit", puis', "fin!", "", "d'accord", "garçon naïf à l'école?", "ligne\nbrisée", "x,y", "ça va ?"]
+    names, words, pauses = [], [], []
+    for k in range(400):
+        t = texts[k % len(texts)]
+        names.append(f"segment_ph{1 + (k // 9) % 17}"); words.append(t); pauses.append(0 if t else int(rng.integers(0, 900)))
+    pauses[0] = 300; pauses[3] = 49; pauses[13] = 50; pauses[6] = 777
+    p = rng.normal(0, 8, 400); r = rng.normal(0, 10, 400); v = np.clip(rng.normal(0, 6, 400), -7, 7)
+    p[5] = -0.0; r[6] = 0.004999; v[7] = 12.345; p[8] = 0.005; p[9] = 0.015; p[10] = -0.025; r[11] = 1e-9; p[12] = float("nan"); r[12] = float("inf"); v[12] = -float("inf")
+    p[13] = 123456.789; r[14] = -0.004999999
+    for factor in (1, 0.5, 1.7):
+        final, syn_rows, synth_rows = SSML.build(names, words, pauses, p, r, v, "fr-FR-HenriNeural", factor)
+        SSML.write_csvs(final, syn_rows, synth_rows, tmp_path / "a.csv", tmp_path / "b.csv", tmp_path / "c.csv")
+        got = SSML.build_csv_bytes(SSML.TextPools(names, words), pauses, p, r, v, "fr-FR-HenriNeural", factor, lib=native_lib)
+        for g, f in zip(got, ("a.csv", "b.csv", "c.csv")):
+            assert g == (tmp_path / f).read_bytes(), (factor, f)
+    # empty input: headers only would need a frame with columns; the reference never gets here (KeyError on the empty frame, :593)
+    one = SSML.build_csv_bytes(SSML.TextPools(["s"], ["mot"]), [0], [1.0], [2.0], [3.0], "v", 1, lib=native_lib)
+    assert one[0].startswith(b"segment,ssml\ns,") and one[1].count(b"\n") == 2
