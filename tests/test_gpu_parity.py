@@ -282,7 +282,8 @@ def test_step_24k_mfa_style_full_ssml(gpu_extractor, oracle):
     assert pl.syn_words == [r_["syntagme"] for r_ in ref["raw_rows"]]
     np.testing.assert_allclose(out["raw_volume"], [r_["raw_volume"] for r_ in ref["raw_rows"]], atol=1e-9)
     np.testing.assert_allclose(out["raw_rate"], [r_["raw_rate"] for r_ in ref["raw_rows"]], atol=1e-12)
-    np.testing.assert_allclose(out["raw_pitch"], [r_["raw_pitch"] for r_ in ref["raw_rows"]], atol=0.6)
+    # pitch carries the float32 F0 (median error p50 3e-6 / p99 2.5e-5 relative on the bench corpus, profiles/r02_flips_c2.json)
+    np.testing.assert_allclose(out["raw_pitch"], [r_["raw_pitch"] for r_ in ref["raw_rows"]], atol=0.02)
     names = [segs[i].name for i in pl.syn_seg]
     final, syn_rows, synth_rows = SSML.build(names, pl.syn_words, pl.syn_pause_ms, out["sm_pitch"], out["sm_rate"], out["raw_volume"], "fr-FR-HenriNeural", 1)
     num = re.compile(r'pitch="([+-][\d.]+)%" rate="([+-][\d.]+)%" volume="([+-][\d.]+)%"')
@@ -291,9 +292,11 @@ def test_step_24k_mfa_style_full_ssml(gpu_extractor, oracle):
         assert num.sub("P", g["ssml"]) == num.sub("P", w["ssml"])
         (gp, gr, gv), (wp, wr, wv) = num.search(g["ssml"]).groups(), num.search(w["ssml"]).groups()
         assert gr == wr and gv == wv
-        assert abs(float(gp) - float(wp)) <= 0.02
+        assert abs(float(gp) - float(wp)) <= 0.0101                    # at most one step of the .2f lattice
         same_pitch += gp == wp
-    assert same_pitch >= 0.8 * len(syn_rows)          # identical except at the documented .2f rounding boundaries
+    # identical except at the documented .2f rounding boundaries: measured flip rate 0.3 - 0.6 % (C3, C2 in full); a handful of
+    # rows here, so allow two
+    assert same_pitch >= len(syn_rows) - 2, (same_pitch, len(syn_rows))
 
 
 # ------------------------------------------------------------------ the "next" rows of SURVEY.md §8(f)
