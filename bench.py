@@ -264,9 +264,16 @@ def bench_steps(args, rank, world, local):
     pools = SSML.TextPools([segs[i].name for i in pl.syn_seg], pl.syn_words) if cfg == "c3" else None
     # the shards are fixed for the whole run: their row counts (and, for the interleaved c5 partition, the global order of the
     # gathered rows) are exchanged once, not in every step
-    row_sizes, perm = None, None
+    # The rows of a step are computed on the HOST (float64 baselines / deltas / EMA), so the gather runs over a gloo group: pushing
+    # them to the GPU for a NCCL send would queue a NCCL kernel behind the persistent pitch kernels that hold every SM for tens of
+    # milliseconds (round-2 measurement: that wait was the weak-scaling loss, 41.9 -> 46.8 ms per step at 8 GPUs).  NCCL stays for
+    # what lives on the GPUs: the barriers and the timing reductions.  PB_BENCH_GATHER=nccl switches back.
+    row_sizes, perm, ggroup = None, None, None
+    use_nccl_gather = os.environ.get("PB_BENCH_GATHER", "gloo") == "nccl"
+    gdev = dev if use_nccl_gather else torch.device("cpu")
     if world > 1:
-        row_sizes = shard.row_counts(pl.n_syn, dev)
+        ggroup = None if use_nccl_gather else dist.new_group(backend="gloo")
+        row_sizes = shard.row_counts(pl.n_syn, gdev, ggroup)
         if strong:
             gid = np.asarray(wl.extra["global_ids"], np.int64)[pl.syn_seg]
             first = np.concatenate([[0], np.cumsum(np.bincount(pl.syn_seg, minlength=pl.n_seg))])
@@ -274,8 +281,8 @@ def bench_steps(args, rank, world, local):
             gathered = [None] * world if rank == 0 else None
             dist.gather_object(keys, gathered, dst=0)
             if rank == 0:
-                perm = torch.from_numpy(np.argsort(np.concatenate(gathered), kind="stable")).to(dev)
-    gathered_host = torch.empty(sum(row_sizes), 5, dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0) else None
+                perm = torch.from_numpy(np.argsort(np.concatenate(gathered), kind="stable")).to(gdev)
+    gathered_host = torch.empty(sum(row_sizes), 5, dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0 and use_nccl_gather) else None
 
     def finish_step(ex):
         out = S.collect(ex, pl, prosody)
@@ -284,10 +291,9 @@ def bench_steps(args, rank, world, local):
                                                prosody["inter_syntagme_pause_factor"], lib=ex._lib)
         if world > 1:
             # final gather of the per-syntagme results on rank 0 (the path's only exchange): ragged, true counts, no ids on the wire
-            rows = torch.from_numpy(np.stack([out["raw_pitch"], out["raw_volume"], out["raw_rate"], out["sm_pitch"], out["sm_rate"]], 1)).to(dev)
-            # (rank 0 puts them in global order on its GPU and copies them to pinned memory asynchronously: the copy is waited for by the
-            # synchronize that closes the timed region, not by every step)
-            g = shard.gather_rows(rows, None, dst=0, sizes=row_sizes, perm=perm, out=gathered_host)
+            rows = torch.from_numpy(np.stack([out["raw_pitch"], out["raw_volume"], out["raw_rate"], out["sm_pitch"], out["sm_rate"]], 1)).to(gdev)
+            # (rank 0 puts them in global order with a permutation worked out once)
+            g = shard.gather_rows(rows, None, dst=0, sizes=row_sizes, perm=perm, out=gathered_host, group=ggroup)
             if rank == 0:
                 out["gathered"] = g
                 assert g.shape == (sum(row_sizes), 5)

@@ -28,41 +28,43 @@ def partition_by_cost(costs: Sequence[float], world: int) -> list[list[int]]:
     return [sorted(np.nonzero(owner == r)[0].tolist()) for r in range(world)]
 
 
-def row_counts(n_local: int, device) -> list[int]:
+def row_counts(n_local: int, device, group=None) -> list[int]:
     """Row count of every rank (ONE all_gather_into_tensor).  A caller whose shards do not change from step to step exchanges them
     once and passes them to gather_rows, which then needs no size exchange and no host synchronisation on the sending ranks."""
     import torch
     import torch.distributed as dist
-    world = dist.get_world_size()
+    world = dist.get_world_size(group)
     mine = torch.tensor([n_local], dtype=torch.int64, device=device)
     sizes = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(sizes, mine)
+    dist.all_gather_into_tensor(sizes, mine, group=group)
     return [int(v) for v in sizes.tolist()]
 
 
-def gather_rows(rows, index=None, dst: int = 0, sizes: list[int] | None = None, order=None, perm=None, out=None):
+def gather_rows(rows, index=None, dst: int = 0, sizes: list[int] | None = None, order=None, perm=None, out=None, group=None):
     """Ragged gather of [n_r, k] float64 rows from every rank onto `dst`: every rank sends exactly its rows (point-to-point, true
     counts — nothing is padded to the largest shard), `dst` receives them rank by rank.  Global order: either `order`, the global
     row id of every gathered row in rank-major order, which `dst` can compute itself when the partition is deterministic (no ids
     travel at all), or `index`, this rank's int64 ids, which then travel as their own int64 message; or `perm`, a precomputed
     index tensor on the rows' device (rank-major position of every global row: the order worked out once for shards that do not
     change).  Returns the rows in global order on dst (None elsewhere): a CPU tensor, or — when `out` (a pinned CPU tensor of the
-    full size) is given — `out`, filled by an asynchronous copy the caller synchronises.  Works for gloo and NCCL."""
+    full size) is given — `out`, filled by an asynchronous copy the caller synchronises.  Works for gloo and NCCL; `group` selects
+    the process group (the rows of the step are computed on the host: a gloo group moves them without touching the GPUs, whose
+    SMs are held by persistent kernels that a NCCL send / receive kernel would have to wait for)."""
     import torch
     import torch.distributed as dist
-    world, rank = dist.get_world_size(), dist.get_rank()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = rows.device
     k = rows.shape[1]
     if sizes is None:
-        sizes = row_counts(rows.shape[0], dev)
+        sizes = row_counts(rows.shape[0], dev, group)
     rows = rows.contiguous()
     send_ids = index is not None and order is None
     if rank != dst:
         ops = []
         if rows.shape[0]:
-            ops.append(dist.P2POp(dist.isend, rows, dst))
+            ops.append(dist.P2POp(dist.isend, rows, dst, group))
             if send_ids:
-                ops.append(dist.P2POp(dist.isend, index.to(torch.int64).contiguous(), dst))
+                ops.append(dist.P2POp(dist.isend, index.to(torch.int64).contiguous(), dst, group))
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
@@ -72,9 +74,9 @@ def gather_rows(rows, index=None, dst: int = 0, sizes: list[int] | None = None, 
     ops = []
     for r in range(world):
         if r != dst and sizes[r]:
-            ops.append(dist.P2POp(dist.irecv, parts[r], r))
+            ops.append(dist.P2POp(dist.irecv, parts[r], r, group))
             if send_ids:
-                ops.append(dist.P2POp(dist.irecv, idp[r], r))
+                ops.append(dist.P2POp(dist.irecv, idp[r], r, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
