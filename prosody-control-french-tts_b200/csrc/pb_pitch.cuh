@@ -20,6 +20,10 @@
 #ifndef PB_WPC
 #define PB_WPC 4            // warps per CTA of the frames kernel (when one group needs fewer)
 #endif
+#ifndef PB_BIG_WARPS
+#define PB_BIG_WARPS 16      // resident warps per SM the multi-warp-group FFT sizes (N >= 2048) are compiled for: 128 registers, no spills;
+                             // measured at 8 / 12 / 16 warps: 5.07 / 4.22 / 3.94 ms (N = 2048), 10.46 / 8.54 / 7.98 ms (N = 4096) for 599 k frames
+#endif
 #define PB_MAXC 32           // hard cap on candidates per frame (Praat default 15)
 #define PB_PI_F 3.14159265358979323846f
 
@@ -166,7 +170,7 @@ template <int LOG2N> struct PbFftCfg {
     static constexpr int GROUPS_PER_CTA = WARPS_PER_CTA / G;
     static constexpr int FB = F > 1 ? (N / F) / GT : 0;   // final-pass butterflies per thread
     static constexpr int RPL = (N / 3 + 2 + GT - 1) / GT + 1;   // lags per thread when extracting r
-    static constexpr int MIN_CTAS = LOG2N <= 10 ? 16 / WARPS_PER_CTA : (8 / WARPS_PER_CTA > 0 ? 8 / WARPS_PER_CTA : 1);   // occupancy target: 128 registers, no spills (a fifth CTA at 96 registers measured no faster)
+    static constexpr int MIN_CTAS = LOG2N <= 10 ? 16 / WARPS_PER_CTA : (PB_BIG_WARPS / WARPS_PER_CTA > 0 ? PB_BIG_WARPS / WARPS_PER_CTA : 1);   // occupancy target: 128 registers, no spills (a fifth CTA at 96 registers measured no faster)
 };
 
 template <int G> __device__ __forceinline__ void pb_group_sync(int bar_id) {

@@ -8,7 +8,7 @@ import prosody_b200 as pb
 from prosody_b200 import synth
 
 n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
-sr, dur = 16000, 5.0
+sr, dur = int(os.environ.get("PB_PROBE_SR", 16000)), float(os.environ.get("PB_PROBE_DUR", 5.0))
 pcm = synth.make_corpus(n_utt, dur, sr, seed=1234, device="cuda")
 n = pcm.shape[1]
 units = pb.Units.from_list([(i * n, n, sr, 0.0, None, float(sr)) for i in range(n_utt)])
