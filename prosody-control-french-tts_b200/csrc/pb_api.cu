@@ -126,6 +126,9 @@ struct PbHandle {
     // device buffers (grow on demand)
     DevBuf pcm, units, pair_off, cand_f, cand_s, ncand, inten, psi, sel_f, sel_s, med, nvoiced;
     DevBuf lunits, meters, lstate, lenergy, lufs, pairpos;
+    DevBuf path_longs, path_jobs, path_ctr, path_T, path_D, path_maps, path_exits;   // K3, long chains (blocked path finder)
+    DevBuf stats_longs, stats_ctr;                                                    // K0, long units
+    DevBuf lufs_longs, lufs_jobs, lufs_ctr, lufs_P, lufs_Z, lufs_S;                   // K4, long units
     DevBuf racf, slot_fr, work_ctr;                        // K1 -> K2: autocorrelations of one launch chunk, slot -> frame map, K2's chunk counter
     size_t cand_smem = 0; int cand_per_sm = 1;             // K2: footprint its function attribute was set for, resident CTAs per SM
     HostBuf stage_units, stage_pairs, stage_lunits, stage_meters, stage_out;
@@ -529,8 +532,17 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
 // Enqueue the F0 path for the caller units `ids` (all planned OK). Frame arrays are reused by every launch group:
 // launches are stream-ordered, and per-frame values are only read back when there is a single segment.
 // Results land in h->med / h->nvoiced (device, caller-indexed).
-struct PitchLaunch { int cls; size_t uoff, poff, m; int64_t pairs; };
-struct LufsLaunch { size_t off, m; int64_t chunks; };
+struct PitchLaunch { int cls; size_t uoff, poff, m; int64_t pairs; int64_t long_units = 0, long_blocks = 0, long_stats = 0; };
+// K0: units with more samples than this are reduced piecewise by the whole grid (pb_pitch.cuh)
+long long stats_long_nx() { const char* e = getenv("PB_STATS_LONG"); const long long x = e ? atoll(e) : 0; return x > 0 ? x : (1LL << 22); }
+// K3: units with more frames than this are cut into blocks of path_block_len() frames (pb_pitch_path.cuh, "long chains")
+// (read at every call: the tests switch them)
+int path_long_thresh() { const char* e = getenv("PB_PATH_LONG"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 8192; }
+int path_block_len() { const char* e = getenv("PB_PATH_BLOCK"); const int x = e ? atoi(e) : 0; return x >= 2 && x <= PB_PATHL_BLOCK_MAX ? x : PB_PATHL_BLOCK_MAX; }
+struct LufsLaunch { size_t off, m; int64_t chunks; int64_t long_units = 0, long_groups = 0; };
+// K4: units with more 100 ms chunks than this go through the long-unit kernels, their chain cut into groups (pb_lufs.cuh, "long units")
+int lufs_long_chunks() { const char* e = getenv("PB_LUFS_LONG"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 4096; }
+int lufs_group_len() { const char* e = getenv("PB_LUFS_GROUP"); const int x = e ? atoi(e) : 0; return x >= 1 && x <= 4096 ? x : 64; }
 
 // Fill the pinned descriptor staging for the caller units `ids` (all planned OK), one launch group per geometry class.
 int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::vector<int64_t>& ids,
@@ -552,7 +564,7 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
         PbUnitDev* su = (PbUnitDev*)h->stage_units.p + h->su_off;
         int32_t* sp = (int32_t*)h->stage_pairs.p + h->sp_off;
         // running pair / frame offsets first (sequential, two adds per unit), then the 80-byte descriptors in parallel
-        int64_t pairs = 0;
+        int64_t pairs = 0, n_long = 0, n_long_blocks = 0, n_long_stats = 0;
         std::vector<int64_t>& fbase = h->plan.fbase;
         fbase.resize(m);
         for (size_t k = 0; k < m; k++) {
@@ -560,6 +572,8 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
             sp[k] = (int32_t)pairs; fbase[k] = frame_base;
             pairs += (pl.n_frames + 1) / 2;
             frame_base += pl.n_frames;
+            if (pl.nx > stats_long_nx()) n_long_stats++;
+            if (pl.n_frames > path_long_thresh()) { n_long++; n_long_blocks += (pl.n_frames + path_block_len() - 1) / path_block_len(); }
             if (pairs > 0x7ffffff0LL) return fail(h, PB_EUNSUPPORTED, "%s", "more than 2^31 frame pairs in one launch; split the batch");
         }
         sp[m] = (int32_t)pairs;
@@ -575,6 +589,7 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
             }
         });
         PitchLaunch L; L.cls = (int)ci; L.uoff = h->su_off; L.poff = h->sp_off; L.m = m; L.pairs = pairs;
+        L.long_units = n_long; L.long_blocks = n_long_blocks; L.long_stats = n_long_stats;
         out.push_back(L);
         h->su_off += m; h->sp_off += m + 1;
     }
@@ -618,13 +633,25 @@ int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p
         gm.dx = pc.g.dx; gm.dt = pc.g.dt; gm.ceiling = pc.g.ceiling; gm.silence_threshold = p->silence_threshold;
         gm.voicing_threshold = p->voicing_threshold; gm.octave_cost_d = p->octave_cost; gm.octave_jump_cost = p->octave_jump_cost;
         gm.voiced_unvoiced_cost = p->voiced_unvoiced_cost;
+        gm.path_long = pc.g.max_cand <= 16 ? path_long_thresh() : 0x7fffffff;      // the blocked path finder packs 16 candidates per word
+        gm.path_block = path_block_len();
         gm.window = (const float*)tb->window.p; gm.inv_wr = (const float*)tb->inv_wr.p;
         gm.tw_a = (const float2*)tb->tw_a.p; gm.tw_b = (const float2*)tb->tw_b.p; gm.half_tab = (const float*)tb->half_tab.p;
         {
             ScopedEv ev(h, EV_STATS);
             int grid = (int)std::max<size_t>(1, std::min<size_t>((m + 7) / 8, (size_t)h->sm_count * 8));     // one warp per unit
-            PB_LAUNCH(pb_unit_stats_kernel, dim3(grid), dim3(256), 0, h->stream, d_pcm, du, (int)m);
+            const long long long_nx = stats_long_nx();
+            PB_LAUNCH(pb_unit_stats_kernel, dim3(grid), dim3(256), 0, h->stream, d_pcm, du, (int)m, long_nx);
             h->last.n_launches++;
+            if (L.long_stats > 0) {
+                PB_CKMEM(h->stats_longs.ensure((size_t)L.long_stats * sizeof(PbStatsLong)) || h->stats_ctr.ensure(16), "long unit statistics");
+                PB_CK(pbrt_memset(h->stats_ctr.p, 0, 16, h->stream), "memset");
+                const int g_idx = (int)std::max<size_t>(1, std::min<size_t>((m + 255) / 256, (size_t)h->sm_count));
+                PB_LAUNCH(pb_unit_stats_long_index_kernel, dim3(g_idx), dim3(256), 0, h->stream, (const PbUnitDev*)du, (int)m, long_nx, (PbStatsLong*)h->stats_longs.p, (int*)h->stats_ctr.p);
+                PB_LAUNCH(pb_unit_stats_long_kernel, dim3(h->sm_count * 8), dim3(256), 0, h->stream, d_pcm, (const PbUnitDev*)du, (PbStatsLong*)h->stats_longs.p, (const int*)h->stats_ctr.p);
+                PB_LAUNCH(pb_unit_stats_long_fin_kernel, dim3(1), dim3(256), 0, h->stream, du, (const PbStatsLong*)h->stats_longs.p, (const int*)h->stats_ctr.p);
+                h->last.n_launches += 3;
+            }
         }
         {
             ScopedEv ev(h, EV_FRAMES);
@@ -649,6 +676,37 @@ int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p
                       (const float*)h->cand_s.p, (const uint8_t*)h->ncand.p, (const float*)h->inten.p, (uint8_t*)h->psi.p,
                       (float*)h->sel_f.p, (float*)h->sel_s.p, (double*)h->med.p, (int32_t*)h->nvoiced.p);
             h->last.n_launches++;
+            if (L.long_units > 0 && gm.path_long != 0x7fffffff) {
+                // long chains: blocked (max, +) path finder, see pb_pitch_path.cuh
+                const size_t nl = (size_t)L.long_units, nbk = (size_t)L.long_blocks;
+                PB_CKMEM(h->path_longs.ensure(nl * sizeof(PbLongUnit)) || h->path_jobs.ensure(nbk * sizeof(int2)) || h->path_ctr.ensure(16) ||
+                         h->path_T.ensure(nbk * 256 * sizeof(double)) || h->path_D.ensure(nbk * 16 * sizeof(double)) ||
+                         h->path_maps.ensure(nbk * 8) || h->path_exits.ensure(nbk), "blocked path finder");
+                PB_CK(pbrt_memset(h->path_ctr.p, 0, 16, h->stream), "memset");
+                PbLongUnit* lg = (PbLongUnit*)h->path_longs.p; int2* jb = (int2*)h->path_jobs.p; int* ctr = (int*)h->path_ctr.p;
+                double* T = (double*)h->path_T.p; double* D = (double*)h->path_D.p;
+                unsigned long long* maps = (unsigned long long*)h->path_maps.p; uint8_t* exits = (uint8_t*)h->path_exits.p;
+                const float* cf = (const float*)h->cand_f.p; const float* cs = (const float*)h->cand_s.p;
+                const uint8_t* nc = (const uint8_t*)h->ncand.p; const float* it = (const float*)h->inten.p;
+                const int cap = h->sm_count * 16;
+                const int g_idx = (int)std::max<size_t>(1, std::min<size_t>((m + 255) / 256, (size_t)h->sm_count));
+                const int g_entry = (int)std::max<size_t>(1, std::min<size_t>((8 * nbk + PB_PATHL_WARPS - 1) / PB_PATHL_WARPS, (size_t)cap));
+                const int g_blk = (int)std::max<size_t>(1, std::min<size_t>((nbk + PB_PATHL_WARPS - 1) / PB_PATHL_WARPS, (size_t)cap));
+                const int g_unit = (int)std::max<size_t>(1, std::min<size_t>(nl, (size_t)cap));
+                PB_LAUNCH(pb_path_long_index_kernel, dim3(g_idx), dim3(256), 0, h->stream, (const PbUnitDev*)du, gm, lg, jb, ctr);
+                PB_LAUNCH(pb_path_block_entry_kernel, dim3(g_entry), dim3(PB_PATHL_WARPS * 32), 0, h->stream, (const PbUnitDev*)du, gm, cf, cs, nc, it,
+                          (const PbLongUnit*)lg, (const int2*)jb, (const int*)ctr, T);
+                PB_LAUNCH(pb_path_block_scan_kernel, dim3(g_unit), dim3(32), 0, h->stream, (const PbUnitDev*)du, gm, nc, lg, (const int*)ctr, (const double*)T, D);
+                PB_LAUNCH(pb_path_block_final_kernel, dim3(g_blk), dim3(PB_PATHL_WARPS * 32), 0, h->stream, (const PbUnitDev*)du, gm, cf, cs, nc, it,
+                          (const PbLongUnit*)lg, (const int2*)jb, (const int*)ctr, (const double*)D, (uint8_t*)h->psi.p, maps);
+                PB_LAUNCH(pb_path_block_link_kernel, dim3(g_unit), dim3(32), 0, h->stream, (const PbLongUnit*)lg, (const int*)ctr, (const unsigned long long*)maps, exits);
+                PB_LAUNCH(pb_path_block_select_kernel, dim3(g_blk), dim3(PB_PATHL_WARPS * 32), 0, h->stream, (const PbUnitDev*)du, gm, cf, cs,
+                          (const PbLongUnit*)lg, (const int2*)jb, (const int*)ctr, (const uint8_t*)h->psi.p, (const uint8_t*)exits,
+                          (float*)h->sel_f.p, (float*)h->sel_s.p);
+                PB_LAUNCH(pb_path_median_long_kernel, dim3(g_unit), dim3(1024), 0, h->stream, (const PbUnitDev*)du, (const PbLongUnit*)lg, (const int*)ctr,
+                          (const float*)h->sel_f.p, (double*)h->med.p, (int32_t*)h->nvoiced.p);
+                h->last.n_launches += 7;
+            }
         }
         PB_CK(pbrt_last_error(), "pitch kernels");
     }
@@ -660,7 +718,12 @@ void stage_lufs(PbHandle* h, const BatchPlan& bp, const std::vector<int64_t>& id
     const size_t m = ids.size();
     PbLufsUnitDev* su = (PbLufsUnitDev*)h->stage_lunits.p + h->sl_off;
     int64_t chunks = 0;
-    for (size_t k = 0; k < m; k++) { su[k] = bp.lunits[(size_t)ids[k]]; su[k].chunk_off = chunks; chunks += su[k].n_chunks; }
+    const int long_chunks = lufs_long_chunks(), group = lufs_group_len();
+    L.long_units = 0; L.long_groups = 0;
+    for (size_t k = 0; k < m; k++) {
+        su[k] = bp.lunits[(size_t)ids[k]]; su[k].chunk_off = chunks; chunks += su[k].n_chunks;
+        if (su[k].n_chunks > long_chunks) { L.long_units++; L.long_groups += (su[k].n_chunks + group - 1) / group; }
+    }
     L.off = h->sl_off; L.m = m; L.chunks = chunks;
     h->sl_off += m;
 }
@@ -675,16 +738,47 @@ int launch_lufs_group(PbHandle* h, const int16_t* d_pcm, const LufsLaunch& L, pb
         ScopedEv ev(h, EV_LUFS, stream);
         const PbMeterDev* dm = (const PbMeterDev*)h->meters.p;
         double* st = (double*)h->lstate.p; double* en = (double*)h->lenergy.p;
+        const int long_chunks = lufs_long_chunks(), group = lufs_group_len();
+        const bool has_long = L.long_units > 0;
+        PbLufsLong* lg = nullptr; int2* jb = nullptr; int* ctr = nullptr; double* P = nullptr; double* Z = nullptr; double* S = nullptr;
+        int g_long = 1, g_grp = 1;
+        if (has_long) {
+            const size_t nl = (size_t)L.long_units, ng = (size_t)L.long_groups;
+            PB_CKMEM(h->lufs_longs.ensure(nl * sizeof(PbLufsLong)) || h->lufs_jobs.ensure(ng * sizeof(int2)) || h->lufs_ctr.ensure(16) ||
+                     h->lufs_P.ensure(ng * 16 * 8) || h->lufs_Z.ensure(ng * 4 * 8) || h->lufs_S.ensure(ng * 4 * 8), "long loudness units");
+            lg = (PbLufsLong*)h->lufs_longs.p; jb = (int2*)h->lufs_jobs.p; ctr = (int*)h->lufs_ctr.p;
+            P = (double*)h->lufs_P.p; Z = (double*)h->lufs_Z.p; S = (double*)h->lufs_S.p;
+            g_long = (int)std::min<size_t>(nl, (size_t)h->sm_count * 16);
+            g_grp = (int)std::max<size_t>(1, std::min<size_t>((ng + 31) / 32, (size_t)h->sm_count * 16));
+            PB_CK(pbrt_memset(ctr, 0, 16, stream), "memset");
+            const int g_idx = (int)std::max<size_t>(1, std::min<size_t>((m + 255) / 256, (size_t)h->sm_count));
+            PB_LAUNCH(pb_lufs_long_index_kernel, dim3(g_idx), dim3(256), 0, stream, (const PbLufsUnitDev*)du, (int)m, long_chunks, group, lg, jb, ctr);
+            PB_LAUNCH(pb_lufs_peak_long_kernel, dim3(h->sm_count * 8), dim3(256), 0, stream, d_pcm, (const PbLufsUnitDev*)du, lg, (const int*)ctr);
+            PB_LAUNCH(pb_lufs_peak_fin_kernel, dim3(1), dim3(256), 0, stream, du, (const PbLufsLong*)lg, (const int*)ctr);
+            h->last.n_launches += 3;
+        }
         int g1 = (int)std::max<size_t>(1, std::min<size_t>((m + 7) / 8, (size_t)h->sm_count * 8));           // one warp per unit
-        PB_LAUNCH(pb_lufs_peak_kernel, dim3(g1), dim3(256), 0, stream, d_pcm, du, (int)m);
+        PB_LAUNCH(pb_lufs_peak_kernel, dim3(g1), dim3(256), 0, stream, d_pcm, du, (int)m, long_chunks);
         int gc = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 127) / 128, (int64_t)h->sm_count * 16));
         auto k_state = pb_lufs_chunk_kernel<false>; auto k_energy = pb_lufs_chunk_kernel<true>;
         PB_LAUNCH(k_state, dim3(gc), dim3(128), 0, stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
         int gu = (int)std::max<size_t>(1, std::min<size_t>((m + 127) / 128, (size_t)h->sm_count * 16));
         int gs = (int)std::max<size_t>(1, std::min<size_t>((m + 31) / 32, (size_t)h->sm_count * 16));         // 8 units per warp
-        PB_LAUNCH(pb_lufs_scan_kernel, dim3(gs), dim3(128), 0, stream, (const PbLufsUnitDev*)du, (int)m, dm, st);
+        PB_LAUNCH(pb_lufs_scan_kernel, dim3(gs), dim3(128), 0, stream, (const PbLufsUnitDev*)du, (int)m, dm, st, long_chunks);
+        if (has_long) {
+            auto k_p1 = pb_lufs_scan_group_kernel<1>; auto k_p3 = pb_lufs_scan_group_kernel<3>;
+            PB_LAUNCH(k_p1, dim3(g_grp), dim3(128), 0, stream, (const PbLufsUnitDev*)du, dm, (const PbLufsLong*)lg, (const int2*)jb, (const int*)ctr, group, st, P, Z, (const double*)S);
+            PB_LAUNCH(pb_lufs_scan_link_kernel, dim3(g_long), dim3(32), 0, stream, (const PbLufsLong*)lg, (const int*)ctr, (const double*)P, (const double*)Z, S);
+            PB_LAUNCH(k_p3, dim3(g_grp), dim3(128), 0, stream, (const PbLufsUnitDev*)du, dm, (const PbLufsLong*)lg, (const int2*)jb, (const int*)ctr, group, st, P, Z, (const double*)S);
+            h->last.n_launches += 3;
+        }
         PB_LAUNCH(k_energy, dim3(gc), dim3(128), 0, stream, d_pcm, (const PbLufsUnitDev*)du, (int)m, dm, (long long)chunks, st, en);
-        PB_LAUNCH(pb_lufs_gate_kernel, dim3(gu), dim3(128), 0, stream, (const PbLufsUnitDev*)du, (int)m, dm, (const double*)en, (double*)h->lufs.p);
+        PB_LAUNCH(pb_lufs_gate_kernel, dim3(gu), dim3(128), 0, stream, (const PbLufsUnitDev*)du, (int)m, dm, (const double*)en, (double*)h->lufs.p, long_chunks);
+        if (has_long) {
+            PB_LAUNCH(pb_lufs_gate_long_kernel, dim3(g_long), dim3(256), 0, stream, (const PbLufsUnitDev*)du, (const PbLufsLong*)lg, (const int*)ctr, dm,
+                      (const double*)en, (double*)h->lufs.p);
+            h->last.n_launches++;
+        }
         h->last.n_launches += 5;
     }
     PB_CK(pbrt_last_error(), "lufs kernels");
@@ -1036,7 +1130,7 @@ void pb_destroy(PbHandle* h) {
     pbrt_stream_sync(h->stream);
     pbrt_stream_sync(h->copy_stream);
     pbrt_stream_sync(h->lufs_stream);
-    DevBuf* dbs[] = {&h->pcm, &h->units, &h->pair_off, &h->cand_f, &h->cand_s, &h->ncand, &h->inten, &h->psi, &h->sel_f, &h->sel_s,
+    DevBuf* dbs[] = {&h->pcm, &h->units, &h->pair_off, &h->cand_f, &h->cand_s, &h->ncand, &h->inten, &h->psi, &h->sel_f, &h->sel_s, &h->stats_longs, &h->stats_ctr, &h->lufs_longs, &h->lufs_jobs, &h->lufs_ctr, &h->lufs_P, &h->lufs_Z, &h->lufs_S, &h->path_longs, &h->path_jobs, &h->path_ctr, &h->path_T, &h->path_D, &h->path_maps, &h->path_exits,
                      &h->med, &h->nvoiced, &h->lunits, &h->meters, &h->lstate, &h->lenergy, &h->lufs, &h->pairpos, &h->racf, &h->slot_fr, &h->work_ctr};
     for (auto* b : dbs) b->release();
     HostBuf* hbs[] = {&h->stage_units, &h->stage_pairs, &h->stage_lunits, &h->stage_meters, &h->stage_out};

@@ -47,10 +47,11 @@ __device__ __forceinline__ long long pb_lufs_bound(int c, double rate, long long
 }
 
 // Peak of every unit (the reference divides by max|samples| before metering). One warp per unit, 16-byte loads.
-__global__ void __launch_bounds__(256) pb_lufs_peak_kernel(const int16_t* __restrict__ pcm, PbLufsUnitDev* __restrict__ units, int n_units) {
+__global__ void __launch_bounds__(256) pb_lufs_peak_kernel(const int16_t* __restrict__ pcm, PbLufsUnitDev* __restrict__ units, int n_units, int long_chunks) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int u = blockIdx.x * wpb + (threadIdx.x >> 5); u < n_units; u += gridDim.x * wpb) {
         const PbLufsUnitDev ud = units[u];
+        if (ud.n_chunks > long_chunks) continue;             // long units: pb_lufs_peak_long_kernel
         int mx = 0;
         pb_warp_foreach_s16(pcm + ud.pcm_off, ud.a, ud.b, lane, [&](int v) { mx = max(mx, v < 0 ? -v : v); });
         PB_UNROLL for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(PB_FULL_MASK, mx, o));
@@ -117,11 +118,34 @@ pb_lufs_chunk_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __res
     }
 }
 
+// s <- A^len s for the state whose component r this lane holds (the other three sit in the lanes base_lane .. base_lane + 3).
+// Every lane of the warp must call it (shuffles); `on` = this lane's result is wanted.
+__device__ __forceinline__ double pb_lufs_advance(const PbMeterDev* __restrict__ mt, int len, int r, int base_lane, bool on, double s) {
+    const double s0 = __shfl_sync(PB_FULL_MASK, s, base_lane + 0), s1 = __shfl_sync(PB_FULL_MASK, s, base_lane + 1);
+    const double s2 = __shfl_sync(PB_FULL_MASK, s, base_lane + 2), s3 = __shfl_sync(PB_FULL_MASK, s, base_lane + 3);
+    if (!on) return s;
+    const int k = len - mt->L0;
+    if (k >= 0 && k < PB_LUFS_NM) {
+        const double* M = mt->M[k] + r * 4;
+        return M[0] * s0 + M[1] * s1 + M[2] * s2 + M[3] * s3;
+    }
+    // a chunk clipped by the end of the unit: step the homogeneous recurrence (only empty chunks follow)
+    double a0 = s0, a1 = s1, a2 = s2, a3 = s3;
+    for (int i = 0; i < len; i++) {
+        const double y1 = a0;
+        const double np0 = -mt->a1[1] * y1 + a1, np1 = -mt->a1[2] * y1;
+        const double y2 = mt->b2[0] * y1 + a2;
+        const double nq0 = mt->b2[1] * y1 - mt->a2[1] * y2 + a3, nq1 = mt->b2[2] * y1 - mt->a2[2] * y2;
+        a0 = np0; a1 = np1; a2 = nq0; a3 = nq1;
+    }
+    return r == 0 ? a0 : r == 1 ? a1 : r == 2 ? a2 : a3;
+}
+
 // (2) Per unit: turn the zero-state chunk contributions into true initial states: s_in[c+1] = A^len(c) s_in[c] + s_zs[c].
 // Four lanes per unit (one state component each, the 4x4 product via shuffles), eight units per warp; the chunk
 // contributions are prefetched one chunk ahead so the sequential chain is only the four FMAs.
 __global__ void __launch_bounds__(128)
-pb_lufs_scan_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const PbMeterDev* __restrict__ meters, double* __restrict__ state) {
+pb_lufs_scan_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const PbMeterDev* __restrict__ meters, double* __restrict__ state, int long_chunks) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const int r = lane & 3, slot = lane >> 2, base_lane = lane & ~3;
     for (int ubase = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 8; ubase < n_units; ubase += gridDim.x * wpb * 8) {
@@ -129,12 +153,11 @@ pb_lufs_scan_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const 
         const bool active = u < n_units;
         const PbLufsUnitDev ud = units[active ? u : n_units - 1];
         const PbMeterDev* __restrict__ mt = meters + ud.meter;
-        const int nch = active ? ud.n_chunks : 0;
+        const int nch = (active && ud.n_chunks <= long_chunks) ? ud.n_chunks : 0;      // long units: pb_lufs_scan_long_kernel
         int maxch = nch;
         PB_UNROLL for (int o = 16; o > 0; o >>= 1) maxch = max(maxch, __shfl_xor_sync(PB_FULL_MASK, maxch, o));
         const long long n = (ud.b - ud.a) + ud.npad;
         const double rate = mt->rate;
-        const int L0 = mt->L0;
         double* st = state + ud.chunk_off * 4 + r;
         double s = 0.0;
         double znext = nch > 0 ? st[0] : 0.0;
@@ -147,37 +170,167 @@ pb_lufs_scan_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const 
             const long long hi = pb_lufs_bound(c + 1, rate, n);
             const int len = (int)(hi - lo);
             lo = hi;
-            const double s0 = __shfl_sync(PB_FULL_MASK, s, base_lane + 0), s1 = __shfl_sync(PB_FULL_MASK, s, base_lane + 1);
-            const double s2 = __shfl_sync(PB_FULL_MASK, s, base_lane + 2), s3 = __shfl_sync(PB_FULL_MASK, s, base_lane + 3);
-            if (on) {
-                const int k = len - L0;
-                if (k >= 0 && k < PB_LUFS_NM) {
-                    const double* M = mt->M[k] + r * 4;
-                    s = M[0] * s0 + M[1] * s1 + M[2] * s2 + M[3] * s3;
-                } else {
-                    // a chunk clipped by the end of the unit: step the homogeneous recurrence (only empty chunks follow)
-                    double a0 = s0, a1 = s1, a2 = s2, a3 = s3;
-                    for (int i = 0; i < len; i++) {
-                        const double y1 = a0;
-                        const double np0 = -mt->a1[1] * y1 + a1, np1 = -mt->a1[2] * y1;
-                        const double y2 = mt->b2[0] * y1 + a2;
-                        const double nq0 = mt->b2[1] * y1 - mt->a2[1] * y2 + a3, nq1 = mt->b2[2] * y1 - mt->a2[2] * y2;
-                        a0 = np0; a1 = np1; a2 = nq0; a3 = nq1;
-                    }
-                    s = r == 0 ? a0 : r == 1 ? a1 : r == 2 ? a2 : a3;
-                }
-                s += z;
-            }
+            s = pb_lufs_advance(mt, len, r, base_lane, on, s);
+            if (on) s += z;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4, long units
+// A one-hour recording measured as one unit has 36 000 chunks: one warp finding its peak, four lanes chaining its states and
+// one thread gating its blocks take ~100 ms while the rest of the GPU idles.  Units with more than `long_chunks` chunks go
+// through these instead (the chunk kernels (1) and (3) are chunk-parallel already):
+//   peak:  one warp per 64 Ki-sample piece, atomicMax into an int per long unit;
+//   scan:  the chain of affine maps s -> A^len s + z is cut into groups of `group` chunks; phase 1 composes every group's
+//          map (the matrix by running the four basis vectors through it), phase 2 walks the groups of a unit, phase 3 redoes
+//          every group from its true entering state;
+//   gate:  one CTA per long unit, block sums through a shared-memory tree.
+// The states reach a chunk through a different association of the same float64 products (~1e-13 relative).
+struct PbLufsLong { int unit; int job_off; int n_groups; int peak; };
+
+__global__ void pb_lufs_long_index_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, int long_chunks, int group,
+                                          PbLufsLong* __restrict__ longs, int2* __restrict__ jobs, int* __restrict__ counters) {
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        const int nch = units[u].n_chunks;
+        if (nch <= long_chunks) continue;
+        const int ng = (nch + group - 1) / group;
+        const int li = atomicAdd(&counters[0], 1), j0 = atomicAdd(&counters[1], ng);
+        PbLufsLong lu; lu.unit = u; lu.job_off = j0; lu.n_groups = ng; lu.peak = 0;
+        longs[li] = lu;
+        for (int g = 0; g < ng; g++) jobs[j0 + g] = make_int2(li, g);
+    }
+}
+
+#define PB_LUFS_PEAK_PIECE 65536
+__global__ void __launch_bounds__(256)
+pb_lufs_peak_long_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, PbLufsLong* __restrict__ longs, const int* __restrict__ counters) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int li = 0; li < counters[0]; li++) {
+        const PbLufsUnitDev ud = units[longs[li].unit];
+        const long long pieces = (ud.b - ud.a + PB_LUFS_PEAK_PIECE - 1) / PB_LUFS_PEAK_PIECE;
+        int mx = 0;
+        for (long long pc = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pc < pieces; pc += (long long)gridDim.x * wpb) {
+            const long long lo = ud.a + pc * PB_LUFS_PEAK_PIECE, hi = lo + PB_LUFS_PEAK_PIECE < ud.b ? lo + PB_LUFS_PEAK_PIECE : ud.b;
+            pb_warp_foreach_s16(pcm + ud.pcm_off, lo, hi, lane, [&](int v) { mx = max(mx, v < 0 ? -v : v); });
+        }
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(PB_FULL_MASK, mx, o));
+        if (lane == 0 && mx > 0) atomicMax(&longs[li].peak, mx);
+    }
+}
+__global__ void pb_lufs_peak_fin_kernel(PbLufsUnitDev* __restrict__ units, const PbLufsLong* __restrict__ longs, const int* __restrict__ counters) {
+    for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < counters[0]; li += gridDim.x * blockDim.x) {
+        const int mx = longs[li].peak;
+        units[longs[li].unit].inv_peak = mx > 0 ? 1.0 / (double)mx : 1.0;
+    }
+}
+
+// PHASE 1: the group's map (P: 4x4, column k = image of basis vector k; Z: image of the zero state) from the chunks' zero-state
+// contributions.  PHASE 3: every chunk's true initial state from the group's entering state S.  Four lanes per group, eight per warp.
+template <int PHASE>
+__global__ void __launch_bounds__(128)
+pb_lufs_scan_group_kernel(const PbLufsUnitDev* __restrict__ units, const PbMeterDev* __restrict__ meters, const PbLufsLong* __restrict__ longs,
+                          const int2* __restrict__ jobs, const int* __restrict__ counters, int group, double* __restrict__ state,
+                          double* __restrict__ P, double* __restrict__ Z, const double* __restrict__ S) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int r = lane & 3, slot = lane >> 2, base_lane = lane & ~3;
+    const int n_jobs = counters[1];
+    for (int jbase = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 8; jbase < n_jobs; jbase += gridDim.x * wpb * 8) {
+        const int job = jbase + slot;
+        const bool active = job < n_jobs;
+        const int2 jb = jobs[active ? job : n_jobs - 1];
+        const PbLufsUnitDev ud = units[longs[jb.x].unit];
+        const PbMeterDev* __restrict__ mt = meters + ud.meter;
+        const int c0 = jb.y * group, c1 = min(ud.n_chunks, c0 + group);
+        const long long n = (ud.b - ud.a) + ud.npad;
+        const double rate = mt->rate;
+        double* st = state + ud.chunk_off * 4 + r;
+        double v0 = r == 0 ? 1.0 : 0.0, v1 = r == 1 ? 1.0 : 0.0, v2 = r == 2 ? 1.0 : 0.0, v3 = r == 3 ? 1.0 : 0.0;
+        double s = PHASE == 3 ? S[(size_t)(active ? job : n_jobs - 1) * 4 + r] : 0.0;
+        long long lo = pb_lufs_bound(c0, rate, n);
+        for (int c = c0; c < c0 + group; c++) {           // uniform trip count: every lane takes part in the shuffles
+            const bool on = active && c < c1;
+            const double z = on ? st[(size_t)c * 4] : 0.0;
+            const long long hi = pb_lufs_bound(c + 1, rate, n);
+            const int len = (int)(hi - lo);
+            lo = hi;
+            if (PHASE == 1) {
+                v0 = pb_lufs_advance(mt, len, r, base_lane, on, v0); v1 = pb_lufs_advance(mt, len, r, base_lane, on, v1);
+                v2 = pb_lufs_advance(mt, len, r, base_lane, on, v2); v3 = pb_lufs_advance(mt, len, r, base_lane, on, v3);
+            } else if (on) st[(size_t)c * 4] = s;
+            s = pb_lufs_advance(mt, len, r, base_lane, on, s);
+            if (on) s += z;
+        }
+        if (PHASE == 1 && active) {
+            double* p = P + (size_t)job * 16;
+            p[0 * 4 + r] = v0; p[1 * 4 + r] = v1; p[2 * 4 + r] = v2; p[3 * 4 + r] = v3;
+            Z[(size_t)job * 4 + r] = s;
+        }
+    }
+}
+
+// PHASE 2: entering state of every group, in order: S_{g+1} = P_g S_g + Z_g.  Four lanes per long unit.
+__global__ void __launch_bounds__(32)
+pb_lufs_scan_link_kernel(const PbLufsLong* __restrict__ longs, const int* __restrict__ counters, const double* __restrict__ P,
+                         const double* __restrict__ Z, double* __restrict__ S) {
+    const int lane = threadIdx.x & 31, r = lane & 3;
+    for (int li = blockIdx.x; li < counters[0]; li += gridDim.x) {
+        const PbLufsLong lu = longs[li];
+        double s = 0.0;
+        for (int g = 0; g < lu.n_groups; g++) {
+            const size_t job = (size_t)lu.job_off + g;
+            const double* p = P + job * 16;
+            const double p0 = p[0 * 4 + r], p1 = p[1 * 4 + r], p2 = p[2 * 4 + r], p3 = p[3 * 4 + r], z = Z[job * 4 + r];   // independent of s
+            if (lane < 4) S[job * 4 + r] = s;
+            const double s0 = __shfl_sync(PB_FULL_MASK, s, 0), s1 = __shfl_sync(PB_FULL_MASK, s, 1);
+            const double s2 = __shfl_sync(PB_FULL_MASK, s, 2), s3 = __shfl_sync(PB_FULL_MASK, s, 3);
+            s = p0 * s0 + p1 * s1 + p2 * s2 + p3 * s3 + z;
+        }
+    }
+}
+
+// Gates of a long unit: one CTA, the two passes of pb_lufs_gate_kernel with block-wide sums.
+__global__ void __launch_bounds__(256)
+pb_lufs_gate_long_kernel(const PbLufsUnitDev* __restrict__ units, const PbLufsLong* __restrict__ longs, const int* __restrict__ counters,
+                         const PbMeterDev* __restrict__ meters, const double* __restrict__ energy, double* __restrict__ lufs_out) {
+    __shared__ double s_sum[256];
+    __shared__ int s_cnt[256];
+    const int tid = threadIdx.x;
+    const double NEG_INF = -(double)INFINITY;
+    for (int li = blockIdx.x; li < counters[0]; li += gridDim.x) {
+        const PbLufsUnitDev ud = units[longs[li].unit];
+        const double inv = 1.0 / (0.4 * meters[ud.meter].rate);
+        const double* e = energy + ud.chunk_off;
+        double gamma_r = 0.0, out = NEG_INF;
+        for (int pass = 0; pass < 2; pass++) {
+            double sum = 0.0; int cnt = 0;
+            for (int j = tid; j < ud.n_blocks; j += 256) {
+                const double z = inv * (e[j] + e[j + 1] + e[j + 2] + e[j + 3]);
+                const double l = z > 0.0 ? -0.691 + 10.0 * log10(z) : NEG_INF;
+                if (pass == 0 ? l >= -70.0 : (l > gamma_r && l > -70.0)) { sum += z; cnt++; }
+            }
+            s_sum[tid] = sum; s_cnt[tid] = cnt;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (tid < o) { s_sum[tid] += s_sum[tid + o]; s_cnt[tid] += s_cnt[tid + o]; }
+                __syncthreads();
+            }
+            sum = s_sum[0]; cnt = s_cnt[0];
+            __syncthreads();
+            if (cnt == 0) break;                                       // uniform: every thread read the same totals
+            if (pass == 0) gamma_r = -0.691 + 10.0 * log10(sum / (double)cnt) - 10.0;
+            else { const double za = sum / (double)cnt; out = za > 0.0 ? -0.691 + 10.0 * log10(za) : NEG_INF; }
+        }
+        if (tid == 0) lufs_out[ud.out_index] = out;
     }
 }
 
 // Per unit: block energies from 4 consecutive chunks, the two gates, LUFS (pyloudnorm meter.py).
 __global__ void __launch_bounds__(128)
 pb_lufs_gate_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const PbMeterDev* __restrict__ meters,
-                    const double* __restrict__ energy, double* __restrict__ lufs_out) {
+                    const double* __restrict__ energy, double* __restrict__ lufs_out, int long_chunks) {
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
         const PbLufsUnitDev ud = units[u];
+        if (ud.n_chunks > long_chunks) continue;             // long units: pb_lufs_gate_long_kernel
         const double rate = meters[ud.meter].rate;
         const double inv = 1.0 / (0.4 * rate);
         const double* e = energy + ud.chunk_off;

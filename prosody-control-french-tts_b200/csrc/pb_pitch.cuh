@@ -55,6 +55,8 @@ struct PbPitchGeomDev {
     int min_refine_lag;   // maxima at smaller lags stay above the ceiling whatever the refinement: never voiced
     int pre_cap;          // samples per staging buffer of the cp.async prefetch (multiple of 8)
     int phase_sync;          // 1: the CTA's warps start every work item together (instruction-cache locality)
+    int path_long;        // K3: units with more frames than this go through the blocked path finder (pb_path_block_*_kernel)
+    int path_block;       // K3: frames per block of the blocked path finder (<= PB_PATHL_BLOCK_MAX)
     long long pcm_len;    // samples in the pcm buffer (prefetch copies stay inside it)
     float sr;             // 1/dx
     float half_voicing;   // 0.5 * voicingThreshold
@@ -90,10 +92,11 @@ __device__ __forceinline__ int pb_upper_unit(const int32_t* __restrict__ off, in
 // Per-unit mean and global peak (Praat: globalPeak = max |x - mean| over the whole analysed sound).
 // Integer sum / min / max of the int16 samples are exact, so mean and peak equal the float64 reference's.
 // One warp per unit, 16-byte loads (pb_stream.cuh): the kernel is a pure HBM stream of 2 B/sample.
-__global__ void __launch_bounds__(256) pb_unit_stats_kernel(const int16_t* __restrict__ pcm, PbUnitDev* __restrict__ units, int n_units) {
+__global__ void __launch_bounds__(256) pb_unit_stats_kernel(const int16_t* __restrict__ pcm, PbUnitDev* __restrict__ units, int n_units, long long long_nx) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int u = blockIdx.x * wpb + (threadIdx.x >> 5); u < n_units; u += gridDim.x * wpb) {
         const PbUnitDev ud = units[u];
+        if (ud.nx > long_nx) continue;                 // long units: pb_unit_stats_long_kernel
         // the part of [ix1-1, ix1-1+nx) that lies inside the file
         const long long a = ud.ix1 - 1, b = a + ud.nx;
         const long long lo = a < 0 ? 0 : a, hi = b > ud.file_nx ? ud.file_nx : b;
@@ -113,6 +116,58 @@ __global__ void __launch_bounds__(256) pb_unit_stats_kernel(const int16_t* __res
             units[u].mean = mean;
             units[u].global_peak = p1 > p2 ? p1 : p2;
         }
+    }
+}
+
+// K0 for long units (a one-hour recording analysed as one sound is 79 M samples: one warp would stream it for tens of
+// milliseconds): the units above long_nx samples are listed, every warp of the grid takes 64 Ki-sample pieces of each in turn and
+// merges its exact integer sum / minimum / maximum with atomics, and a last small kernel turns them into mean and global peak.
+struct PbStatsLong { int unit; int mn; int mx; int pad; unsigned long long sum; };
+#define PB_STATS_PIECE 65536
+__global__ void pb_unit_stats_long_index_kernel(const PbUnitDev* __restrict__ units, int n_units, long long long_nx, PbStatsLong* __restrict__ longs, int* __restrict__ counter) {
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        if (units[u].nx <= long_nx) continue;
+        PbStatsLong e; e.unit = u; e.mn = 32767; e.mx = -32768; e.pad = 0; e.sum = 0ull;
+        longs[atomicAdd(counter, 1)] = e;
+    }
+}
+__global__ void __launch_bounds__(256) pb_unit_stats_long_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, PbStatsLong* __restrict__ longs, const int* __restrict__ counter) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int li = 0; li < *counter; li++) {
+        const PbUnitDev ud = units[longs[li].unit];
+        const long long a = ud.ix1 - 1, b = a + ud.nx;
+        const long long lo = a < 0 ? 0 : a, hi = b > ud.file_nx ? ud.file_nx : b;
+        const long long pieces = hi > lo ? (hi - lo + PB_STATS_PIECE - 1) / PB_STATS_PIECE : 0;
+        long long sum = 0; int mn = 32767, mx = -32768;
+        for (long long pc = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pc < pieces; pc += (long long)gridDim.x * wpb) {
+            const long long p0 = lo + pc * PB_STATS_PIECE, p1 = p0 + PB_STATS_PIECE < hi ? p0 + PB_STATS_PIECE : hi;
+            pb_warp_foreach_s16(pcm + ud.pcm_off, p0, p1, lane, [&](int v) { sum += v; mn = min(mn, v); mx = max(mx, v); });
+        }
+        PB_UNROLL for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(PB_FULL_MASK, sum, o);
+            mn = min(mn, __shfl_xor_sync(PB_FULL_MASK, mn, o));
+            mx = max(mx, __shfl_xor_sync(PB_FULL_MASK, mx, o));
+        }
+        if (lane == 0 && mn <= mx) {
+            atomicAdd(&longs[li].sum, (unsigned long long)sum);          // two's complement: wraps to the exact signed total
+            atomicMin(&longs[li].mn, mn); atomicMax(&longs[li].mx, mx);
+        }
+    }
+}
+__global__ void pb_unit_stats_long_fin_kernel(PbUnitDev* __restrict__ units, const PbStatsLong* __restrict__ longs, const int* __restrict__ counter) {
+    for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < *counter; li += gridDim.x * blockDim.x) {
+        const PbStatsLong e = longs[li];
+        const PbUnitDev ud = units[e.unit];
+        const long long a = ud.ix1 - 1, b = a + ud.nx;
+        const long long lo = a < 0 ? 0 : a, hi = b > ud.file_nx ? ud.file_nx : b;
+        const bool padded = (lo > a) || (hi < b) || (hi <= lo);
+        int mn = e.mn, mx = e.mx;
+        if (padded) { mn = min(mn, 0); mx = max(mx, 0); }
+        if (hi <= lo) { mn = 0; mx = 0; }
+        const double mean = ((double)(long long)e.sum / 32768.0) / (double)ud.nx;
+        const double p1 = fabs((double)mx / 32768.0 - mean), p2 = fabs((double)mn / 32768.0 - mean);
+        units[e.unit].mean = mean;
+        units[e.unit].global_peak = p1 > p2 ? p1 : p2;
     }
 }
 

@@ -209,3 +209,47 @@ def test_emulated_overflow_and_deep_refinement_paths(emu, oracle, floor, ceiling
     agree, rel = compare_tracks(r["frame_f0"], o["frequency"])
     assert agree >= 1.0 - 1.0 / o["n_frames"] and rel < 5e-3
     assert np.max(np.abs(r["frame_strength"] - o["strength"])) < 2e-3
+
+
+def test_emulated_blocked_path_finder_matches_one_warp_walk(emu, monkeypatch):
+    """K3 for long chains (pb_path_block_*_kernel: blocks, (max, +) transfer matrices, back-maps) against the one-warp kernel on the
+    same candidate lattice: selected frequencies / strengths frame by frame, medians and voiced counts identical."""
+    import prosody_b200 as pb
+    sr, dur = 16000, 0.9
+    x = speechlike(3, dur, sr, seed=11)
+    x[1, 3000:7000] = 0                                # a stretch of single-candidate frames inside a unit
+    n = x.shape[1]
+    units = pb.Units.from_list([(0, n, sr, 0.0, None), (n, n, sr, 0.0, None), (2 * n, n, sr, 0.1, 0.8), (0, n, sr, 0.0, 0.3)])
+    p = pb.pitch_params(75.0, 600.0)
+    monkeypatch.delenv("PB_PATH_LONG", raising=False)
+    ref = emu.median_pitch(x.reshape(-1), units, p, frames=True)
+    for long_thresh, block in ((40, 16), (40, 7), (60, 512), (10, 2)):
+        monkeypatch.setenv("PB_PATH_LONG", str(long_thresh))
+        monkeypatch.setenv("PB_PATH_BLOCK", str(block))
+        monkeypatch.setenv("PB_STATS_LONG", str(50 * block))       # K0 for long units too (piecewise, exact integer merges)
+        r = emu.median_pitch(x.reshape(-1), units, p, frames=True)
+        assert np.array_equal(r["frame_f0"], ref["frame_f0"]) and np.array_equal(r["frame_strength"], ref["frame_strength"])
+        assert np.array_equal(r["median_f0"], ref["median_f0"]) and np.array_equal(r["n_voiced"], ref["n_voiced"])
+    assert (ref["n_voiced"] > 0).all()
+
+
+def test_emulated_long_unit_loudness_matches_chained_scan(emu, oracle, monkeypatch):
+    """K4 for long units (piecewise peak, grouped state scan, CTA-wide gates: pb_lufs.cuh "long units") against the per-unit
+    chain and against the oracle; the thresholds are lowered so a 1.2 s clip counts as long."""
+    import prosody_b200 as pb
+    x = speechlike(1, 1.7, 16000, seed=4)[0]
+    y = speechlike(1, 0.9, 11025, seed=8)[0]            # 1102.5 samples per chunk: chunk lengths alternate
+    pcm = np.concatenate([x, y])
+    items = [(0, len(x), 16000, 0.0, None, 16000.0), (0, len(x), 16000, 0.1, 1.3, 44100.0), (0, len(x), 16000, 0.2, 0.4, 16000.0),
+             (len(x), len(y), 11025, 0.0, None, 11025.0), (0, len(x), 16000, 0.7, 1.7015, 16000.0)]
+    units = pb.Units.from_list(items)
+    monkeypatch.delenv("PB_LUFS_LONG", raising=False)
+    ref, st_ref = emu.lufs(pcm, units)
+    for long_chunks, group in ((3, 2), (5, 3), (1, 1), (6, 64)):
+        monkeypatch.setenv("PB_LUFS_LONG", str(long_chunks)); monkeypatch.setenv("PB_LUFS_GROUP", str(group))
+        out, st = emu.lufs(pcm, units)
+        assert np.array_equal(st, st_ref)
+        assert np.max(np.abs(out - ref)) < 1e-10, (long_chunks, group, out, ref)
+        for k, it in enumerate(items):
+            src = x if it[0] == 0 else y
+            assert abs(out[k] - oracle.lufs(src, it[2], it[5], it[3], it[4])) < 1e-9

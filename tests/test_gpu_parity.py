@@ -222,6 +222,57 @@ def test_long_form_unit_path_finder(gpu_extractor, oracle):
     assert abs(out[0] - oracle.lufs(x, sr, float(sr))) < 1e-9
 
 
+def test_blocked_path_finder_equals_one_warp_walk(gpu_extractor, monkeypatch):
+    """K3 for long chains (blocks, (max, +) transfer matrices, back-maps: pb_path_block_*_kernel) against the one-warp kernel on the
+    same candidate lattice: the selected path of a 17 997-frame chain (above the default threshold), of chains cut into short and
+    ragged blocks, and of a batch that mixes long and short units — frame by frame, bit for bit."""
+    import prosody_b200 as pb
+    sr = 22050
+    parts = speechlike(6, 30.0, sr, seed=77)
+    parts[2][5 * sr:9 * sr] = 0                         # a run of single-candidate frames across block boundaries
+    x = np.concatenate(list(parts))
+    n1 = len(parts[0])
+    units = pb.Units.from_list([(0, len(x), sr, 0.0, None), (0, n1, sr, 0.0, None), (n1, 3 * n1, sr, 1.0, 80.0), (0, n1, sr, 0.5, 2.0)])
+    p = pb.pitch_params(75.0, 600.0)
+    monkeypatch.setenv("PB_PATH_LONG", str(10 ** 9))
+    ref = gpu_extractor.median_pitch(x, units, p, frames=True)
+    assert ref["n_frames"][0] == 17997
+    for long_thresh, block in ((None, None), (1000, 512), (1000, 333), (100, 64)):
+        if long_thresh is None:
+            monkeypatch.delenv("PB_PATH_LONG"); monkeypatch.delenv("PB_PATH_BLOCK", raising=False)
+        else:
+            monkeypatch.setenv("PB_PATH_LONG", str(long_thresh)); monkeypatch.setenv("PB_PATH_BLOCK", str(block))
+            monkeypatch.setenv("PB_STATS_LONG", str(1000 * block))     # K0 for long units too (piecewise, exact integer merges)
+        r = gpu_extractor.median_pitch(x, units, p, frames=True)
+        assert np.array_equal(r["frame_f0"], ref["frame_f0"]) and np.array_equal(r["frame_strength"], ref["frame_strength"]), (long_thresh, block)
+        assert np.array_equal(r["median_f0"], ref["median_f0"]) and np.array_equal(r["n_voiced"], ref["n_voiced"])
+
+
+def test_long_unit_loudness_equals_chained_scan(gpu_extractor, oracle, monkeypatch):
+    """K4 for long units (piecewise peak, grouped state scan, CTA-wide gates) against the per-unit chain on a 10-minute recording
+    (6 000 chunks: above the default threshold) mixed with short units and slices, and against the oracle."""
+    import prosody_b200 as pb
+    sr = 22050
+    parts = speechlike(6, 100.0, sr, seed=78)
+    parts[3][10 * sr:14 * sr] = 0
+    x = np.concatenate(list(parts))
+    n1 = len(parts[0])
+    items = [(0, len(x), sr, 0.0, None, float(sr)), (0, n1, sr, 0.0, None, float(sr)), (0, len(x), sr, 3.0, 555.5, 44100.0), (n1, n1, sr, 0.5, 2.0, float(sr))]
+    units = pb.Units.from_list(items)
+    monkeypatch.setenv("PB_LUFS_LONG", str(10 ** 9))
+    ref, st_ref = gpu_extractor.lufs(x, units)
+    for long_chunks, group in ((None, None), (100, 7), (10, 4096)):
+        if long_chunks is None:
+            monkeypatch.delenv("PB_LUFS_LONG"); monkeypatch.delenv("PB_LUFS_GROUP", raising=False)
+        else:
+            monkeypatch.setenv("PB_LUFS_LONG", str(long_chunks)); monkeypatch.setenv("PB_LUFS_GROUP", str(group))
+        out, st = gpu_extractor.lufs(x, units)
+        assert np.array_equal(st, st_ref)
+        assert np.max(np.abs(out - ref)) < 1e-10, (long_chunks, group, out, ref)
+    assert abs(ref[0] - oracle.lufs(x, sr, float(sr))) < 1e-9
+    assert abs(ref[2] - oracle.lufs(x, sr, 44100.0, 3.0, 555.5)) < 1e-9
+
+
 def test_mixed_rate_corpus_in_one_call(gpu_extractor, oracle):
     """BASELINE config 5 in miniature: 16 / 24 / 44.1 kHz files in one batch (three analysis geometries, three meters),
     reference parameters (floor 150, ceiling 600), whole files and slices."""
