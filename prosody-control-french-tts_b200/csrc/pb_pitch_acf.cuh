@@ -134,6 +134,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     typedef PbFftCfg<LOG2N> C;
     constexpr int R = C::R, LR = C::LR, N = C::N, G = C::G, GT = C::GT;
     constexpr bool FAST = (R == 32);                    // compile-time shared-memory offsets (all sizes >= 1024)
+    constexpr bool REG_OUT = FAST && G == 1 && C::F == 1 && C::RPL <= R;   // N = 1024: r leaves from the registers of the last pass
     PB_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = warp / G, wg = warp % G;          // group in CTA, warp in group
@@ -160,6 +161,8 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     const int span_hi = max(nw, mean_n0 + mean_len);
     const int span_len = span_hi - span_lo;
     const float mean_scale = (float)(1.0 / (32768.0 * (double)mean_len));
+    const int nrows0 = (nw + GT - 1) / GT;              // rows n = g + GT t of the first pass that hold window samples; the others are zero in registers
+    const int npad_end = nrows0 * GT < N ? nrows0 * GT : N;
     const bool fuse_ok = mean_n0 >= 0 && mean_n0 + mean_len <= nw;     // the local-mean span lies inside the window (periods_per_window >= 2)
     // per thread, loop-invariant: which of its R first-pass inputs n = g + GT t lie inside the window / inside the local-peak span
     unsigned vmask = 0, pkmask = 0;
@@ -290,7 +293,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                         buf[pb_pad5(n1)] = x1;
                     }
                 }
-                for (int n = nw + g; n < N; n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding
+                for (int n = nw + g; n < (FAST ? npad_end : N); n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding (of the last row that holds samples: FAST sizes)
                 PB_K1_SYNC();                   // the windowed frames are in the buffer
             }
         } else {
@@ -325,7 +328,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                 if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, bb); }
                 buf[pb_pad5(n)] = ab;
             }
-            for (int n = nw + g; n < N; n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding
+            for (int n = nw + g; n < (FAST ? npad_end : N); n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding (of the last row that holds samples: FAST sizes)
             mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB);
             if (G > 1) {
                 if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; }
@@ -381,7 +384,8 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
             } else if (FAST) {
                 // i = g + 32 G t  ->  i + (i >> 5) = g + (g >> 5) + 33 G t: one base, compile-time offsets
                 const float2* src = buf + (g + (g >> 5));
-                PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * (33 * G)];
+                const int nrows = step == 0 ? nrows0 : R;          // the frames end after nrows0 rows: nothing was written beyond
+                PB_UNROLL for (int t = 0; t < R; t++) v[t] = t < nrows ? src[t * (33 * G)] : make_float2(0.0f, 0.0f);
                 if (step == 0 && !interior) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
             } else {
                 const int sh = pass ? LR : 5;
@@ -400,7 +404,24 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
             if (step == 0) PB_K1_STAGE_NEXT();
             pb_dft<R>(v);
             // pass 1 (Ns = 1): out[g*R + t], skew (index >> LR);  pass 2 (Ns = R): out[(g/R) R^2 + g%R + t R], skew 5
-            if (FAST) {
+            if (REG_OUT && step == 3) {
+                // ---- the last pass of the second transform leaves lags g + 32 t in this lane's registers: the lags 0..B+1 go
+                //      straight to the global scratch, r[lag] = ac[lag] / (ac[0] windowR[lag]); nothing returns to shared memory
+                const float2 a0v = v[0];
+                const float2 ac0 = make_float2(__shfl_sync(PB_FULL_MASK, a0v.x, 0), __shfl_sync(PB_FULL_MASK, a0v.y, 0));
+                const float2 inv0 = make_float2(ac0.x > 0.0f ? 1.0f / ac0.x : 0.0f, ac0.y > 0.0f ? 1.0f / ac0.y : 0.0f);
+                float* ra = racf + (size_t)(2 * li) * rstride_g + g;
+                float* rb = ra + rstride_g;
+                const float* iwp = gm.inv_wr + g;                  // inv_wr[B + 1] = 0
+                PB_UNROLL for (int q = 0; q < C::RPL; q++) {
+                    if (g + q * GT <= B + 1) {
+                        const float iw = __ldg(iwp + q * GT);
+                        float2 r2 = __fmul2_rn(v[pb_bitrev(q, LR)], __fmul2_rn(inv0, make_float2(iw, iw)));
+                        if (q == 0 && g == 0) r2 = make_float2(1.0f, 1.0f);
+                        ra[q * GT] = r2.x; rb[q * GT] = r2.y;
+                    }
+                }
+            } else if (FAST) {
                 // pass 1: 32 g + t -> 33 g + t;  pass 2: (g>>5) 1024 + (g&31) + 32 t -> (g>>5) 1056 + (g&31) + 33 t
                 if (pass) {
                     float2* dst = buf + ((g >> 5) * 1056 + (g & 31));
@@ -415,7 +436,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                 const int osh = pass ? 5 : LR;
                 PB_UNROLL for (int t = 0; t < R; t++) { const int o = ob + t * os; buf[o + (o >> osh)] = v[pb_bitrev(t, LR)]; }
             }
-            PB_K1_SYNC();
+            if (!(REG_OUT && step == 3)) PB_K1_SYNC();
             if (pass && C::F > 1) {
                 // ---- final pass (radix F, Ns = R*R): butterflies are in place
                 constexpr int F = C::F > 1 ? C::F : 2, LF = pb_ilog2(F);
@@ -481,7 +502,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
         // ---- outputs: r[lag] = ac[lag] / (ac[0] * windowR[lag]) for lags 0..B+1 of the active frames, to the global scratch
         const int slot = 2 * li;
         const bool actA = active && pkA > 0.0f, actB = active && hasB && pkB > 0.0f;
-        if (active) {
+        if (active && !REG_OUT) {
             // both rows of the slot pair are written whenever the pair is active (K2 only reads the rows slot_fr marks)
             const float2 ac0 = buf[0];
             const float2 inv0 = make_float2(ac0.x > 0.0f ? 1.0f / ac0.x : 0.0f, ac0.y > 0.0f ? 1.0f / ac0.y : 0.0f);
@@ -512,7 +533,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                 else { const float t = pkB / gpk; intensity[frA + 1] = t > 1.0f ? 1.0f : t; }
             }
         }
-        PB_K1_SYNC();     // buf is reused by the next iteration
+        if (!REG_OUT) PB_K1_SYNC();     // buf is reused by the next iteration (REG_OUT: its last reads were the loads of the last pass, already fenced)
     }
 }
 #undef PB_K1_SYNC
