@@ -382,11 +382,12 @@ def bench_steps(args, rank, world, local):
             hbm_gbs = alg_bytes * frames_per_launch / (frames_ms * 1e-3) / 1e9
             traffic = None                           # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
             try:
-                tr = json.loads((ROOT / "profiles" / "r02_acf_traffic.json").read_text())
-                traffic = tr["bytes_per_frame"] * frames_per_launch if cfg == "c2" else None
+                tr = json.loads((ROOT / "profiles" / "r02b_acf_traffic.json").read_text())
             except Exception:       # noqa: BLE001
-                pass
+                tr = {}
             kname = f"pb_pitch_acf_kernel<{max(8, int(math.ceil(math.log2(g.nsamp_window + g.brent_ixmax + 1))))}>"
+            if kname in tr and cfg in ("c2", "c3"):          # captured on this geometry
+                traffic = tr[kname]["bytes_per_frame"] * frames_per_launch
             roof = dict(bound="fp32", kernel=kname, achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=traffic,
                         peak_source=fp32_src,
                         note="non-tensor FP32 pipe: no stage is a dense contraction. Round 2 split the round-1 frames kernel in two: K1 pb_pitch_acf_kernel "

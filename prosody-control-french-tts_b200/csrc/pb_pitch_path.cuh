@@ -1,5 +1,6 @@
 // pb_pitch_path.cuh — K3: Viterbi path finder + median of the voiced frames (see pb_pitch.cuh for the overview).
 #pragma once
+#include "pb_async.cuh"
 #include "pb_pitch.cuh"
 
 // ------------------------------------------------------------------------------------------------ K3: path finder + median
@@ -101,6 +102,19 @@ __device__ __forceinline__ void pb_path_forward(const PbPathConsts& k, int maxc,
 // np.median(freqs[freqs > 0]) of sel[0..n) by the threads of one warp (NT = 32) or one CTA (NT = blockDim.x, `scratch` = two ints of
 // shared memory): positive floats order like their bit patterns, so the lower middle is found by bisection on the pattern and
 // the upper middle is either the same value (duplicates) or the smallest value above it.  Returns the count of positives in nv.
+// f(v) for v = sel[tid], sel[tid + nt], ...: eight independent loads in flight per thread (the bisection below streams the
+// selected frequencies ~32 times; one load at a time it ran at L2 latency)
+template <typename F>
+__device__ __forceinline__ void pb_foreach_strided(const float* __restrict__ sel, int n, int tid, int nt, F f) {
+    int i = tid;
+    for (; i + 7 * nt < n; i += 8 * nt) {
+        float v[8];
+        PB_UNROLL for (int q = 0; q < 8; q++) v[q] = sel[i + q * nt];
+        PB_UNROLL for (int q = 0; q < 8; q++) f(v[q]);
+    }
+    for (; i < n; i += nt) f(sel[i]);
+}
+
 template <bool CTA>
 __device__ __forceinline__ double pb_median_positive(const float* __restrict__ sel, int n, int tid, int nt, int* scratch, int& nv_out) {
     auto total = [&](int v) -> int {
@@ -114,7 +128,7 @@ __device__ __forceinline__ double pb_median_positive(const float* __restrict__ s
         return scratch[0];
     };
     int nv = 0;
-    for (int f = tid; f < n; f += nt) nv += sel[f] > 0.0f;
+    pb_foreach_strided(sel, n, tid, nt, [&](float v) { nv += v > 0.0f; });
     nv = total(nv);
     nv_out = nv;
     if (nv <= 0) return 0.0;
@@ -123,7 +137,7 @@ __device__ __forceinline__ double pb_median_positive(const float* __restrict__ s
     while (lo < hi) {
         const unsigned mid = lo + ((hi - lo) >> 1);
         int cnt = 0;
-        for (int f = tid; f < n; f += nt) { const float v = sel[f]; cnt += (v > 0.0f && __float_as_uint(v) <= mid); }
+        pb_foreach_strided(sel, n, tid, nt, [&](float v) { cnt += (v > 0.0f && __float_as_uint(v) <= mid); });
         cnt = total(cnt);
         if (cnt >= kk + 1) hi = mid; else lo = mid + 1;
     }
@@ -132,10 +146,7 @@ __device__ __forceinline__ double pb_median_positive(const float* __restrict__ s
     if ((nv & 1) == 0) {
         // the next order statistic: lower again if enough duplicates, else the smallest value above it
         int cnt = 0; float nxt = 3.0e38f;
-        for (int f = tid; f < n; f += nt) {
-            const float v = sel[f];
-            if (v > 0.0f) { if (v <= lower) cnt++; else nxt = fminf(nxt, v); }
-        }
+        pb_foreach_strided(sel, n, tid, nt, [&](float v) { if (v > 0.0f) { if (v <= lower) cnt++; else nxt = fminf(nxt, v); } });
         cnt = total(cnt);
         PB_UNROLL for (int o = 16; o > 0; o >>= 1) nxt = fminf(nxt, __shfl_xor_sync(PB_FULL_MASK, nxt, o));
         if (CTA) {
@@ -298,30 +309,52 @@ pb_path_block_entry_kernel(const PbUnitDev* __restrict__ units, PbPitchGeomDev g
     }
 }
 
-// (b) D_b = D_{b-1} (x) T_b in order; D[job][c] = score of candidate c of the block's last frame
+// (b) D_b = D_{b-1} (x) T_b in order; D[job][c] = score of candidate c of the block's last frame.  The matrices (2 KB each,
+// independent of the running scores) are pulled into a ring of shared-memory slots by bulk copies issued PB_PATHL_RING blocks ahead,
+// so a step is the sixteen shuffle / add / compare triples and not an L2 round trip.
+#define PB_PATHL_RING 4
 __global__ void __launch_bounds__(32)
 pb_path_block_scan_kernel(const PbUnitDev* __restrict__ units, PbPitchGeomDev gm, const uint8_t* __restrict__ ncand,
                           PbLongUnit* __restrict__ longs, const int* __restrict__ counters, const double* __restrict__ T, double* __restrict__ D) {
+    __shared__ __align__(16) double s_T[PB_PATHL_RING][256];
+    __shared__ pbMbar s_bar[PB_PATHL_RING];
     const int lane = threadIdx.x & 31, c = lane & 15;
     const double NEG_INF = PB_NEG_INF_D;
+    if (lane == 0) for (int i = 0; i < PB_PATHL_RING; i++) pb_mbar_init(&s_bar[i], 1);
+    pb_mbar_init_fence();
+    __syncwarp();
+    unsigned parity = 0;                                         // bit i: the phase slot i is waited on next
     for (int li = blockIdx.x; li < counters[0]; li += gridDim.x) {
         const PbLongUnit lu = longs[li];
         const PbUnitDev* ud = units + lu.unit;
         const int nF = ud->n_frames; const int64_t f0 = ud->frame_off;
+        const int nb = lu.n_blocks;
+        auto issue = [&](int b) {                                // block b -> slot b % RING (lane 0)
+            pbMbar* bar = &s_bar[b % PB_PATHL_RING];
+            pb_mbar_expect_tx(bar, 2048u);
+            pb_bulk_g2s(s_T[b % PB_PATHL_RING], T + ((size_t)lu.job_off + b) * 256, 2048u, bar);
+        };
+        if (lane == 0) for (int b = 1; b < nb && b <= PB_PATHL_RING; b++) issue(b);
         double d = T[(size_t)lu.job_off * 256 + c];              // block 0: row 0
         if (lane < 16) D[(size_t)lu.job_off * 16 + c] = d;
-        for (int b = 1; b < lu.n_blocks; b++) {
+        int ncp_next = nb > 1 ? ncand[f0 + gm.path_block - 1] : 0;
+        for (int b = 1; b < nb; b++) {
             const size_t job = (size_t)lu.job_off + b;
-            const int ncp = ncand[f0 + (int64_t)b * gm.path_block - 1];
-            double t[16];
-            PB_UNROLL for (int e = 0; e < 16; e++) t[e] = e < ncp ? T[(job * 16 + e) * 16 + c] : NEG_INF;     // independent of d: all in flight at once
+            const int slot = b % PB_PATHL_RING;
+            const int ncp = ncp_next;
+            if (b + 1 < nb) ncp_next = ncand[f0 + (int64_t)(b + 1) * gm.path_block - 1];
+            pb_mbar_wait(&s_bar[slot], (parity >> slot) & 1u); parity ^= 1u << slot;
+            __syncwarp();
+            const double* t = s_T[slot] + c;
             double best = NEG_INF;
             PB_UNROLL for (int e = 0; e < 16; e++) {
-                const double v = pb_shfl_d(d, e) + t[e];
+                const double v = pb_shfl_d(d, e) + t[e * 16];
                 if (e < ncp && v > best) best = v;
             }
             d = best;
             if (lane < 16) D[job * 16 + c] = d;
+            __syncwarp();                                        // every lane has read the slot before it is refilled
+            if (lane == 0 && b + PB_PATHL_RING < nb) issue(b + PB_PATHL_RING);
         }
         // terminal candidate: first maximum
         const int ncl = ncand[f0 + nF - 1];
