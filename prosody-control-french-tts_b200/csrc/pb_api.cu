@@ -565,6 +565,7 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
         int32_t* sp = (int32_t*)h->stage_pairs.p + h->sp_off;
         // running pair / frame offsets first (sequential, two adds per unit), then the 80-byte descriptors in parallel
         int64_t pairs = 0, n_long = 0, n_long_blocks = 0, n_long_stats = 0;
+        const long long long_nx = stats_long_nx(); const int path_long = path_long_thresh(), path_block = path_block_len();   // (getenv: not per unit)
         std::vector<int64_t>& fbase = h->plan.fbase;
         fbase.resize(m);
         for (size_t k = 0; k < m; k++) {
@@ -572,8 +573,8 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
             sp[k] = (int32_t)pairs; fbase[k] = frame_base;
             pairs += (pl.n_frames + 1) / 2;
             frame_base += pl.n_frames;
-            if (pl.nx > stats_long_nx()) n_long_stats++;
-            if (pl.n_frames > path_long_thresh()) { n_long++; n_long_blocks += (pl.n_frames + path_block_len() - 1) / path_block_len(); }
+            if (pl.nx > long_nx) n_long_stats++;
+            if (pl.n_frames > path_long) { n_long++; n_long_blocks += (pl.n_frames + path_block - 1) / path_block; }
             if (pairs > 0x7ffffff0LL) return fail(h, PB_EUNSUPPORTED, "%s", "more than 2^31 frame pairs in one launch; split the batch");
         }
         sp[m] = (int32_t)pairs;

@@ -68,22 +68,29 @@ __device__ __forceinline__ int pb_lufs_find_unit(const PbLufsUnitDev* __restrict
 // (1) and (3): one thread per chunk runs the K-weighting recurrence over its samples, eight at a time through aligned
 // 16-byte loads.  ENERGY = false: from rest, keeping only the final state (the chunk's zero-state contribution);
 // ENERGY = true: from the chunk's true initial state, accumulating the energy of the weighted signal.
-// (A chain-free formulation of pass 1 — the final state as four dot products against A^j B, one warp per chunk — was
-// tried and lost: 2-byte strided loads gave it no memory-level parallelism, 79 % long-scoreboard stalls, 6.6 ms vs 2.4 ms
-// for this kernel on the same data; profiles/r01_lufs_state_dot_ncu_summary.csv.)
+// Both passes work on the INTEGER sample values: the filter is linear, so the reference's division by the peak becomes a factor
+// inv_peak^2 on the block energies (applied by the gate kernels) and costs nothing per sample.  Every state update is written as
+// t = b x + s_next (off the critical path), s = -a y + t — scipy.signal.lfilter's own association (direct form II transposed):
+// 10 (+1 for the energy) FP64 operations per sample, two of them on the dependent chain; round 1 spent 13 (+1) with a chain of
+// four.  The kernels are FP64-pipe bound (profiles/r02b_lufs_chunk_ncu_summary.csv), so the operation count is the time.
+// Formulations of pass (1) without the chain were tried and lost: four dot products against A^j B with one warp per chunk and
+// 2-byte strided loads (round 1: no memory-level parallelism, 6.6 ms vs 2.4 ms); thread per chunk against a whole-chunk table in
+// global memory (round 2: L1 misses, 555 us vs 353 us); 64-sample sub-blocks against a 2 KB shared-memory table chained through
+// A^64 (round 2: 4.25 FP64 operations per sample, but two broadcast 16-byte shared loads per sample and the I2F.F64 conversions
+// — 8 lanes per clock — bound it: no faster than the recurrence).
 #define PB_LUFS_STEP(xv)                                                  \
     {                                                                     \
         const double x_ = (xv);                                           \
-        const double y1_ = b10 * x_ + p0;      /* scipy.signal.lfilter, direct form II transposed */ \
-        p0 = b11 * x_ - a11 * y1_ + p1;                                   \
-        p1 = b12 * x_ - a12 * y1_;                                        \
-        const double y2_ = b20 * y1_ + q0;                                \
-        q0 = b21 * y1_ - a21 * y2_ + q1;                                  \
-        q1 = b22 * y1_ - a22 * y2_;                                       \
-        e += y2_ * y2_;                                                   \
+        const double y1_ = fma(b10, x_, p0);                              \
+        p0 = fma(-a11, y1_, fma(b11, x_, p1));                            \
+        p1 = fma(-a12, y1_, b12 * x_);                                    \
+        const double y2_ = fma(b20, y1_, q0);                             \
+        q0 = fma(-a21, y2_, fma(b21, y1_, q1));                           \
+        q1 = fma(-a22, y2_, b22 * y1_);                                   \
+        e = fma(y2_, y2_, e);                                             \
     }
 template <bool ENERGY>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 pb_lufs_chunk_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __restrict__ units, int n_units,
                      const PbMeterDev* __restrict__ meters, long long n_chunks_total,
                      double* __restrict__ state /* [n_chunks][4] */, double* __restrict__ energy /* [n_chunks] */) {
@@ -100,18 +107,17 @@ pb_lufs_chunk_kernel(const int16_t* __restrict__ pcm, const PbLufsUnitDev* __res
         double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0, e = 0.0;
         if (ENERGY) { p0 = state[ch * 4 + 0]; p1 = state[ch * 4 + 1]; q0 = state[ch * 4 + 2]; q1 = state[ch * 4 + 3]; }
         const int16_t* __restrict__ p = pcm + ud.pcm_off + ud.a;
-        const double ip = ud.inv_peak;
         long long i = lo;
-        while (i < real_hi && (((size_t)(p + i)) & 15)) { PB_LUFS_STEP((double)p[i] * ip); i++; }
+        while (i < real_hi && (((size_t)(p + i)) & 15)) { PB_LUFS_STEP((double)p[i]); i++; }
         while (i + 8 <= real_hi) {
             const int4 v = *reinterpret_cast<const int4*>(p + i);
-            PB_LUFS_STEP((double)(short)(v.x & 0xffff) * ip); PB_LUFS_STEP((double)(v.x >> 16) * ip);
-            PB_LUFS_STEP((double)(short)(v.y & 0xffff) * ip); PB_LUFS_STEP((double)(v.y >> 16) * ip);
-            PB_LUFS_STEP((double)(short)(v.z & 0xffff) * ip); PB_LUFS_STEP((double)(v.z >> 16) * ip);
-            PB_LUFS_STEP((double)(short)(v.w & 0xffff) * ip); PB_LUFS_STEP((double)(v.w >> 16) * ip);
+            PB_LUFS_STEP((double)(short)(v.x & 0xffff)); PB_LUFS_STEP((double)(v.x >> 16));
+            PB_LUFS_STEP((double)(short)(v.y & 0xffff)); PB_LUFS_STEP((double)(v.y >> 16));
+            PB_LUFS_STEP((double)(short)(v.z & 0xffff)); PB_LUFS_STEP((double)(v.z >> 16));
+            PB_LUFS_STEP((double)(short)(v.w & 0xffff)); PB_LUFS_STEP((double)(v.w >> 16));
             i += 8;
         }
-        while (i < real_hi) { PB_LUFS_STEP((double)p[i] * ip); i++; }
+        while (i < real_hi) { PB_LUFS_STEP((double)p[i]); i++; }
         while (i < hi) { PB_LUFS_STEP(0.0); i++; }          // pydub's silent padding
         if (ENERGY) energy[ch] = e;
         else { state[ch * 4 + 0] = p0; state[ch * 4 + 1] = p1; state[ch * 4 + 2] = q0; state[ch * 4 + 3] = q1; }
@@ -298,7 +304,7 @@ pb_lufs_gate_long_kernel(const PbLufsUnitDev* __restrict__ units, const PbLufsLo
     const double NEG_INF = -(double)INFINITY;
     for (int li = blockIdx.x; li < counters[0]; li += gridDim.x) {
         const PbLufsUnitDev ud = units[longs[li].unit];
-        const double inv = 1.0 / (0.4 * meters[ud.meter].rate);
+        const double inv = ud.inv_peak * ud.inv_peak / (0.4 * meters[ud.meter].rate);   // the chunk energies are those of the integer samples
         const double* e = energy + ud.chunk_off;
         double gamma_r = 0.0, out = NEG_INF;
         for (int pass = 0; pass < 2; pass++) {
@@ -332,7 +338,7 @@ pb_lufs_gate_kernel(const PbLufsUnitDev* __restrict__ units, int n_units, const 
         const PbLufsUnitDev ud = units[u];
         if (ud.n_chunks > long_chunks) continue;             // long units: pb_lufs_gate_long_kernel
         const double rate = meters[ud.meter].rate;
-        const double inv = 1.0 / (0.4 * rate);
+        const double inv = ud.inv_peak * ud.inv_peak / (0.4 * rate);      // the chunk energies are those of the integer samples
         const double* e = energy + ud.chunk_off;
         const double NEG_INF = -(double)INFINITY;
         // absolute gate
