@@ -537,7 +537,12 @@ struct PitchLaunch { int cls; size_t uoff, poff, m; int64_t pairs; int64_t long_
 long long stats_long_nx() { const char* e = getenv("PB_STATS_LONG"); const long long x = e ? atoll(e) : 0; return x > 0 ? x : (1LL << 22); }
 // K3: units with more frames than this are cut into blocks of path_block_len() frames (pb_pitch_path.cuh, "long chains")
 // (read at every call: the tests switch them)
-int path_long_thresh() { const char* e = getenv("PB_PATH_LONG"); const int x = e ? atoi(e) : 0; return x > 0 ? x : 8192; }
+// (a launch group with few units cannot fill the GPU with one-warp walks: there the blocked form already pays at 2 048 frames)
+int path_long_thresh(size_t units_in_group, int sm_count) {
+    const char* e = getenv("PB_PATH_LONG"); const int x = e ? atoi(e) : 0;
+    if (x > 0) return x;
+    return units_in_group < (size_t)sm_count * 4 ? 2048 : 8192;
+}
 int path_block_len() { const char* e = getenv("PB_PATH_BLOCK"); const int x = e ? atoi(e) : 0; return x >= 2 && x <= PB_PATHL_BLOCK_MAX ? x : PB_PATHL_BLOCK_MAX; }
 struct LufsLaunch { size_t off, m; int64_t chunks; int64_t long_units = 0, long_groups = 0; };
 // K4: units with more 100 ms chunks than this go through the long-unit kernels, their chain cut into groups (pb_lufs.cuh, "long units")
@@ -565,7 +570,7 @@ int stage_pitch(PbHandle* h, const PbUnits* u, const BatchPlan& bp, const std::v
         int32_t* sp = (int32_t*)h->stage_pairs.p + h->sp_off;
         // running pair / frame offsets first (sequential, two adds per unit), then the 80-byte descriptors in parallel
         int64_t pairs = 0, n_long = 0, n_long_blocks = 0, n_long_stats = 0;
-        const long long long_nx = stats_long_nx(); const int path_long = path_long_thresh(), path_block = path_block_len();   // (getenv: not per unit)
+        const long long long_nx = stats_long_nx(); const int path_long = path_long_thresh(m, h->sm_count), path_block = path_block_len();   // (getenv: not per unit)
         std::vector<int64_t>& fbase = h->plan.fbase;
         fbase.resize(m);
         for (size_t k = 0; k < m; k++) {
@@ -634,7 +639,7 @@ int launch_pitch_group(PbHandle* h, const int16_t* d_pcm, const PbPitchParams* p
         gm.dx = pc.g.dx; gm.dt = pc.g.dt; gm.ceiling = pc.g.ceiling; gm.silence_threshold = p->silence_threshold;
         gm.voicing_threshold = p->voicing_threshold; gm.octave_cost_d = p->octave_cost; gm.octave_jump_cost = p->octave_jump_cost;
         gm.voiced_unvoiced_cost = p->voiced_unvoiced_cost;
-        gm.path_long = pc.g.max_cand <= 16 ? path_long_thresh() : 0x7fffffff;      // the blocked path finder packs 16 candidates per word
+        gm.path_long = pc.g.max_cand <= 16 ? path_long_thresh(m, h->sm_count) : 0x7fffffff;      // the blocked path finder packs 16 candidates per word
         gm.path_block = path_block_len();
         gm.window = (const float*)tb->window.p; gm.inv_wr = (const float*)tb->inv_wr.p;
         gm.tw_a = (const float2*)tb->tw_a.p; gm.tw_b = (const float2*)tb->tw_b.p; gm.half_tab = (const float*)tb->half_tab.p;

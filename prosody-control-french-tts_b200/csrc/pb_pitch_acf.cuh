@@ -161,8 +161,6 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     const int span_hi = max(nw, mean_n0 + mean_len);
     const int span_len = span_hi - span_lo;
     const float mean_scale = (float)(1.0 / (32768.0 * (double)mean_len));
-    const int nrows0 = (nw + GT - 1) / GT;              // rows n = g + GT t of the first pass that hold window samples; the others are zero in registers
-    const int npad_end = nrows0 * GT < N ? nrows0 * GT : N;
     const bool fuse_ok = mean_n0 >= 0 && mean_n0 + mean_len <= nw;     // the local-mean span lies inside the window (periods_per_window >= 2)
     // per thread, loop-invariant: which of its R first-pass inputs n = g + GT t lie inside the window / inside the local-peak span
     unsigned vmask = 0, pkmask = 0;
@@ -192,6 +190,9 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     for (int li = it_begin; li < it_end; li++) {
         const int item = item0 + li;
         const PbPairPos pos = pos_next;
+        // the next pair's descriptor is fetched now and used after the first pass's loads: its latency hides behind the windowing
+        // (fetched where it is used, the `edge` test on it was the kernel's single hottest stall: profiles/r02b_acf_ncu_summary.csv)
+        const int4 d_next = li + 1 < it_end ? __ldg(pairpos + item + 1) : make_int4(0, 0, 0, 0);
         if (u != u_next) {
             u = u_next;
             const PbUnitDev* up = units + u;
@@ -293,7 +294,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                         buf[pb_pad5(n1)] = x1;
                     }
                 }
-                for (int n = nw + g; n < (FAST ? npad_end : N); n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding (of the last row that holds samples: FAST sizes)
+                for (int n = nw + g; n < N; n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding
                 PB_K1_SYNC();                   // the windowed frames are in the buffer
             }
         } else {
@@ -328,7 +329,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
                 if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, bb); }
                 buf[pb_pad5(n)] = ab;
             }
-            for (int n = nw + g; n < (FAST ? npad_end : N); n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding (of the last row that holds samples: FAST sizes)
+            for (int n = nw + g; n < N; n += GT) buf[pb_pad5(n)] = make_float2(0.0f, 0.0f);      // zero padding
             mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB);
             if (G > 1) {
                 if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; }
@@ -349,7 +350,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
             staged_next = true; \
             if (li + 1 < it_end) { \
                 if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); } \
-                pos_next = pb_stage_pair<GT>(pcm, units, u_next, pairpos[item + 1], gm.pcm_len, span_lo, span_len, pre, g, mbar); \
+                pos_next = pb_stage_pair<GT>(pcm, units, u_next, d_next, gm.pcm_len, span_lo, span_len, pre, g, mbar); \
             } } while (0)
 
         // ---- two FFTs x two passes through ONE copy of the butterfly code: FFT (step >> 1), pass (step & 1).  The step
@@ -384,8 +385,7 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
             } else if (FAST) {
                 // i = g + 32 G t  ->  i + (i >> 5) = g + (g >> 5) + 33 G t: one base, compile-time offsets
                 const float2* src = buf + (g + (g >> 5));
-                const int nrows = step == 0 ? nrows0 : R;          // the frames end after nrows0 rows: nothing was written beyond
-                PB_UNROLL for (int t = 0; t < R; t++) v[t] = t < nrows ? src[t * (33 * G)] : make_float2(0.0f, 0.0f);
+                PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * (33 * G)];
                 if (step == 0 && !interior) { const float2 sc = make_float2(sA, sB); PB_UNROLL for (int t = 0; t < R; t++) v[t] = __fmul2_rn(v[t], sc); }
             } else {
                 const int sh = pass ? LR : 5;
