@@ -118,3 +118,22 @@ def test_native_csv_tables_equal_the_pandas_writer_byte_for_byte(tmp_path, nativ
     # empty input: headers only would need a frame with columns; the reference never gets here (KeyError on the empty frame, :593)
     one = SSML.build_csv_bytes(SSML.TextPools(["s"], ["mot"]), [0], [1.0], [2.0], [3.0], "v", 1, lib=native_lib)
     assert one[0].startswith(b"segment,ssml\ns,") and one[1].count(b"\n") == 2
+
+
+def test_native_two_decimal_formatter_on_the_rounding_lattice(native_lib):
+    """pb_ssml_csv formats its percentages without the C library (exact integer arithmetic on the double's mantissa): every multiple
+    of 0.005 in [-40, 40] (the ties and near-ties of the :+.2f lattice), both neighbouring doubles of each, tiny, huge and subnormal
+    values must print exactly like Python's f'{x:+.2f}' (audioPipeline.py:610-612)."""
+    import re
+    from prosody_b200 import ssml as SSML
+    base = np.arange(-8000, 8001) * 0.005
+    vals = np.concatenate([base, np.nextafter(base, 1e9), np.nextafter(base, -1e9), np.arange(-8000, 8001) / 800.0,
+                           [0.0, -0.0, 5e-324, -5e-324, 1e-300, 0.125, 0.375, 2.675, 1.005, 999999999999999.0, -123456789.125, 1e15, -3e18, 7.5e22]])
+    n = len(vals)
+    tables = SSML.build_csv_bytes(SSML.TextPools(["s"] * n, ["mot"] * n), [0] * n, vals, vals[::-1].copy(), -vals, "v", 1, lib=native_lib)
+    rows = tables[1].decode().splitlines()[1:]
+    assert len(rows) == n
+    pat = re.compile(r'pitch=""([^"]*)%"" rate=""([^"]*)%"" volume=""([^"]*)%""')
+    for k, row in enumerate(rows):
+        got = pat.search(row).groups()
+        assert got == (f"{vals[k]:+.2f}", f"{vals[n - 1 - k]:+.2f}", f"{-vals[k]:+.2f}"), (k, vals[k], got)
