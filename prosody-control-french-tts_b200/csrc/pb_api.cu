@@ -447,8 +447,13 @@ template <int LOG2N>
 int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, const int32_t* d_pair_off, const PbPitchGeomDev& gm,
                   float* cand_f, float* cand_s, uint8_t* ncand, float* inten) {
     typedef PbFftCfg<LOG2N> C;
-    const size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + C::GROUPS_PER_CTA * sizeof(pbMbar);
+    size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + C::GROUPS_PER_CTA * sizeof(pbMbar);
     const int threads = C::WARPS_PER_CTA * 32;
+    // N = 2048 with a window of at most 1024 samples and lags below 512 (24 kHz / 22.05 kHz at a 75 Hz floor): two independent
+    // 1024-point pipelines per pair (pb_pitch_acf_split_kernel); PB_ACF_SPLIT=0 keeps the general 32 x 32 x 2 kernel
+    static const int acf_split = [] { const char* e = getenv("PB_ACF_SPLIT"); return e ? atoi(e) : 1; }();
+    const bool split = LOG2N == 11 && acf_split && gm.nw <= 1024 && gm.brent_ixmax + 1 <= 511 && PB_WPC == 4;
+    if (split) smem = (size_t)(PB_WPC / 2) * ((2 * (1024 + 32 + 8) + 16) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + (PB_WPC / 2) * sizeof(pbMbar);
     static const int acf_ctas = [] { const char* e = getenv("PB_ACF_CTAS"); return e ? atoi(e) : 0; }();
     static const int acf_wsync = [] { const char* e = getenv("PB_ACF_WSYNC"); return e ? atoi(e) : 1; }();     // measured 3 % faster than named barriers
     auto kfn = pb_pitch_acf_kernel<LOG2N, C::MIN_CTAS, false>;
@@ -456,6 +461,7 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
         if (acf_ctas == 5) kfn = acf_wsync ? pb_pitch_acf_kernel<LOG2N, 5, true> : pb_pitch_acf_kernel<LOG2N, 5, false>;
         else if (acf_wsync) kfn = pb_pitch_acf_kernel<LOG2N, C::MIN_CTAS, true>;
     }
+    if constexpr (LOG2N == 11) { if (split) kfn = pb_pitch_acf_split_kernel<C::MIN_CTAS>; }
     static const int cand_ctas = [] { const char* e = getenv("PB_CAND_CTAS"); return e ? atoi(e) : 8; }();
     auto cfn = cand_ctas == 10 ? pb_pitch_cand_kernel<10> : cand_ctas == 12 ? pb_pitch_cand_kernel<12> : pb_pitch_cand_kernel<8>;
     int per_sm = 2;
@@ -464,9 +470,9 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
 #ifndef PB_SIMT_EMU
     // function attributes persist, so they are (re)applied whenever the shared-memory footprint of this instantiation
     // changes (another analysis geometry with the same FFT size)
-    const auto okey = std::make_pair((int)LOG2N, smem);
+    const auto okey = std::make_pair((int)LOG2N + (split ? 100 : 0), smem);
     auto oc = h->occ_cache.find(okey);
-    if (oc == h->occ_cache.end() || h->occ_last[LOG2N] != smem) {
+    if (oc == h->occ_cache.end() || h->occ_last[LOG2N + (split ? 100 : 0)] != smem) {
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return fail(h, PB_ECUDA, "cudaFuncSetAttribute: %s", pbrt_error());
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -477,7 +483,7 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
         if (pct > 100) pct = 100;
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         h->occ_cache[okey] = per_sm;
-        h->occ_last[LOG2N] = smem;
+        h->occ_last[LOG2N + (split ? 100 : 0)] = smem;
     } else per_sm = oc->second;
     if (h->cand_smem != cand_smem) {
         if (cudaFuncSetAttribute(cfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem) != cudaSuccess)

@@ -537,3 +537,329 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
     }
 }
 #undef PB_K1_SYNC
+
+// ------------------------------------------------------------------------------------------------ K1 at 2048 points, split
+// 24 kHz and 22.05 kHz at a 75 Hz floor (BASELINE configs 3 and 4) need a 2048-point transform, but their window fills less than
+// half of it (958 / 880 samples) and fewer than a quarter of the lags are read (481 / 442).  Both facts prune a radix-2 stage:
+//   * zero-padded input: X[2k] = DFT_1024(x)[k] and X[2k+1] = DFT_1024(x[n] W^n)[k], W = exp(-2 pi i / 2048) — the first
+//     decimation-in-frequency stage has nothing to add;
+//   * lags below 1024 only: r[t] = E[t] + W^t O[t] with E, O the 1024-point transforms of the even- and odd-indexed power
+//     spectrum — and those are exactly what the two halves of the first transform produce (the conjugate partner of an even bin is
+//     an even bin, of an odd bin an odd bin: j <-> 1024 - j and j <-> 1023 - j).
+// So a pair of frames is TWO independent 1024-point pipelines — one warp each, the register-blocked radix-32 x 32 code of the
+// 1024-point kernel with warp-level synchronisation — that meet twice: when the window is written (every sample goes to both
+// buffers, to the second one times W^n) and when the lags are combined (486 complex multiply-adds instead of a 2048-point
+// radix-2 pass through shared memory).  The general kernel above runs N = 2048 as 32 x 32 x 2 with two warps sharing one buffer
+// and a named barrier around every pass; it stays for geometries whose window or lag range exceeds 1024.
+template <int MINB>
+__global__ void __launch_bounds__(PB_WPC * 32, MINB)
+pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off,
+                          const int4* __restrict__ pairpos, PbPitchGeomDev gm, int item0, int n_items, int rstride_g,
+                          float* __restrict__ racf, long long* __restrict__ slot_fr,
+                          float* __restrict__ cand_f, float* __restrict__ cand_s, uint8_t* __restrict__ ncand, float* __restrict__ intensity) {
+    constexpr int R = 32, LR = 5, NH = 1024, G = 2, GT = 64;
+    constexpr int BUFH = NH + (NH >> 5) + 8;            // float2 slots of one half (skew padding as in the 1024-point kernel)
+    constexpr int GROUPS = PB_WPC / G;
+    constexpr int RPL = 16;                             // rows of 32 lags a lane may have to deliver (lags <= 511)
+    PB_DYN_SMEM(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = warp / G, wg = warp % G;
+    const int g = wg * 32 + lane;                       // thread in group
+    const int bar_id = 1 + group;
+#define PB_KS_SYNC() pb_group_sync<G>(bar_id)
+    const size_t group_bytes = (size_t)(2 * BUFH + 8 * G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t);
+    unsigned char* gbase = smem_raw + (size_t)group * group_bytes;
+    float2* buf = (float2*)gbase + wg * BUFH;           // this warp's half
+    float2* buf_other = (float2*)gbase + (wg ^ 1) * BUFH;
+    float* red = (float*)((float2*)gbase + 2 * BUFH);   // [G][4] floats / [G][6] ints
+    int16_t* pre = (int16_t*)((float2*)gbase + 2 * BUFH + 8 * G);
+    pbMbar* mbar = (pbMbar*)(smem_raw + (size_t)GROUPS * group_bytes) + group;
+    if (g == 0) pb_mbar_init(mbar, 1);
+    pb_mbar_init_fence();
+    __syncthreads();
+    unsigned phase = 0;
+    const int B = gm.brent_ixmax;
+    const int nw = gm.nw;
+    const int pk_lo = max(0, gm.half_nw - gm.half_period), pk_n = min(nw, gm.half_nw + gm.half_period) - pk_lo;
+    const int mean_n0 = gm.half_nw - gm.nsamp_period;
+    const int mean_len = 2 * gm.nsamp_period;
+    const int span_lo = min(0, mean_n0);
+    const int span_hi = max(nw, mean_n0 + mean_len);
+    const int span_len = span_hi - span_lo;
+    const float mean_scale = (float)(1.0 / (32768.0 * (double)mean_len));
+    const bool fuse_ok = mean_n0 >= 0 && mean_n0 + mean_len <= nw;
+    const float2* __restrict__ tw_in = gm.tw_b + NH;    // W^n, n < 1024
+
+    const int n_groups = gridDim.x * GROUPS;
+    const int per_group = (n_items + n_groups - 1) / n_groups;
+    const int it_begin = (blockIdx.x * GROUPS + group) * per_group;
+    const int it_end = min(n_items, it_begin + per_group);
+    if (it_begin >= it_end) return;
+    int u_next = pb_upper_unit(pair_off, gm.n_units, item0 + it_begin);
+    int u_next_end = pair_off[u_next + 1];
+    int u = -1;
+    PbPairPos pos_next = pb_stage_pair<GT>(pcm, units, u_next, pairpos[item0 + it_begin], gm.pcm_len, span_lo, span_len, pre, g, mbar);
+    int u_pair_off = 0, u_nframes = 0, u_pmin = 0, u_pmax1 = 0;
+    long long u_frame_off = 0;
+    float gpk = 0.0f;
+
+    for (int li = it_begin; li < it_end; li++) {
+        const int item = item0 + li;
+        const PbPairPos pos = pos_next;
+        const int4 d_next = li + 1 < it_end ? __ldg(pairpos + item + 1) : make_int4(0, 0, 0, 0);
+        if (u != u_next) {
+            u = u_next;
+            const PbUnitDev* up = units + u;
+            u_pair_off = up->pair_off; u_nframes = up->n_frames; u_frame_off = up->frame_off; gpk = (float)up->global_peak;
+            const long long ix1 = up->ix1, e = (long long)up->file_nx - ix1 + 1;
+            const long long pmin = 2 - ix1 > 1 ? 2 - ix1 : 1, pmax1 = (up->nx < e ? up->nx : e) + 1;
+            const long long BIG = 1LL << 30;
+            u_pmin = (int)(pmin > BIG ? BIG : pmin); u_pmax1 = (int)(pmax1 > BIG ? BIG : (pmax1 < -BIG ? -BIG : pmax1));
+        }
+        const int fA = 2 * (item - u_pair_off);
+        const bool hasB = fA + 1 < u_nframes;
+        const bool global_silent = gpk == 0.0f;
+        const long long frA = u_frame_off + fA;
+        pb_mbar_wait(mbar, phase); phase ^= 1u;
+#ifdef PB_SIMT_EMU
+        PB_KS_SYNC();
+#else
+        if (pos.edge) PB_KS_SYNC();
+#endif
+        const int16_t* sm = pre;
+        const int sb0 = pos.shift - span_lo, sb1 = sb0 + pos.hop;
+        float pkA = 0.0f, pkB = 0.0f;
+        float sA = 1.0f, sB = 1.0f;
+        bool any_signal = false;
+        const long long loA = (long long)u_pmin - pos.start0, hiA = (long long)u_pmax1 - pos.start0;
+        const bool interior = fuse_ok && hasB && loA <= span_lo && hiA - pos.hop >= span_hi;
+        if (interior) {
+            // ---- exact integer statistics of the local-mean span (see the general kernel), then the scaled window into BOTH halves
+            int s0, s1, mn0, mx0, mn1, mx1;
+            {
+                int sum[2]; unsigned vmn[2], vmx[2];
+                PB_UNROLL for (int f = 0; f < 2; f++) {
+                    const int M0 = (f ? sb1 : sb0) + mean_n0, M1 = M0 + mean_len;
+                    const int k0 = (M0 + 1) >> 1, k1 = M1 >> 1;
+                    const unsigned* smw = reinterpret_cast<const unsigned*>(sm);
+                    int acc = 0; unsigned lo = 0x7fff7fffu, hi = 0x80008000u;
+                    for (int k = k0 + g; k < k1; k += GT) {
+                        const unsigned w = smw[k];
+                        acc = __dp2a_lo((int)w, 0x0101, acc);
+                        lo = __vmins2(lo, w); hi = __vmaxs2(hi, w);
+                    }
+                    if (g == 0) {
+                        if (M0 & 1) acc += (int)sm[M0];
+                        if (M1 & 1) acc += (int)sm[M1 - 1];
+                    }
+                    sum[f] = acc; vmn[f] = lo; vmx[f] = hi;
+                }
+                s0 = sum[0]; s1 = sum[1];
+                mn0 = min((int)(short)(vmn[0] & 0xffff), (int)(short)(vmn[0] >> 16)); mx0 = max((int)(short)(vmx[0] & 0xffff), (int)(short)(vmx[0] >> 16));
+                mn1 = min((int)(short)(vmn[1] & 0xffff), (int)(short)(vmn[1] >> 16)); mx1 = max((int)(short)(vmx[1] & 0xffff), (int)(short)(vmx[1] >> 16));
+            }
+            s0 = __reduce_add_sync(PB_FULL_MASK, s0); s1 = __reduce_add_sync(PB_FULL_MASK, s1);
+            mn0 = __reduce_min_sync(PB_FULL_MASK, mn0); mx0 = __reduce_max_sync(PB_FULL_MASK, mx0);
+            mn1 = __reduce_min_sync(PB_FULL_MASK, mn1); mx1 = __reduce_max_sync(PB_FULL_MASK, mx1);
+            {
+                int* redi = (int*)red;
+                if (lane == 0) { redi[wg * 6 + 0] = s0; redi[wg * 6 + 1] = s1; redi[wg * 6 + 2] = mn0; redi[wg * 6 + 3] = mx0; redi[wg * 6 + 4] = mn1; redi[wg * 6 + 5] = mx1; }
+                PB_KS_SYNC();
+                s0 = redi[0] + redi[6]; s1 = redi[1] + redi[7];
+                mn0 = min(redi[2], redi[8]); mx0 = max(redi[3], redi[9]); mn1 = min(redi[4], redi[10]); mx1 = max(redi[5], redi[11]);
+            }
+            const float q15 = 1.0f / 32768.0f;
+            const float meanA = (float)s0 * mean_scale, meanB = (float)s1 * mean_scale;
+            const float mA = fmaxf(fabsf((float)mx0 * q15 - meanA), fabsf((float)mn0 * q15 - meanA));
+            const float mB = fmaxf(fabsf((float)mx1 * q15 - meanB), fabsf((float)mn1 * q15 - meanB));
+            sA = mA > 0.0f ? __int_as_float((254 - ((__float_as_int(mA) >> 23) & 0xff)) << 23) : 1.0f;
+            sB = mB > 0.0f ? __int_as_float((254 - ((__float_as_int(mB) >> 23) & 0xff)) << 23) : 1.0f;
+            const float2 q15s = make_float2(q15 * sA, q15 * sB), nms = make_float2(-meanA * sA, -meanB * sB);
+            any_signal = mA > 0.0f || mB > 0.0f;
+            const int16_t* pa = sm + sb0; const int16_t* pb = sm + sb1;
+            float2* b0 = (float2*)gbase; float2* b1 = b0 + BUFH;
+            for (int n = g; n < nw; n += GT) {
+                const float w0 = __ldg(gm.window + n);
+                const float2 x = __fmul2_rn(__ffma2_rn(make_float2((float)pa[n], (float)pb[n]), q15s, nms), make_float2(w0, w0));
+                if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, fabsf(x.x)); pkB = fmaxf(pkB, fabsf(x.y)); }
+                const float2 tw = __ldg(tw_in + n);
+                b0[pb_pad5(n)] = x;
+                b1[pb_pad5(n)] = make_float2(x.x * tw.x - x.y * tw.y, x.x * tw.y + x.y * tw.x);
+            }
+            for (int n = nw + g; n < NH; n += GT) { b0[pb_pad5(n)] = make_float2(0.0f, 0.0f); b1[pb_pad5(n)] = make_float2(0.0f, 0.0f); }
+        } else {
+            // ---- frames that Praat zero-fills beyond the file, or a unit with an odd frame count: masked samples
+            float mxA = 0.0f, mxB = 0.0f;
+            int nlo[2], nhi[2], sb[2]; float lmean[2];
+            PB_UNROLL for (int f = 0; f < 2; f++) {
+                long long lo = loA - (f ? pos.hop : 0), hi = hiA - (f ? pos.hop : 0);
+                const long long BIG = 1 << 30;
+                nlo[f] = (int)(lo < -BIG ? -BIG : (lo > BIG ? BIG : lo));
+                nhi[f] = (int)(hi < -BIG ? -BIG : (hi > BIG ? BIG : hi));
+                sb[f] = f ? sb1 : sb0;
+                int s = 0;
+                for (int q = lane; q < mean_len; q += 32) {
+                    const int n = mean_n0 + q;
+                    s += (n >= nlo[f] && n < nhi[f]) ? (int)sm[sb[f] + n] : 0;
+                }
+                s = pb_warp_sum_i(s);
+                lmean[f] = (float)s * mean_scale;
+            }
+            if (!hasB) { nlo[1] = 0; nhi[1] = 0; sb[1] = sb[0]; }
+            const float2 nmean = make_float2(-lmean[0], -lmean[1]), q15 = make_float2(1.0f / 32768.0f, 1.0f / 32768.0f);
+            const float hb = hasB ? 1.0f : 0.0f;
+            // two sweeps: the magnitudes first (the scales must be applied BEFORE the second half's samples are rotated by W^n, which
+            // mixes the two frames' components), then the scaled window into both halves
+            auto windowed = [&](int n) -> float2 {
+                const float w = __ldg(&gm.window[n]);
+                const int sa = (n >= nlo[0] && n < nhi[0]) ? (int)sm[sb[0] + n] : 0;
+                const int sbv = (n >= nlo[1] && n < nhi[1]) ? (int)sm[sb[1] + n] : 0;
+                return __fmul2_rn(__ffma2_rn(make_float2((float)sa, (float)sbv), q15, nmean), make_float2(w, w * hb));
+            };
+            for (int n = g; n < nw; n += GT) {
+                const float2 x = windowed(n);
+                const float aa = fabsf(x.x), bb = fabsf(x.y);
+                mxA = fmaxf(mxA, aa); mxB = fmaxf(mxB, bb);
+                if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, aa); pkB = fmaxf(pkB, bb); }
+            }
+            mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB);
+            if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; }
+            PB_KS_SYNC();
+            mxA = fmaxf(red[0], red[4]); mxB = fmaxf(red[1], red[5]);
+            sA = mxA > 0.0f ? __int_as_float((254 - ((__float_as_int(mxA) >> 23) & 0xff)) << 23) : 1.0f;
+            sB = mxB > 0.0f ? __int_as_float((254 - ((__float_as_int(mxB) >> 23) & 0xff)) << 23) : 1.0f;
+            pkA *= sA; pkB *= sB;
+            const float2 sc = make_float2(sA, sB);
+            float2* b0 = (float2*)gbase; float2* b1 = b0 + BUFH;
+            for (int n = g; n < nw; n += GT) {
+                const float2 x = __fmul2_rn(windowed(n), sc);
+                const float2 tw = __ldg(tw_in + n);
+                b0[pb_pad5(n)] = x;
+                b1[pb_pad5(n)] = make_float2(x.x * tw.x - x.y * tw.y, x.x * tw.y + x.y * tw.x);
+            }
+            for (int n = nw + g; n < NH; n += GT) { b0[pb_pad5(n)] = make_float2(0.0f, 0.0f); b1[pb_pad5(n)] = make_float2(0.0f, 0.0f); }
+            any_signal = mxA > 0.0f || mxB > 0.0f;
+        }
+        PB_KS_SYNC();                       // both halves hold the windowed pair; the staging buffer is free
+        const bool active = !global_silent && any_signal;
+        if (li + 1 < it_end) {
+            if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); }
+            pos_next = pb_stage_pair<GT>(pcm, units, u_next, d_next, gm.pcm_len, span_lo, span_len, pre, g, mbar);
+        }
+        // ---- this warp's 1024-point pipeline: two transforms x two passes through one copy of the butterfly code
+        float2 v[R];
+        int n_steps = active ? 4 : 0;
+        asm volatile("" : "+r"(n_steps));
+#ifndef PB_SIMT_EMU
+#pragma unroll 1
+#endif
+        for (int s_it = 0; s_it < n_steps; s_it++) {
+            int step = s_it;
+            asm volatile("" : "+r"(step));
+            int pass = step & 1;
+            asm volatile("" : "+r"(pass));
+            {
+                const float2* src = buf + lane;                       // i = lane + 32 t  ->  lane + 33 t
+                PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * 33];
+            }
+            if (pass) {
+                const float2* tw = gm.tw_a + lane;
+                PB_UNROLL for (int t = 1; t < R; t++) {
+                    const float2 w = __ldg(tw + t * R);
+                    const float2 x = v[t];
+                    v[t] = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(x.x, x.x), w));
+                }
+            }
+            __syncwarp();
+            pb_dft<R>(v);
+            if (step == 3) break;                                     // the lags stay in registers
+            if (pass) { float2* dst = buf + lane; PB_UNROLL for (int t = 0; t < R; t++) dst[t * 33] = v[pb_bitrev(t, LR)]; }
+            else { float2* dst = buf + 33 * lane; PB_UNROLL for (int t = 0; t < R; t++) dst[t] = v[pb_bitrev(t, LR)]; }
+            __syncwarp();
+            if (step == 1) {
+                // ---- power spectra of both frames, packed again as P_a + i P_b; this half holds the even (wg = 0) or the odd
+                //      (wg = 1) bins of the 2048-point spectrum: bin j pairs with 1024 - j, respectively 1023 - j
+                if (wg == 0) {
+                    const float2* pk_ = buf + lane;
+                    float2* qk = buf + (lane ? 32 - lane : 33);
+                    PB_UNROLL for (int i = 0; i < 16; i++) {
+                        const float2 za = pk_[33 * i];
+                        float2 zb = qk[33 * (31 - i)];
+                        if (i == 0 && lane == 0) zb = za;
+                        const float2 p = make_float2(za.x + zb.x, za.y - zb.y), q = make_float2(za.x - zb.x, za.y + zb.y);
+                        const float2 w = make_float2(p.x * p.x + p.y * p.y, q.x * q.x + q.y * q.y);
+                        ((float2*)pk_)[33 * i] = w;
+                        if (!(i == 0 && lane == 0)) qk[33 * (31 - i)] = w;
+                    }
+                    if (lane == 0) {
+                        const float2 za = buf[pb_pad5(NH / 2)];
+                        buf[pb_pad5(NH / 2)] = make_float2(4.0f * za.x * za.x, 4.0f * za.y * za.y);
+                    }
+                } else {
+                    // j = lane + 32 i -> slot lane + 33 i;  1023 - j = (31 - lane) + 32 (31 - i) -> slot (31 - lane) + 33 (31 - i)
+                    float2* pk_ = buf + lane;
+                    float2* qk = buf + (31 - lane);
+                    PB_UNROLL for (int i = 0; i < 16; i++) {
+                        const float2 za = pk_[33 * i], zb = qk[33 * (31 - i)];
+                        const float2 p = make_float2(za.x + zb.x, za.y - zb.y), q = make_float2(za.x - zb.x, za.y + zb.y);
+                        const float2 w = make_float2(p.x * p.x + p.y * p.y, q.x * q.x + q.y * q.y);
+                        pk_[33 * i] = w; qk[33 * (31 - i)] = w;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // local peaks over the group, back to unscaled units
+        pkA = pb_warp_max(pkA); pkB = pb_warp_max(pkB);
+        if (lane == 0) { red[wg * 4 + 2] = pkA; red[wg * 4 + 3] = pkB; }
+        // ---- r[t] = E[t] + W^t O[t]: the odd half hands its lags (times W^t) over through its own buffer
+        if (active && wg == 1) {
+            float2* dst = buf + lane;
+            PB_UNROLL for (int q = 0; q < RPL; q++) {
+                if (lane + 32 * q <= B + 1) {
+                    const float2 w = __ldg(tw_in + lane + 32 * q);
+                    const float2 x = v[pb_bitrev(q, LR)];
+                    dst[32 * q] = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+                }
+            }
+        }
+        PB_KS_SYNC();
+        pkA = fmaxf(red[2], red[6]); pkB = fmaxf(red[3], red[7]);
+        pkA = pkA / sA; pkB = pkB / sB;
+        const int slot = 2 * li;
+        const bool actA = active && pkA > 0.0f, actB = active && hasB && pkB > 0.0f;
+        if (active && wg == 0) {
+            const float2* src = buf_other + lane;
+            const float2 o0 = src[0];
+            const float2 e0 = v[0];
+            const float2 a0v = make_float2(e0.x + o0.x, e0.y + o0.y);
+            const float2 ac0 = make_float2(__shfl_sync(PB_FULL_MASK, a0v.x, 0), __shfl_sync(PB_FULL_MASK, a0v.y, 0));
+            const float2 inv0 = make_float2(ac0.x > 0.0f ? 1.0f / ac0.x : 0.0f, ac0.y > 0.0f ? 1.0f / ac0.y : 0.0f);
+            float* ra = racf + (size_t)slot * rstride_g + lane;
+            float* rb = ra + rstride_g;
+            const float* iwp = gm.inv_wr + lane;               // inv_wr[B + 1] = 0
+            PB_UNROLL for (int q = 0; q < RPL; q++) {
+                if (lane + 32 * q <= B + 1) {
+                    const float2 o = src[32 * q], ev = v[pb_bitrev(q, LR)];
+                    const float iw = __ldg(iwp + 32 * q);
+                    float2 r2 = __fmul2_rn(make_float2(ev.x + o.x, ev.y + o.y), __fmul2_rn(inv0, make_float2(iw, iw)));
+                    if (q == 0 && lane == 0) r2 = make_float2(1.0f, 1.0f);
+                    ra[32 * q] = r2.x; rb[32 * q] = r2.y;
+                }
+            }
+        }
+        if (g == 0) {
+            const int mc = gm.max_cand;
+            slot_fr[slot] = actA ? frA : -1;
+            slot_fr[slot + 1] = actB ? frA + 1 : -1;
+            if (!actA) { cand_f[frA * mc] = 0.0f; cand_s[frA * mc] = 0.0f; ncand[frA] = 1; intensity[frA] = 0.0f; }
+            else { const float t = pkA / gpk; intensity[frA] = t > 1.0f ? 1.0f : t; }
+            if (hasB) {
+                if (!actB) { cand_f[(frA + 1) * mc] = 0.0f; cand_s[(frA + 1) * mc] = 0.0f; ncand[frA + 1] = 1; intensity[frA + 1] = 0.0f; }
+                else { const float t = pkB / gpk; intensity[frA + 1] = t > 1.0f ? 1.0f : t; }
+            }
+        }
+        PB_KS_SYNC();     // the halves and the reduction scratch are reused by the next pair
+    }
+}
+#undef PB_KS_SYNC

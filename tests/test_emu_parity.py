@@ -253,3 +253,28 @@ def test_emulated_long_unit_loudness_matches_chained_scan(emu, oracle, monkeypat
         for k, it in enumerate(items):
             src = x if it[0] == 0 else y
             assert abs(out[k] - oracle.lufs(src, it[2], it[5], it[3], it[4])) < 1e-9
+
+
+def test_emulated_split_2048_kernel_on_odd_and_edge_frames(emu, oracle):
+    """The split 2048-point K1 (two 1024-point pipelines per frame pair) on slices whose frame counts are odd (an unpaired last
+    frame: the path where the two frames' power-of-two scales differ most) and whose first / last frames are zero-filled: every
+    frame's strength and frequency against the oracle, tighter than the tolerance gates (a scale applied after the W^n rotation
+    once produced 3 % strength errors on exactly these frames and still passed the 0.5 % F0 gate)."""
+    import prosody_b200 as pb
+    sr = 44100
+    x = speechlike(1, 0.9, sr, seed=31)[0]
+    n = len(x)
+    items = [(0, n, sr, 0.0, 0.1), (0, n, sr, 0.05, 0.33), (0, n, sr, 0.2, 0.565), (0, n, sr, 0.0, None), (0, n, sr, 0.41, 0.9)]
+    r = emu.median_pitch(x, pb.Units.from_list(items), pb.pitch_params(150.0, 600.0), frames=True)
+    counts = np.diff(r["frame_off"])
+    assert (counts % 2 == 1).sum() >= 2
+    for i, it in enumerate(items):
+        o = oracle.pitch_track(x, sr, it[3], it[4], params=oracle.pitch_params(150.0, 600.0))
+        a, b = r["frame_off"][i], r["frame_off"][i + 1]
+        assert b - a == o["n_frames"] and o["geom"].nsampFFT == 2048
+        f = r["frame_f0"][a:b]
+        assert np.array_equal(f > 0, o["frequency"] > 0)
+        both = f > 0
+        assert np.max(np.abs(r["frame_strength"][a:b] - o["strength"])) < 5e-4
+        if both.any():
+            assert np.max(np.abs(f[both] - o["frequency"][both]) / o["frequency"][both]) < 1e-3

@@ -273,6 +273,29 @@ def test_long_unit_loudness_equals_chained_scan(gpu_extractor, oracle, monkeypat
     assert abs(ref[2] - oracle.lufs(x, sr, 44100.0, 3.0, 555.5)) < 1e-9
 
 
+@pytest.mark.parametrize("sr,floor", [(24000, 75.0), (22050, 75.0), (44100, 150.0)])
+def test_split_2048_kernel_on_odd_and_edge_frames(gpu_extractor, oracle, sr, floor):
+    """The split 2048-point K1 (two 1024-point pipelines per frame pair: 24 kHz / 22.05 kHz at 75 Hz, 44.1 kHz at 150 Hz) on many
+    slices with odd frame counts (an unpaired last frame) and zero-filled first / last frames, frame by frame and tighter than the
+    tolerance gates: strengths within 5e-4, frequencies within 1e-3, voicing identical."""
+    import prosody_b200 as pb
+    x = speechlike(1, 3.0, sr, seed=41)[0]
+    n = len(x)
+    items = [(0, n, sr, 0.0, None)] + [(0, n, sr, 0.07 * k, 0.07 * k + 0.2 + 0.013 * k) for k in range(1, 30)]
+    r = gpu_extractor.median_pitch(x, pb.Units.from_list(items), pb.pitch_params(floor, 600.0), frames=True)
+    assert (np.diff(r["frame_off"]) % 2 == 1).sum() >= 5
+    for i, it in enumerate(items):
+        o = oracle.pitch_track(x, sr, it[3], it[4], params=oracle.pitch_params(floor, 600.0))
+        a, b = r["frame_off"][i], r["frame_off"][i + 1]
+        assert b - a == o["n_frames"] and o["geom"].nsampFFT == 2048
+        f = r["frame_f0"][a:b]
+        assert np.array_equal(f > 0, o["frequency"] > 0), i
+        assert np.max(np.abs(r["frame_strength"][a:b] - o["strength"])) < 5e-4, i
+        both = f > 0
+        if both.any():
+            assert np.max(np.abs(f[both] - o["frequency"][both]) / o["frequency"][both]) < 1e-3, i
+
+
 def test_mixed_rate_corpus_in_one_call(gpu_extractor, oracle):
     """BASELINE config 5 in miniature: 16 / 24 / 44.1 kHz files in one batch (three analysis geometries, three meters),
     reference parameters (floor 150, ceiling 600), whole files and slices."""
