@@ -387,8 +387,8 @@ def bench_steps(args, rank, world, local):
                 tr = {}
             log2n = max(8, int(math.ceil(math.log2(g.nsamp_window + g.brent_ixmax + 1))))
             kname = f"pb_pitch_acf_kernel<{log2n}>"
-            if log2n == 11 and g.nsamp_window <= 1024 and g.brent_ixmax + 1 <= 511 and os.environ.get("PB_ACF_SPLIT", "1") != "0":
-                kname = "pb_pitch_acf_split_kernel (N = 2048)"       # two 1024-point pipelines per frame pair
+            if log2n == 11 and g.nsamp_window <= 1024 and g.brent_ixmax + 2 <= 512 and os.environ.get("PB_ACF_SPLIT", "1") != "0":
+                kname = "pb_pitch_acf_split_kernel (N = 2048)"       # two independent 1024-point pipelines per frame pair
             if kname in tr and cfg in ("c2", "c3"):          # captured on this geometry
                 traffic = tr[kname]["bytes_per_frame"] * frames_per_launch
             roof = dict(bound="fp32", kernel=kname, achieved=achieved, peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=traffic,

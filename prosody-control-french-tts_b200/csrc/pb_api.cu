@@ -449,11 +449,18 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
     typedef PbFftCfg<LOG2N> C;
     size_t smem = (size_t)C::GROUPS_PER_CTA * ((C::BUF + 8 * C::G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + C::GROUPS_PER_CTA * sizeof(pbMbar);
     const int threads = C::WARPS_PER_CTA * 32;
-    // N = 2048 with a window of at most 1024 samples and lags below 512 (24 kHz / 22.05 kHz at a 75 Hz floor): two independent
-    // 1024-point pipelines per pair (pb_pitch_acf_split_kernel); PB_ACF_SPLIT=0 keeps the general 32 x 32 x 2 kernel
+    // N = 2048 with a window of at most 1024 samples and lags below 512 (24 kHz / 22.05 kHz at a 75 Hz floor, 44.1 kHz at 150 Hz):
+    // two independent 1024-point pipelines per pair (pb_pitch_acf_split_kernel<2>).  PB_ACF_SPLIT=0 keeps the general kernel;
+    // PB_ACF_SPLIT=4 also runs N = 4096 (44.1 kHz at 75 Hz) as FOUR pipelines — measured no faster than the general 32 x 32 x 4
+    // kernel (8.05 against 8.08 ms for 599 k frames: two of the four pipelines read each other's spectra, five group barriers per
+    // pair), so it is not the default.
     static const int acf_split = [] { const char* e = getenv("PB_ACF_SPLIT"); return e ? atoi(e) : 1; }();
-    const bool split = LOG2N == 11 && acf_split && gm.nw <= 1024 && gm.brent_ixmax + 1 <= 511 && PB_WPC == 4;
-    if (split) smem = (size_t)(PB_WPC / 2) * ((2 * (1024 + 32 + 8) + 16) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + (PB_WPC / 2) * sizeof(pbMbar);
+    constexpr int NP = LOG2N == 11 ? 2 : (LOG2N == 12 ? 4 : 0);
+    const bool split = NP != 0 && (NP == 2 ? acf_split != 0 : acf_split == 4) && gm.nw <= C::N / 2 && gm.brent_ixmax + 2 <= (NP == 2 ? 512 : 1024) && PB_WPC == 4;
+    if (split) {
+        const int groups = PB_WPC / NP > 0 ? PB_WPC / NP : 1;
+        smem = (size_t)groups * ((NP * (1024 + 32 + 8) + 8 * NP) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t)) + groups * sizeof(pbMbar);
+    }
     static const int acf_ctas = [] { const char* e = getenv("PB_ACF_CTAS"); return e ? atoi(e) : 0; }();
     static const int acf_wsync = [] { const char* e = getenv("PB_ACF_WSYNC"); return e ? atoi(e) : 1; }();     // measured 3 % faster than named barriers
     auto kfn = pb_pitch_acf_kernel<LOG2N, C::MIN_CTAS, false>;
@@ -461,7 +468,7 @@ int launch_frames(PbHandle* h, const int16_t* d_pcm, const PbUnitDev* d_units, c
         if (acf_ctas == 5) kfn = acf_wsync ? pb_pitch_acf_kernel<LOG2N, 5, true> : pb_pitch_acf_kernel<LOG2N, 5, false>;
         else if (acf_wsync) kfn = pb_pitch_acf_kernel<LOG2N, C::MIN_CTAS, true>;
     }
-    if constexpr (LOG2N == 11) { if (split) kfn = pb_pitch_acf_split_kernel<C::MIN_CTAS>; }
+    if constexpr (NP != 0) { if (split) kfn = pb_pitch_acf_split_kernel<NP, C::MIN_CTAS>; }
     static const int cand_ctas = [] { const char* e = getenv("PB_CAND_CTAS"); return e ? atoi(e) : 8; }();
     auto cfn = cand_ctas == 10 ? pb_pitch_cand_kernel<10> : cand_ctas == 12 ? pb_pitch_cand_kernel<12> : pb_pitch_cand_kernel<8>;
     int per_sm = 2;

@@ -538,41 +538,50 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
 }
 #undef PB_K1_SYNC
 
-// ------------------------------------------------------------------------------------------------ K1 at 2048 points, split
-// 24 kHz and 22.05 kHz at a 75 Hz floor (BASELINE configs 3 and 4) need a 2048-point transform, but their window fills less than
-// half of it (958 / 880 samples) and fewer than a quarter of the lags are read (481 / 442).  Both facts prune a radix-2 stage:
-//   * zero-padded input: X[2k] = DFT_1024(x)[k] and X[2k+1] = DFT_1024(x[n] W^n)[k], W = exp(-2 pi i / 2048) — the first
-//     decimation-in-frequency stage has nothing to add;
-//   * lags below 1024 only: r[t] = E[t] + W^t O[t] with E, O the 1024-point transforms of the even- and odd-indexed power
-//     spectrum — and those are exactly what the two halves of the first transform produce (the conjugate partner of an even bin is
-//     an even bin, of an odd bin an odd bin: j <-> 1024 - j and j <-> 1023 - j).
-// So a pair of frames is TWO independent 1024-point pipelines — one warp each, the register-blocked radix-32 x 32 code of the
-// 1024-point kernel with warp-level synchronisation — that meet twice: when the window is written (every sample goes to both
-// buffers, to the second one times W^n) and when the lags are combined (486 complex multiply-adds instead of a 2048-point
-// radix-2 pass through shared memory).  The general kernel above runs N = 2048 as 32 x 32 x 2 with two warps sharing one buffer
-// and a named barrier around every pass; it stays for geometries whose window or lag range exceeds 1024.
-template <int MINB>
-__global__ void __launch_bounds__(PB_WPC * 32, MINB)
+// ------------------------------------------------------------------------------------------------ K1 at 2048 / 4096 points, split
+// 24 kHz and 22.05 kHz at a 75 Hz floor (BASELINE configs 3 and 4) need a 2048-point transform and 44.1 kHz a 4096-point one, but
+// their windows fill less than half of it (958 / 880 / 1764 samples) and fewer than a quarter of the lags are read (481 / 442 /
+// 884).  With N = 1024 NP (NP = 2 or 4) and W = exp(-2 pi i / N) both facts prune radix-2 stages:
+//   * zero-padded input: the bins k = NP j + q are a 1024-point transform of their own,
+//         X[NP j + q] = DFT_1024(y_q)[j],   y_q[n] = W^(n q) sum_{m < NP/2} x[n + 1024 m] exp(-2 pi i m q / NP),
+//     (NP = 2: y_q = x W^(nq); NP = 4: y_q = W^(nq) (x[n] + (-i)^q x[n + 1024]));
+//   * lags below 1024 only:  r[t] = sum_q W^(q t) DFT_1024(P_q)[t],  P_q[j] = P[NP j + q] — the power spectrum of exactly those bins.
+// So a pair of frames is NP independent 1024-point pipelines — one warp each, the register-blocked radix-32 x 32 code of the
+// 1024-point kernel — that meet three times: when the window is written (every sample goes to all NP buffers, rotated), at the
+// power spectrum (the conjugate partner of bin NP j + q is bin NP (1023 - j) + (NP - q): the q = 0 and q = NP/2 pipelines pair
+// inside their own buffer, the others read their partner's; every lane computes the 32 power values of its own column straight
+// into the registers the second transform's first pass wants, so nothing is written back) and when the lags are combined
+// (NP - 1 complex multiply-adds per lag instead of log2 NP radix-2 passes through shared memory).
+// The general kernel above runs these sizes as 32 x 32 x NP with NP warps sharing one buffer and a named barrier around every
+// pass; it stays for geometries whose window exceeds N/2 or whose lag range exceeds 1024.  Measured (599 k frames): NP = 2 3.94 ->
+// 3.24 ms (24 kHz), 3.86 -> 3.10 ms (22.05 kHz): the default at N = 2048.  NP = 4 8.08 -> 8.05 ms (44.1 kHz): two of its four
+// pipelines read each other's spectra and a pair takes five group barriers — no gain, so N = 4096 keeps the general kernel unless
+// PB_ACF_SPLIT=4 asks for this one.
+// The power-of-two frame scales must be applied BEFORE the rotation by W^(nq), which mixes the two frames' components.
+template <int NP, int MINB>
+__global__ void __launch_bounds__((NP > PB_WPC ? NP : PB_WPC) * 32, MINB)
 pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict__ units, const int32_t* __restrict__ pair_off,
                           const int4* __restrict__ pairpos, PbPitchGeomDev gm, int item0, int n_items, int rstride_g,
                           float* __restrict__ racf, long long* __restrict__ slot_fr,
                           float* __restrict__ cand_f, float* __restrict__ cand_s, uint8_t* __restrict__ ncand, float* __restrict__ intensity) {
-    constexpr int R = 32, LR = 5, NH = 1024, G = 2, GT = 64;
-    constexpr int BUFH = NH + (NH >> 5) + 8;            // float2 slots of one half (skew padding as in the 1024-point kernel)
-    constexpr int GROUPS = PB_WPC / G;
-    constexpr int RPL = 16;                             // rows of 32 lags a lane may have to deliver (lags <= 511)
+    constexpr int R = 32, LR = 5, NH = 1024, G = NP, GT = 32 * NP;
+    constexpr int BUFH = NH + (NH >> 5) + 8;            // float2 slots of one pipeline's buffer (skew padding as in the 1024-point kernel)
+    constexpr int WARPS = NP > PB_WPC ? NP : PB_WPC;
+    constexpr int GROUPS = WARPS / G;
     PB_DYN_SMEM(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int group = warp / G, wg = warp % G;
+    const int group = warp / G, wg = warp % G;          // wg = q: the residue class of this warp's bins
     const int g = wg * 32 + lane;                       // thread in group
     const int bar_id = 1 + group;
 #define PB_KS_SYNC() pb_group_sync<G>(bar_id)
-    const size_t group_bytes = (size_t)(2 * BUFH + 8 * G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t);
+    const size_t group_bytes = (size_t)(NP * BUFH + 8 * G) * sizeof(float2) + (size_t)gm.pre_cap * sizeof(int16_t);
     unsigned char* gbase = smem_raw + (size_t)group * group_bytes;
-    float2* buf = (float2*)gbase + wg * BUFH;           // this warp's half
-    float2* buf_other = (float2*)gbase + (wg ^ 1) * BUFH;
-    float* red = (float*)((float2*)gbase + 2 * BUFH);   // [G][4] floats / [G][6] ints
-    int16_t* pre = (int16_t*)((float2*)gbase + 2 * BUFH + 8 * G);
+    float2* const bufs = (float2*)gbase;                // NP buffers
+    float2* buf = bufs + wg * BUFH;                     // this warp's
+    const int wq = (NP - wg) % NP;                      // the pipeline that holds this one's conjugate partners
+    const float2* buf_partner = bufs + wq * BUFH;
+    float* red = (float*)(bufs + NP * BUFH);            // [G][4] floats / [G][6] ints
+    int16_t* pre = (int16_t*)(bufs + NP * BUFH + 8 * G);
     pbMbar* mbar = (pbMbar*)(smem_raw + (size_t)GROUPS * group_bytes) + group;
     if (g == 0) pb_mbar_init(mbar, 1);
     pb_mbar_init_fence();
@@ -580,6 +589,7 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
     unsigned phase = 0;
     const int B = gm.brent_ixmax;
     const int nw = gm.nw;
+    constexpr int RPL = NP == 2 ? 16 : 32;              // rows of 32 lags a lane may have to deliver (lags 0 .. B + 1 < 32 RPL)
     const int pk_lo = max(0, gm.half_nw - gm.half_period), pk_n = min(nw, gm.half_nw + gm.half_period) - pk_lo;
     const int mean_n0 = gm.half_nw - gm.nsamp_period;
     const int mean_len = 2 * gm.nsamp_period;
@@ -588,7 +598,7 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
     const int span_len = span_hi - span_lo;
     const float mean_scale = (float)(1.0 / (32768.0 * (double)mean_len));
     const bool fuse_ok = mean_n0 >= 0 && mean_n0 + mean_len <= nw;
-    const float2* __restrict__ tw_in = gm.tw_b + NH;    // W^n, n < 1024
+    const float2* __restrict__ tw_q = gm.tw_b;          // tw_q[q * 1024 + n] = W^(n q)
 
     const int n_groups = gridDim.x * GROUPS;
     const int per_group = (n_items + n_groups - 1) / n_groups;
@@ -602,6 +612,20 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
     int u_pair_off = 0, u_nframes = 0, u_pmin = 0, u_pmax1 = 0;
     long long u_frame_off = 0;
     float gpk = 0.0f;
+
+    // one windowed, scaled sample pair (x = a + i b at n, and at n + 1024 when NP = 4) into the NP buffers, rotated
+    auto scatter = [&](int n, float2 x0, float2 x1) {
+        bufs[pb_pad5(n)] = NP == 2 ? x0 : make_float2(x0.x + x1.x, x0.y + x1.y);
+        PB_UNROLL for (int q = 1; q < NP; q++) {
+            float2 y;
+            if (NP == 2) y = x0;
+            else if (q == 1) y = make_float2(x0.x + x1.y, x0.y - x1.x);          // x0 - i x1
+            else if (q == 2) y = make_float2(x0.x - x1.x, x0.y - x1.y);          // x0 - x1
+            else y = make_float2(x0.x - x1.y, x0.y + x1.x);                      // x0 + i x1
+            const float2 tw = __ldg(tw_q + q * NH + n);
+            bufs[q * BUFH + pb_pad5(n)] = make_float2(y.x * tw.x - y.y * tw.y, y.x * tw.y + y.y * tw.x);
+        }
+    };
 
     for (int li = it_begin; li < it_end; li++) {
         const int item = item0 + li;
@@ -634,7 +658,7 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
         const long long loA = (long long)u_pmin - pos.start0, hiA = (long long)u_pmax1 - pos.start0;
         const bool interior = fuse_ok && hasB && loA <= span_lo && hiA - pos.hop >= span_hi;
         if (interior) {
-            // ---- exact integer statistics of the local-mean span (see the general kernel), then the scaled window into BOTH halves
+            // ---- exact integer statistics of the local-mean span (see the general kernel), then the scaled window into the buffers
             int s0, s1, mn0, mx0, mn1, mx1;
             {
                 int sum[2]; unsigned vmn[2], vmx[2];
@@ -665,8 +689,11 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
                 int* redi = (int*)red;
                 if (lane == 0) { redi[wg * 6 + 0] = s0; redi[wg * 6 + 1] = s1; redi[wg * 6 + 2] = mn0; redi[wg * 6 + 3] = mx0; redi[wg * 6 + 4] = mn1; redi[wg * 6 + 5] = mx1; }
                 PB_KS_SYNC();
-                s0 = redi[0] + redi[6]; s1 = redi[1] + redi[7];
-                mn0 = min(redi[2], redi[8]); mx0 = max(redi[3], redi[9]); mn1 = min(redi[4], redi[10]); mx1 = max(redi[5], redi[11]);
+                s0 = 0; s1 = 0;
+                PB_UNROLL for (int k = 0; k < G; k++) {
+                    s0 += redi[k * 6 + 0]; s1 += redi[k * 6 + 1];
+                    mn0 = min(mn0, redi[k * 6 + 2]); mx0 = max(mx0, redi[k * 6 + 3]); mn1 = min(mn1, redi[k * 6 + 4]); mx1 = max(mx1, redi[k * 6 + 5]);
+                }
             }
             const float q15 = 1.0f / 32768.0f;
             const float meanA = (float)s0 * mean_scale, meanB = (float)s1 * mean_scale;
@@ -677,18 +704,17 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
             const float2 q15s = make_float2(q15 * sA, q15 * sB), nms = make_float2(-meanA * sA, -meanB * sB);
             any_signal = mA > 0.0f || mB > 0.0f;
             const int16_t* pa = sm + sb0; const int16_t* pb = sm + sb1;
-            float2* b0 = (float2*)gbase; float2* b1 = b0 + BUFH;
-            for (int n = g; n < nw; n += GT) {
+            auto windowed = [&](int n) -> float2 {
+                if (n >= nw) return make_float2(0.0f, 0.0f);
                 const float w0 = __ldg(gm.window + n);
                 const float2 x = __fmul2_rn(__ffma2_rn(make_float2((float)pa[n], (float)pb[n]), q15s, nms), make_float2(w0, w0));
                 if ((unsigned)(n - pk_lo) < (unsigned)pk_n) { pkA = fmaxf(pkA, fabsf(x.x)); pkB = fmaxf(pkB, fabsf(x.y)); }
-                const float2 tw = __ldg(tw_in + n);
-                b0[pb_pad5(n)] = x;
-                b1[pb_pad5(n)] = make_float2(x.x * tw.x - x.y * tw.y, x.x * tw.y + x.y * tw.x);
-            }
-            for (int n = nw + g; n < NH; n += GT) { b0[pb_pad5(n)] = make_float2(0.0f, 0.0f); b1[pb_pad5(n)] = make_float2(0.0f, 0.0f); }
+                return x;
+            };
+            for (int n = g; n < NH; n += GT) scatter(n, windowed(n), NP > 2 ? windowed(n + NH) : make_float2(0.0f, 0.0f));
         } else {
-            // ---- frames that Praat zero-fills beyond the file, or a unit with an odd frame count: masked samples
+            // ---- frames that Praat zero-fills beyond the file, or a unit with an odd frame count: masked samples; two sweeps, the
+            //      magnitudes first (the scales are wanted before the rotation), then the scaled window into the buffers
             float mxA = 0.0f, mxB = 0.0f;
             int nlo[2], nhi[2], sb[2]; float lmean[2];
             PB_UNROLL for (int f = 0; f < 2; f++) {
@@ -708,9 +734,8 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
             if (!hasB) { nlo[1] = 0; nhi[1] = 0; sb[1] = sb[0]; }
             const float2 nmean = make_float2(-lmean[0], -lmean[1]), q15 = make_float2(1.0f / 32768.0f, 1.0f / 32768.0f);
             const float hb = hasB ? 1.0f : 0.0f;
-            // two sweeps: the magnitudes first (the scales must be applied BEFORE the second half's samples are rotated by W^n, which
-            // mixes the two frames' components), then the scaled window into both halves
             auto windowed = [&](int n) -> float2 {
+                if (n >= nw) return make_float2(0.0f, 0.0f);
                 const float w = __ldg(&gm.window[n]);
                 const int sa = (n >= nlo[0] && n < nhi[0]) ? (int)sm[sb[0] + n] : 0;
                 const int sbv = (n >= nlo[1] && n < nhi[1]) ? (int)sm[sb[1] + n] : 0;
@@ -725,22 +750,16 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
             mxA = pb_warp_max(mxA); mxB = pb_warp_max(mxB);
             if (lane == 0) { red[wg * 4 + 0] = mxA; red[wg * 4 + 1] = mxB; }
             PB_KS_SYNC();
-            mxA = fmaxf(red[0], red[4]); mxB = fmaxf(red[1], red[5]);
+            PB_UNROLL for (int k = 0; k < G; k++) { mxA = fmaxf(mxA, red[k * 4 + 0]); mxB = fmaxf(mxB, red[k * 4 + 1]); }
             sA = mxA > 0.0f ? __int_as_float((254 - ((__float_as_int(mxA) >> 23) & 0xff)) << 23) : 1.0f;
             sB = mxB > 0.0f ? __int_as_float((254 - ((__float_as_int(mxB) >> 23) & 0xff)) << 23) : 1.0f;
             pkA *= sA; pkB *= sB;
             const float2 sc = make_float2(sA, sB);
-            float2* b0 = (float2*)gbase; float2* b1 = b0 + BUFH;
-            for (int n = g; n < nw; n += GT) {
-                const float2 x = __fmul2_rn(windowed(n), sc);
-                const float2 tw = __ldg(tw_in + n);
-                b0[pb_pad5(n)] = x;
-                b1[pb_pad5(n)] = make_float2(x.x * tw.x - x.y * tw.y, x.x * tw.y + x.y * tw.x);
-            }
-            for (int n = nw + g; n < NH; n += GT) { b0[pb_pad5(n)] = make_float2(0.0f, 0.0f); b1[pb_pad5(n)] = make_float2(0.0f, 0.0f); }
+            for (int n = g; n < NH; n += GT)
+                scatter(n, __fmul2_rn(windowed(n), sc), NP > 2 ? __fmul2_rn(windowed(n + NH), sc) : make_float2(0.0f, 0.0f));
             any_signal = mxA > 0.0f || mxB > 0.0f;
         }
-        PB_KS_SYNC();                       // both halves hold the windowed pair; the staging buffer is free
+        PB_KS_SYNC();                       // every buffer holds the windowed pair; the staging buffer is free
         const bool active = !global_silent && any_signal;
         if (li + 1 < it_end) {
             if (item + 1 >= u_next_end) { do { u_next++; u_next_end = pair_off[u_next + 1]; } while (item + 1 >= u_next_end); }
@@ -758,27 +777,12 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
             asm volatile("" : "+r"(step));
             int pass = step & 1;
             asm volatile("" : "+r"(pass));
-            {
-                const float2* src = buf + lane;                       // i = lane + 32 t  ->  lane + 33 t
-                PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * 33];
-            }
-            if (pass) {
-                const float2* tw = gm.tw_a + lane;
-                PB_UNROLL for (int t = 1; t < R; t++) {
-                    const float2 w = __ldg(tw + t * R);
-                    const float2 x = v[t];
-                    v[t] = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(x.x, x.x), w));
-                }
-            }
-            __syncwarp();
-            pb_dft<R>(v);
-            if (step == 3) break;                                     // the lags stay in registers
-            if (pass) { float2* dst = buf + lane; PB_UNROLL for (int t = 0; t < R; t++) dst[t * 33] = v[pb_bitrev(t, LR)]; }
-            else { float2* dst = buf + 33 * lane; PB_UNROLL for (int t = 0; t < R; t++) dst[t] = v[pb_bitrev(t, LR)]; }
-            __syncwarp();
-            if (step == 1) {
-                // ---- power spectra of both frames, packed again as P_a + i P_b; this half holds the even (wg = 0) or the odd
-                //      (wg = 1) bins of the 2048-point spectrum: bin j pairs with 1024 - j, respectively 1023 - j
+            // ---- step 2 starts from the power spectra of both frames, packed as P_a + i P_b.  Bin j = lane + 32 i of pipeline q pairs
+            //      with bin 1023 - j of pipeline NP - q (q > 0), with bin (1024 - j) mod 1024 of its own (q = 0).
+            constexpr bool CROSS = NP > 2;
+            const bool own_pair = wg == 0 || 2 * wg == NP;            // the partner bins sit in this warp's own buffer
+            if (step == 2 && own_pair) {
+                // in place, one evaluation per PAIR of bins (written to both), as in the 1024-point kernel
                 if (wg == 0) {
                     const float2* pk_ = buf + lane;
                     float2* qk = buf + (lane ? 32 - lane : 33);
@@ -808,31 +812,65 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
                 }
                 __syncwarp();
             }
+            if (!(CROSS && step == 2 && !own_pair)) {
+                const float2* src = buf + lane;                       // i = lane + 32 t  ->  lane + 33 t
+                PB_UNROLL for (int t = 0; t < R; t++) v[t] = src[t * 33];
+            } else {
+                // the partner bins sit in ANOTHER pipeline's buffer (which that warp must not lose to an in-place update): every lane
+                // computes the 32 power values of its own column straight into the registers of the first pass
+                const float2* own = buf + lane;
+                const float2* qk = buf_partner + (31 - lane);
+                PB_UNROLL for (int i = 0; i < R; i++) {
+                    const float2 za = own[33 * i], zb = qk[33 * (31 - i)];
+                    const float2 p = make_float2(za.x + zb.x, za.y - zb.y), q = make_float2(za.x - zb.x, za.y + zb.y);
+                    v[i] = make_float2(p.x * p.x + p.y * p.y, q.x * q.x + q.y * q.y);
+                }
+            }
+            // every partner has been read before any buffer is written again (the stores of this step)
+            if (CROSS && step == 2) PB_KS_SYNC();
+            if (pass) {
+                const float2* tw = gm.tw_a + lane;
+                PB_UNROLL for (int t = 1; t < R; t++) {
+                    const float2 w = __ldg(tw + t * R);
+                    const float2 x = v[t];
+                    v[t] = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), __fmul2_rn(make_float2(x.x, x.x), w));
+                }
+            }
+            __syncwarp();
+            pb_dft<R>(v);
+            if (step == 3) break;                                     // the lags stay in registers
+            if (pass) { float2* dst = buf + lane; PB_UNROLL for (int t = 0; t < R; t++) dst[t * 33] = v[pb_bitrev(t, LR)]; }
+            else { float2* dst = buf + 33 * lane; PB_UNROLL for (int t = 0; t < R; t++) dst[t] = v[pb_bitrev(t, LR)]; }
+            // the first transform's spectrum is read across pipelines when NP > 2
+            if (NP > 2 && step == 1) PB_KS_SYNC(); else __syncwarp();
         }
         // local peaks over the group, back to unscaled units
         pkA = pb_warp_max(pkA); pkB = pb_warp_max(pkB);
         if (lane == 0) { red[wg * 4 + 2] = pkA; red[wg * 4 + 3] = pkB; }
-        // ---- r[t] = E[t] + W^t O[t]: the odd half hands its lags (times W^t) over through its own buffer
-        if (active && wg == 1) {
+        // ---- r[t] = sum_q W^(q t) F_q[t]: the pipelines q > 0 hand their lags (rotated) over through their own buffers
+        if (active && wg > 0) {
             float2* dst = buf + lane;
+            const float2* tw = tw_q + wg * NH + lane;
             PB_UNROLL for (int q = 0; q < RPL; q++) {
-                if (lane + 32 * q <= B + 1) {
-                    const float2 w = __ldg(tw_in + lane + 32 * q);
+                if (32 * q <= B + 1) {
+                    const float2 w = __ldg(tw + 32 * q);
                     const float2 x = v[pb_bitrev(q, LR)];
                     dst[32 * q] = make_float2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
                 }
             }
         }
         PB_KS_SYNC();
-        pkA = fmaxf(red[2], red[6]); pkB = fmaxf(red[3], red[7]);
+        PB_UNROLL for (int k = 0; k < G; k++) { if (k != wg) { pkA = fmaxf(pkA, red[k * 4 + 2]); pkB = fmaxf(pkB, red[k * 4 + 3]); } }
         pkA = pkA / sA; pkB = pkB / sB;
         const int slot = 2 * li;
         const bool actA = active && pkA > 0.0f, actB = active && hasB && pkB > 0.0f;
         if (active && wg == 0) {
-            const float2* src = buf_other + lane;
-            const float2 o0 = src[0];
-            const float2 e0 = v[0];
-            const float2 a0v = make_float2(e0.x + o0.x, e0.y + o0.y);
+            auto lag = [&](int q) -> float2 {
+                float2 a = v[pb_bitrev(q, LR)];
+                PB_UNROLL for (int k = 1; k < NP; k++) { const float2 o = bufs[k * BUFH + lane + 32 * q]; a.x += o.x; a.y += o.y; }
+                return a;
+            };
+            const float2 a0v = lag(0);
             const float2 ac0 = make_float2(__shfl_sync(PB_FULL_MASK, a0v.x, 0), __shfl_sync(PB_FULL_MASK, a0v.y, 0));
             const float2 inv0 = make_float2(ac0.x > 0.0f ? 1.0f / ac0.x : 0.0f, ac0.y > 0.0f ? 1.0f / ac0.y : 0.0f);
             float* ra = racf + (size_t)slot * rstride_g + lane;
@@ -840,9 +878,8 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
             const float* iwp = gm.inv_wr + lane;               // inv_wr[B + 1] = 0
             PB_UNROLL for (int q = 0; q < RPL; q++) {
                 if (lane + 32 * q <= B + 1) {
-                    const float2 o = src[32 * q], ev = v[pb_bitrev(q, LR)];
                     const float iw = __ldg(iwp + 32 * q);
-                    float2 r2 = __fmul2_rn(make_float2(ev.x + o.x, ev.y + o.y), __fmul2_rn(inv0, make_float2(iw, iw)));
+                    float2 r2 = __fmul2_rn(lag(q), __fmul2_rn(inv0, make_float2(iw, iw)));
                     if (q == 0 && lane == 0) r2 = make_float2(1.0f, 1.0f);
                     ra[32 * q] = r2.x; rb[32 * q] = r2.y;
                 }
@@ -859,7 +896,7 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
                 else { const float t = pkB / gpk; intensity[frA + 1] = t > 1.0f ? 1.0f : t; }
             }
         }
-        PB_KS_SYNC();     // the halves and the reduction scratch are reused by the next pair
+        PB_KS_SYNC();     // the buffers and the reduction scratch are reused by the next pair
     }
 }
 #undef PB_KS_SYNC

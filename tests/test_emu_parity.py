@@ -255,8 +255,9 @@ def test_emulated_long_unit_loudness_matches_chained_scan(emu, oracle, monkeypat
             assert abs(out[k] - oracle.lufs(src, it[2], it[5], it[3], it[4])) < 1e-9
 
 
-def test_emulated_split_2048_kernel_on_odd_and_edge_frames(emu, oracle):
-    """The split 2048-point K1 (two 1024-point pipelines per frame pair) on slices whose frame counts are odd (an unpaired last
+@pytest.mark.parametrize("floor,nfft", [(150.0, 2048), (75.0, 4096)])
+def test_emulated_split_2048_kernel_on_odd_and_edge_frames(emu, oracle, floor, nfft):
+    """The split K1 (two / four 1024-point pipelines per frame pair at 2048 / 4096 points) on slices whose frame counts are odd (an unpaired last
     frame: the path where the two frames' power-of-two scales differ most) and whose first / last frames are zero-filled: every
     frame's strength and frequency against the oracle, tighter than the tolerance gates (a scale applied after the W^n rotation
     once produced 3 % strength errors on exactly these frames and still passed the 0.5 % F0 gate)."""
@@ -265,16 +266,49 @@ def test_emulated_split_2048_kernel_on_odd_and_edge_frames(emu, oracle):
     x = speechlike(1, 0.9, sr, seed=31)[0]
     n = len(x)
     items = [(0, n, sr, 0.0, 0.1), (0, n, sr, 0.05, 0.33), (0, n, sr, 0.2, 0.565), (0, n, sr, 0.0, None), (0, n, sr, 0.41, 0.9)]
-    r = emu.median_pitch(x, pb.Units.from_list(items), pb.pitch_params(150.0, 600.0), frames=True)
+    if nfft == 4096:
+        items = items[1:]                              # 0.1 s is shorter than three periods of 75 Hz plus a frame
+    r = emu.median_pitch(x, pb.Units.from_list(items), pb.pitch_params(floor, 600.0), frames=True)
     counts = np.diff(r["frame_off"])
-    assert (counts % 2 == 1).sum() >= 2
+    assert (counts % 2 == 1).sum() >= 1
     for i, it in enumerate(items):
-        o = oracle.pitch_track(x, sr, it[3], it[4], params=oracle.pitch_params(150.0, 600.0))
+        o = oracle.pitch_track(x, sr, it[3], it[4], params=oracle.pitch_params(floor, 600.0))
         a, b = r["frame_off"][i], r["frame_off"][i + 1]
-        assert b - a == o["n_frames"] and o["geom"].nsampFFT == 2048
+        assert b - a == o["n_frames"] and o["geom"].nsampFFT == nfft
         f = r["frame_f0"][a:b]
         assert np.array_equal(f > 0, o["frequency"] > 0)
         both = f > 0
         assert np.max(np.abs(r["frame_strength"][a:b] - o["strength"])) < 5e-4
         if both.any():
             assert np.max(np.abs(f[both] - o["frequency"][both]) / o["frequency"][both]) < 1e-3
+
+
+def test_emulated_four_pipeline_split_in_a_subprocess(oracle):
+    """PB_ACF_SPLIT=4 (N = 4096 as four 1024-point pipelines; not the default: no faster than the general kernel on the GPU) keeps
+    working: the switch is read once per process, so this case runs the emulated library in a process of its own."""
+    import subprocess, sys, os
+    from pathlib import Path
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+import build_emu, prosody_b200 as pb
+from conftest import speechlike
+from oracle import oracle as O
+ex = pb.Extractor(0, lib=pb._native.load(build_emu.build()))
+sr = 44100
+x = speechlike(1, 0.6, sr, seed=31)[0]
+items = [(0, len(x), sr, 0.05, 0.33), (0, len(x), sr, 0.0, None)]
+r = ex.median_pitch(x, pb.Units.from_list(items), pb.pitch_params(75.0, 600.0), frames=True)
+for i, it in enumerate(items):
+    o = O.pitch_track(x, sr, it[3], it[4], params=O.pitch_params(75.0, 600.0))
+    a, b = r["frame_off"][i], r["frame_off"][i + 1]
+    assert b - a == o["n_frames"] and o["geom"].nsampFFT == 4096
+    f = r["frame_f0"][a:b]
+    assert np.array_equal(f > 0, o["frequency"] > 0)
+    assert np.max(np.abs(r["frame_strength"][a:b] - o["strength"])) < 5e-4
+print("ok")
+"""
+    root = Path(__file__).resolve().parent.parent
+    env = dict(os.environ, PB_ACF_SPLIT="4")
+    res = subprocess.run([sys.executable, "-c", code % (str(root), str(root / "tests"), str(root / "tests" / "simt_emu"))], env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]

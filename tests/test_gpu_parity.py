@@ -273,9 +273,9 @@ def test_long_unit_loudness_equals_chained_scan(gpu_extractor, oracle, monkeypat
     assert abs(ref[2] - oracle.lufs(x, sr, 44100.0, 3.0, 555.5)) < 1e-9
 
 
-@pytest.mark.parametrize("sr,floor", [(24000, 75.0), (22050, 75.0), (44100, 150.0)])
+@pytest.mark.parametrize("sr,floor", [(24000, 75.0), (22050, 75.0), (44100, 150.0), (44100, 75.0), (48000, 75.0)])
 def test_split_2048_kernel_on_odd_and_edge_frames(gpu_extractor, oracle, sr, floor):
-    """The split 2048-point K1 (two 1024-point pipelines per frame pair: 24 kHz / 22.05 kHz at 75 Hz, 44.1 kHz at 150 Hz) on many
+    """The split K1 (two 1024-point pipelines per frame pair: 24 kHz / 22.05 kHz at 75 Hz, 44.1 kHz at 150 Hz; 44.1 / 48 kHz at 75 Hz run the general 4096-point kernel and are held to the same frame-by-frame bar) on many
     slices with odd frame counts (an unpaired last frame) and zero-filled first / last frames, frame by frame and tighter than the
     tolerance gates: strengths within 5e-4, frequencies within 1e-3, voicing identical."""
     import prosody_b200 as pb
@@ -287,7 +287,7 @@ def test_split_2048_kernel_on_odd_and_edge_frames(gpu_extractor, oracle, sr, flo
     for i, it in enumerate(items):
         o = oracle.pitch_track(x, sr, it[3], it[4], params=oracle.pitch_params(floor, 600.0))
         a, b = r["frame_off"][i], r["frame_off"][i + 1]
-        assert b - a == o["n_frames"] and o["geom"].nsampFFT == 2048
+        assert b - a == o["n_frames"] and o["geom"].nsampFFT == (4096 if (sr >= 44100 and floor == 75.0) else 2048)
         f = r["frame_f0"][a:b]
         assert np.array_equal(f > 0, o["frequency"] > 0), i
         assert np.max(np.abs(r["frame_strength"][a:b] - o["strength"])) < 5e-4, i
