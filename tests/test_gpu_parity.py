@@ -296,6 +296,30 @@ def test_split_2048_kernel_on_odd_and_edge_frames(gpu_extractor, oracle, sr, flo
             assert np.max(np.abs(f[both] - o["frequency"][both]) / o["frequency"][both]) < 1e-3, i
 
 
+@pytest.mark.parametrize("sr,floor,nfft", [(8000, 150.0, 256), (8000, 75.0, 512), (16000, 150.0, 512), (16000, 75.0, 1024), (32000, 75.0, 2048),
+                                           (96000, 75.0, 8192)])
+def test_every_fft_geometry_frame_by_frame_on_slices(gpu_extractor, oracle, sr, floor, nfft):
+    """The same frame-by-frame bar as the split-kernel test for every other transform size of K1 (256 ... 8192 points; 32 kHz at 75 Hz
+    is a 2048-point geometry whose window exceeds 1024 samples, i.e. the general two-warp kernel): slices with odd frame counts and
+    zero-filled first / last frames, strengths within 5e-4, frequencies within 1e-3, voicing identical."""
+    import prosody_b200 as pb
+    x = speechlike(1, 2.0, sr, seed=43)[0]
+    n = len(x)
+    items = [(0, n, sr, 0.0, None)] + [(0, n, sr, 0.09 * k, 0.09 * k + 0.2 + 0.017 * k) for k in range(1, 16)]
+    r = gpu_extractor.median_pitch(x, pb.Units.from_list(items), pb.pitch_params(floor, 600.0), frames=True)
+    assert (np.diff(r["frame_off"]) % 2 == 1).sum() >= 3
+    for i, it in enumerate(items):
+        o = oracle.pitch_track(x, sr, it[3], it[4], params=oracle.pitch_params(floor, 600.0))
+        a, b = r["frame_off"][i], r["frame_off"][i + 1]
+        assert b - a == o["n_frames"] and o["geom"].nsampFFT == nfft
+        f = r["frame_f0"][a:b]
+        assert np.array_equal(f > 0, o["frequency"] > 0), i
+        assert np.max(np.abs(r["frame_strength"][a:b] - o["strength"])) < 5e-4, i
+        both = f > 0
+        if both.any():
+            assert np.max(np.abs(f[both] - o["frequency"][both]) / o["frequency"][both]) < 1e-3, i
+
+
 def test_mixed_rate_corpus_in_one_call(gpu_extractor, oracle):
     """BASELINE config 5 in miniature: 16 / 24 / 44.1 kHz files in one batch (three analysis geometries, three meters),
     reference parameters (floor 150, ceiling 600), whole files and slices."""
