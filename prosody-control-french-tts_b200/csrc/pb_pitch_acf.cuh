@@ -554,8 +554,8 @@ pb_pitch_acf_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __restrict
 // (NP - 1 complex multiply-adds per lag instead of log2 NP radix-2 passes through shared memory).
 // The general kernel above runs these sizes as 32 x 32 x NP with NP warps sharing one buffer and a named barrier around every
 // pass; it stays for geometries whose window exceeds N/2 or whose lag range exceeds 1024.  Measured (599 k frames): NP = 2 3.94 ->
-// 3.24 ms (24 kHz), 3.86 -> 3.10 ms (22.05 kHz): the default at N = 2048.  NP = 4 8.08 -> 8.05 ms (44.1 kHz): two of its four
-// pipelines read each other's spectra and a pair takes five group barriers — no gain, so N = 4096 keeps the general kernel unless
+// 3.24 ms (24 kHz), 3.86 -> 3.10 ms (22.05 kHz): the default at N = 2048.  NP = 4 8.08 -> 7.89 ms (44.1 kHz): two of its four
+// pipelines read each other's spectra, the window is rotated four ways and a pair still takes four group barriers — 2 %, so N = 4096 keeps the general kernel unless
 // PB_ACF_SPLIT=4 asks for this one.
 // The power-of-two frame scales must be applied BEFORE the rotation by W^(nq), which mixes the two frames' components.
 template <int NP, int MINB>
@@ -826,8 +826,9 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
                     v[i] = make_float2(p.x * p.x + p.y * p.y, q.x * q.x + q.y * q.y);
                 }
             }
-            // every partner has been read before any buffer is written again (the stores of this step)
-            if (CROSS && step == 2) PB_KS_SYNC();
+            // every partner has been read before any buffer is written again (the stores of this step): only the pipelines that read
+            // each other's buffers meet (64 threads on a barrier of their own)
+            if (CROSS && step == 2 && !own_pair) PB_GROUP_SYNC(8 + group, 64);
             if (pass) {
                 const float2* tw = gm.tw_a + lane;
                 PB_UNROLL for (int t = 1; t < R; t++) {
@@ -841,8 +842,8 @@ pb_pitch_acf_split_kernel(const int16_t* __restrict__ pcm, const PbUnitDev* __re
             if (step == 3) break;                                     // the lags stay in registers
             if (pass) { float2* dst = buf + lane; PB_UNROLL for (int t = 0; t < R; t++) dst[t * 33] = v[pb_bitrev(t, LR)]; }
             else { float2* dst = buf + 33 * lane; PB_UNROLL for (int t = 0; t < R; t++) dst[t] = v[pb_bitrev(t, LR)]; }
-            // the first transform's spectrum is read across pipelines when NP > 2
-            if (NP > 2 && step == 1) PB_KS_SYNC(); else __syncwarp();
+            // the first transform's spectrum is read across pipelines when NP > 2 (by the cross-paired ones only)
+            if (NP > 2 && step == 1 && !own_pair) PB_GROUP_SYNC(8 + group, 64); else __syncwarp();
         }
         // local peaks over the group, back to unscaled units
         pkA = pb_warp_max(pkA); pkB = pb_warp_max(pkB);
