@@ -10,7 +10,8 @@ rules the reference's closures rely on.  Mirrors, on in-memory mono s16 PCM, the
 The arithmetic behind them lives in packages that are neither vendored in the reference nor installable
 here (praat-parselmouth 0.4.5 / Praat 6.1.38, pyloudnorm 0.1.x, pydub 0.25.1) and the reference ships no
 golden vectors, so this oracle restates their published algorithms and is pinned only by first-principles
-known-answer tests.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
+known-answer tests, by torchaudio's independent BS.1770 implementation (loudness) and by a second, independently written
+numpy / scipy restatement of the published pitch algorithm (tests/test_oracle_independent.py) — none of which is Praat.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
 import this module; the product never does.
 """
 from __future__ import annotations

@@ -7,7 +7,9 @@
  * None of these packages (nor any golden vector) is shipped with the reference or installable here,
  * so this file restates the PUBLISHED algorithms (Praat fon/Sound_to_Pitch.cpp, fon/Pitch.cpp,
  * melder/NUMinterpol.cpp, dwsys/NUM2.cpp, fon/Sampled.cpp, fon/Sound.cpp; pyloudnorm meter.py,
- * iirfilter.py) and is pinned only by first-principles known-answer tests (tests/test_oracle_*.py).
+ * iirfilter.py) and is pinned only by first-principles known-answer tests (tests/test_oracle_kat.py), by torchaudio's
+ * independent BS.1770 implementation for the loudness part (tests/test_oracle_vs_torchaudio.py) and by a second, independently
+ * written numpy / scipy restatement of the published pitch algorithm (tests/test_oracle_independent.py) — none of which is Praat.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library. The product (prosody-control-french-tts_b200/) never does.
