@@ -28,7 +28,6 @@ typedef cudaEvent_t pbEvent_t;
 
 #define PB_FULL_MASK 0xffffffffu
 
-
 // ---- NVTX ranges (header-only NVTX3: no library to link; a no-op unless a profiler is attached).  The reference has no tracing
 // at all; these mark the host phases and kernel groups of a batch call on an Nsight timeline.
 #ifdef PB_SIMT_EMU
