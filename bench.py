@@ -448,6 +448,34 @@ def bench_steps(args, rank, world, local):
 
 
 # ----------------------------------------------------------------------------------------------------------- c1: the repo clips, file level
+def frame_level_parity(ex, pcm, segs, pitch):
+    """north_star's tolerances are stated per FRAME (F0 within 0.5 % on frames voiced in both, voicing decisions agree on >= 99.5 % of
+    frames, intensity within 0.05 dB): every whole natural clip, frame by frame, against the oracle."""
+    import numpy as np
+    import prosody_b200 as pb
+    from oracle import oracle as O
+    items = [(s.nat_off, s.nat_nx, s.nat_sr, 0.0, None) for s in segs]
+    r = ex.median_pitch(pcm, pb.Units.from_list(items), pb.pitch_params(**pitch), frames=True)
+    n = agree = n_both = 0
+    rel, st_err, in_err = [], 0.0, 0.0
+    for i, s in enumerate(segs):
+        o = O.pitch_track(pcm[s.nat_off:s.nat_off + s.nat_nx], s.nat_sr, params=O.pitch_params(pitch["pitch_floor"], pitch["pitch_ceiling"]))
+        a, b = r["frame_off"][i], r["frame_off"][i + 1]
+        f, g = r["frame_f0"][a:b].astype(np.float64), o["frequency"]
+        n += len(g); agree += int(np.sum((f > 0) == (g > 0)))
+        both = (f > 0) & (g > 0); n_both += int(both.sum())
+        rel.append(np.abs(f[both] - g[both]) / g[both])
+        st_err = max(st_err, float(np.max(np.abs(r["frame_strength"][a:b] - o["strength"]))))
+        gi, oi = r["frame_intensity"][a:b].astype(np.float64), o["intensity"]
+        pos = (gi > 0) & (oi > 0)
+        if pos.any():
+            in_err = max(in_err, float(np.max(np.abs(20.0 * np.log10(gi[pos] / oi[pos])))))
+    rel = np.concatenate(rel) if rel else np.zeros(1)
+    return dict(frames=int(n), voicing_agreement=agree / max(1, n), voiced_in_both=int(n_both), f0_rel_err_p50=float(np.median(rel)),
+                f0_rel_err_p99=float(np.quantile(rel, 0.99)), f0_rel_err_max=float(rel.max()), frames_over_0p5_percent=int(np.sum(rel > 5e-3)),
+                strength_abs_err_max=st_err, frame_intensity_err_max_db=in_err)
+
+
 def bench_c1(args, rank, world, local):
     """BASELINE configs[0]: the ten repo clips through the file-level drop-in (WAV + TextGrid read from disk, three CSVs written),
     next to the oracle's loop-by-loop restatement of the reference step on the same files, plus the flip listing against it."""
@@ -491,6 +519,7 @@ def bench_c1(args, rank, world, local):
     # the reference step restated (oracle/flow.py), single Python thread like the reference's own loop
     t0 = time.perf_counter(); _, ref = G.run(root / "oracle_copy"); dt_cpu = time.perf_counter() - t0
     rep = column_report(out["sm_pitch"], ref["sm_p"])
+    frames = frame_level_parity(ex, pcm, segs, wl.pitch)
     pu = np.array([u["p_nat"] for u in ref["units"]]); got = out["syn"]["p_nat"]; both = (pu > 0) & (got > 0)
     line = dict(metric=METRIC, value=wl.audio_s * args.steps / dt_dev, unit="audio-s/s", n_gpus=1, steps=args.steps, warmup=max(3, args.warmup),
                 ms_per_step=1e3 * dt_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="reference clips + synthetic alignments",
@@ -500,7 +529,7 @@ def bench_c1(args, rank, world, local):
                 gpu_launches=int(o2["timings"]["n_launches"]),
                 kernels_ms_per_step={k: float(o2["timings"][k]) for k in ("frames_ms", "acf_ms", "cand_ms", "path_ms", "lufs_ms", "total_ms", "host_plan_ms")},
                 cpu_baseline=dict(value=wl.audio_s / dt_cpu, unit="audio-s/s", cores=1, kind="port", sample="the whole config: oracle/flow.py, one Python thread"),
-                parity=dict(pitch_strings=dict(rows=rep["rows"], identical=rep["identical"], flipped=rep["flipped"], max_abs_delta=rep["max_abs_delta"], listed=rep["listed"]),
+                parity=dict(frames=frames, pitch_strings=dict(rows=rep["rows"], identical=rep["identical"], flipped=rep["flipped"], max_abs_delta=rep["max_abs_delta"], listed=rep["listed"]),
                             rate_strings_flipped=column_report(out["sm_rate"], ref["sm_r"])["flipped"],
                             volume_strings_flipped=column_report(out["raw_volume"], [r["raw_volume"] for r in ref["raw_rows"]])["flipped"],
                             median_f0_rel_err_max=float(np.max(np.abs(got[both] - pu[both]) / pu[both])), voicing_mismatch_units=int(np.sum((pu > 0) != (got > 0))),

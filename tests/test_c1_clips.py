@@ -106,3 +106,23 @@ def test_c1_file_level_dropin_on_real_speech(tmp_path, gpu_extractor):
     print("C1 pitch strings:", {k: rep[k] for k in ("rows", "identical", "flipped", "max_abs_delta")}, rep["listed"][:5])
     assert rep["flipped"] <= 6, rep["listed"]                                 # documented rounding boundary: a few of 115 rows
     assert column_report(out["sm_rate"], vals["sm_rate"])["flipped"] == 0 and column_report(out["raw_volume"], [r["raw_volume"] for r in vals["raw_rows"]])["flipped"] == 0
+
+
+@pytest.mark.gpu
+def test_c1_frame_level_tolerances_on_real_speech(tmp_path, gpu_extractor):
+    """BASELINE north_star states its tolerances per FRAME: F0 within 0.5 % on frames voiced in both implementations, voicing
+    decisions agreeing on >= 99.5 % of frames, intensity within 0.05 dB.  Every frame of the reference's ten clips (44.1 kHz, floor
+    150 / ceiling 600: the reference's own parameters) against the oracle — and far inside those bars."""
+    sys.path.insert(0, str(GOLD.parent.parent))
+    import bench
+    import make_c1_fixture as C1
+    from prosody_b200 import pipeline as P
+    from prosody_b200 import step as S
+    v = C1.build_voice(tmp_path / "data")
+    pcm, segs = P.load_voice(v["voice_dir"] / "audio", v["raw_audio_dir"], v["textgrid_dir"])
+    rep = bench.frame_level_parity(gpu_extractor, pcm, segs, dict(S.REFERENCE_PITCH))
+    assert rep["frames"] > 30000 and rep["voiced_in_both"] > 5000      # floor 150 Hz: most of this speaker's frames are below it
+    assert rep["voicing_agreement"] >= 0.9999                 # north_star: 0.995
+    assert rep["frames_over_0p5_percent"] == 0 and rep["f0_rel_err_max"] < 5e-3
+    assert rep["f0_rel_err_p99"] < 2e-4 and rep["strength_abs_err_max"] < 2e-3
+    assert rep["frame_intensity_err_max_db"] < 0.01           # north_star: 0.05 dB
