@@ -438,6 +438,14 @@ def bench_steps(args, rank, world, local):
             cpu_baseline=dict(value=cpu["value"], unit="audio-s/s", cores=cpu["cores"], kind="port", sample=cpu["sample"], pitch_s=cpu["pitch_s"], lufs_s=cpu["lufs_s"],
                               single_core=dict(value=cpu1["value"], unit="audio-s/s", cores=1, audio_s=cpu1["audio_s"])),
             clocks=sampler.summary())
+        # north_star's per-frame tolerances on a bounded sample of this workload: the first 64 natural utterances, every frame, against
+        # the oracle (outside every timed region)
+        try:
+            line["parity"] = dict(frames=frame_level_parity(exs[0], host_pcm.numpy(), segs[:64], pitch),
+                                  sample="first 64 natural utterances of rank 0, whole files, every frame against the float64 oracle; bars: voicing "
+                                         "agreement >= 0.995, F0 within 5e-3 on frames voiced in both, intensity within 0.05 dB")
+        except Exception as e:          # noqa: BLE001  (the measurement stands without it)
+            line["parity"] = dict(error=repr(e))
         if world > 1 or strong:
             mean_b = sum(busy_dev) / len(busy_dev)
             line["ranks"] = dict(busy_s_resident=busy_dev, busy_s_e2e=busy_e2e, imbalance_resident=max(busy_dev) / mean_b if mean_b else None,
